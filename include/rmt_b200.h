@@ -1,0 +1,149 @@
+/* rmt_b200.h — C ABI of librmtb200.so, the B200-native engine behind PyREMOT's
+ * `rmtExe` for the pseudo-homogeneous packed-bed models N1 and N2.
+ *
+ * The reference is pure Python and has no FFI; the boundary it exposes for this
+ * path is (file:line relative to /root/reference/PyREMOT/)
+ *
+ *   rmtExe(modelInput)                                       rmt.py:21-80
+ *     -> rmtCoreClass.modExe -> N1Init / N2Init              docs/rmtCore.py:63-127, :393-413
+ *     -> PackedBedHomoReactorClass.runN1 / runN2             docs/pbHomoReactor.py:2694, :3319
+ *          setup of per-solve constants                      :2744-2852 / :3370-3507
+ *          solve_ivp(fun=modelEquationN1|N2, ...)            :2931 / :3609   <- hot loop
+ *          un-scaling sortResult4/5 + mole fractions         solvers/solResultAnalysis.py:191-301
+ *   reactionRateExe(loopVars, VARS, RATES)                   docs/rmtReaction.py:11-61
+ *
+ * A maintainer binds these entry points with `ctypes`;
+ * rmt_app_b200/capi.py is that binding.  Conventions:
+ *   - every function returns 0 on success, non-zero on error; the message is
+ *     available (per thread) from rmt_last_error();
+ *   - `d_*` arguments are DEVICE pointers owned by the caller (e.g. the
+ *     data_ptr() of a torch CUDA tensor), `h_*` / unprefixed arrays are host
+ *     memory; the library allocates only internal scratch, released by
+ *     rmt_module_free / rmt_shutdown;
+ *   - `stream` is a CUstream / cudaStream_t handle (NULL = default stream);
+ *     device-pointer entry points are asynchronous on it;
+ *   - a per-instance solver failure is reported in status[], never as a call
+ *     failure:  0 ok, 1 max_steps reached, 2 step size underflow, 3 non-finite
+ *     state (the Python reference raises on those);
+ *   - all arrays are FP64, structure-of-arrays, instance index fastest.
+ *
+ * There is no CPU fallback: without a CUDA driver rmt_init fails.
+ */
+#ifndef RMT_B200_H
+#define RMT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef uint64_t rmt_blob_t;     /* host-side compiled module image (cubin)   */
+typedef uint64_t rmt_module_t;   /* module loaded on the current device       */
+
+/* model description read back from a loaded module */
+typedef struct rmt_module_info {
+    int32_t model;        /* 1 = N1, 2 = N2                                    */
+    int32_t n;            /* unknowns per axial point                          */
+    int32_t nc;           /* species                                           */
+    int32_t nr;           /* reactions                                         */
+    int32_t nin;          /* primary input rows (rmt_setup)                    */
+    int32_t nconst;       /* derived constant rows                             */
+    int32_t nkp;          /* kinetic parameter slots                           */
+    int32_t stages;       /* Rosenbrock stages                                 */
+    int32_t block;        /* threads per block of the integrator               */
+    int32_t iso;          /* 1 = iso-thermal                                   */
+    int32_t flops_rhs_alg, flops_rhs_wt;     /* per RHS evaluation (per node)  */
+    int32_t flops_jac_alg, flops_jac_wt;     /* per RHS+Jacobian evaluation    */
+} rmt_module_info;
+
+const char* rmt_last_error(void);
+const char* rmt_version(void);
+
+/* Bind the calling thread to CUDA device `device` (primary context, shared with
+ * the CUDA runtime / PyTorch).  Fails when no driver or device is present. */
+int rmt_init(int device);
+int rmt_device_count(int* count);
+int rmt_shutdown(void);
+
+/* ---- code generation back end: NVRTC, sm_100a --------------------------------
+ * Replaces the reference's per-call `eval()` of Cp strings (docs/rmtThermo.py:37)
+ * and Python-lambda kinetics (docs/rmtReaction.py:44-58).  `model_src` is the
+ * generated "rmt_model.cuh", `kernels_src` the hand-written rmt_kernels.cu.
+ * Works without a GPU (used by the build check). */
+int rmt_nvrtc_compile(const char* model_src, const char* kernels_src, const char* arch,
+                      int block, const char* const* extra_opts, int n_extra_opts, rmt_blob_t* blob_out);
+int rmt_blob_data(rmt_blob_t blob, const void** data, size_t* size);
+const char* rmt_blob_log(rmt_blob_t blob);
+int rmt_blob_ptx(rmt_blob_t blob, const char** ptx, size_t* size);
+int rmt_blob_free(rmt_blob_t blob);
+
+int rmt_module_load(const void* cubin, size_t size, rmt_module_t* module_out);
+int rmt_module_get_info(rmt_module_t m, rmt_module_info* info);
+int rmt_module_free(rmt_module_t m);
+
+/* ---- per-solve constants: runN1 :2744-2852 / runN2 :3370-3507 ------------------
+ * d_rows [n_rows][B] holds the inputs that vary per instance; row_map[q] (q <
+ * nin) is the row of input q in d_rows or -1, in which case uniform[q] is used
+ * for every instance.  Input order: temperature, pressure, concentration[nc],
+ * volumetric-flowrate, ReInDi, ReLe, PaDi, BeVoFr, OvHeTrCo, MeTe, then the
+ * scalar VARS entries in VARS order.  d_consts [nconst][B]. */
+int rmt_setup(rmt_module_t m, int64_t B, const double* d_rows, int32_t n_rows, const int32_t* row_map,
+              const double* uniform, double* d_consts, void* stream);
+
+/* ---- N1: modelEquationN1 (:3017-3314) ------------------------------------------
+ * d_y, d_f [n][B];  d_J [n*n][B] with d f_r / d y_c at row r*n + c. */
+int rmt_n1_rhs(rmt_module_t m, int64_t B, const double* d_consts, const double* d_y, double* d_f, void* stream);
+int rmt_n1_jac(rmt_module_t m, int64_t B, const double* d_consts, const double* d_y, double* d_f, double* d_J,
+               void* stream);
+
+/* ---- N1: solve_ivp call of runN1 (:2931) + post-processing (:2949-2983) ---------
+ * z_eval[n_eval] (host): increasing output positions in [0, 1], the last one is
+ * the end of the integration (the reference uses linspace(0, 1, 101)).
+ * out_mode 0: raw scaled states (sol.y), rows = n;  1: dataYs rows (y_i, P [Pa],
+ * T [K]), rows = n;  2: everything runN1 packs, rows = 2n + nc: raw | C_i
+ * [mol/m^3] (dataYCons2) | dataYs rows.
+ * dense 1: Rosenbrock dense output at z_eval;  0: steps land on every z_eval.
+ * d_out [n_eval][rows][B], d_status [B], d_stats [4][B] = accepted steps, rejected
+ * steps, RHS evaluations, Jacobian(+RHS) evaluations.
+ * obj_ref (host, [n], may be NULL) + d_obj [B]: fused least-squares objective of
+ * the outlet against obj_ref (parameter-estimation populations). */
+int rmt_n1_solve(rmt_module_t m, int64_t B, const double* d_consts, int32_t n_eval, const double* z_eval,
+                 double rtol, double atol, int32_t max_steps, int32_t dense, int32_t out_mode,
+                 double* d_out, int32_t* d_status, int32_t* d_stats,
+                 const double* obj_ref, double* d_obj, void* stream);
+
+/* Same path with HOST buffers: copies inputs in, runs setup + solve, copies
+ * results back, synchronises.  h_rows [n_rows][B], h_out [n_eval][rows][B]. */
+int rmt_n1_solve_host(rmt_module_t m, int64_t B, const double* h_rows, int32_t n_rows, const int32_t* row_map,
+                      const double* uniform, int32_t n_eval, const double* z_eval,
+                      double rtol, double atol, int32_t max_steps, int32_t dense, int32_t out_mode,
+                      double* h_out, int32_t* h_status, int32_t* h_stats,
+                      const double* obj_ref, double* h_obj);
+
+/* ---- N2: modelEquationN2 (:3706-4134) and the slab loop of runN2 (:3589-3685) ---
+ * States are variable-major like the reference's reshape (:3873): d_y, d_f
+ * [n][zNo][B].  rmt_n2_solve integrates t in [0, period] and writes the state at
+ * the end of each of the tNo slabs: d_out [tNo][n][zNo][B] (out_mode as above,
+ * mode 1 rows = y_i, T [K]).  d_work is caller-provided scratch of
+ * rmt_n2_work_doubles(m, B, zNo) doubles. */
+int rmt_n2_rhs(rmt_module_t m, int64_t B, int32_t zNo, const double* d_consts, const double* d_y, double* d_f,
+               void* stream);
+int64_t rmt_n2_work_doubles(rmt_module_t m, int64_t B, int32_t zNo);
+int rmt_n2_solve(rmt_module_t m, int64_t B, int32_t zNo, int32_t tNo, double period, const double* d_consts,
+                 double rtol, double atol, int32_t max_steps, int32_t out_mode,
+                 double* d_out, int32_t* d_status, int32_t* d_stats, double* d_work, void* stream);
+
+/* ---- ensemble reductions (per GPU; the cross-GPU step is an NCCL all-reduce of
+ * these three numbers, done by the caller's torch.distributed group) ------------- */
+int rmt_reduce_objective(rmt_module_t m, int64_t n, const double* d_obj, int64_t index_offset,
+                         double* h_sum, double* h_min, int64_t* h_argmin, void* stream);
+
+/* ---- measurement helper: FP64 FMA throughput of the device (TFLOP/s) ------------ */
+int rmt_fp64_peak(rmt_module_t m, int32_t iters, int32_t repeats, double* tflops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RMT_B200_H */

@@ -1,0 +1,257 @@
+"""Code generator: ModelSpec -> `rmt_model.cuh`.
+
+The generated header is the model-specific half of the NVRTC translation
+unit; the hand-written half (`csrc/rmt_kernels.cu`) `#include`s it.  It holds
+
+* compile-time sizes (species, reactions, unknowns, kinetic-parameter slots),
+* component / reaction literals from the component table,
+* `rmt_rates()`      — the traced RATES as straight-line FP64 device code,
+* `rmt_rates_jac()`  — the same plus dR_j/d{T, P, y_i, C_i} from symbolic
+  differentiation of the traced DAG (shared sub-expressions emitted once),
+* the Rosenbrock tableau as constexpr arrays,
+* per-evaluation flop counts recomputed from the DAG.
+
+Expression printing keeps Python's evaluation order; `x**k` / `math.pow(x,k)`
+with small integer k becomes repeated multiplication (<= 1 ulp from the
+correctly-rounded libm pow the reference calls), everything else maps to the
+CUDA double-precision math library.
+"""
+from .expr import Graph
+from .tableau import TABLEAUX
+
+_CFUN = {
+    "exp": "exp", "log": "log", "log10": "log10", "log2": "log2", "sqrt": "sqrt", "exp10": "exp10",
+    "abs": "fabs", "sin": "sin", "cos": "cos", "tan": "tan", "tanh": "tanh", "sinh": "sinh", "cosh": "cosh",
+    "atan": "atan", "asin": "asin", "acos": "acos", "expm1": "expm1", "log1p": "log1p", "cbrt": "cbrt",
+    "pow": "pow", "min": "fmin", "max": "fmax", "atan2": "atan2",
+}
+_INFIX = {"add": "+", "sub": "-", "mul": "*", "div": "/"}
+
+
+def lit(v):
+    v = float(v)
+    if v != v:
+        return "(0.0/0.0)"
+    if v in (float("inf"), float("-inf")):
+        return "(%s1.0/0.0)" % ("-" if v < 0 else "")
+    s = repr(v)
+    if "e" not in s and "." not in s:
+        s += ".0"
+    return s
+
+
+def _powi_expr(a, k):
+    if k == 0:
+        return "1.0"
+    neg = k < 0
+    k = abs(k)
+    if k > 16:
+        return "pow(%s, %s)" % (a, lit(-k if neg else k))
+    # square-and-multiply over a fully parenthesised chain
+    e = "*".join([a]*k) if k <= 3 else None
+    if e is None:
+        half = _powi_expr(a, k//2)
+        e = "((%s)*(%s)%s)" % (half, half, "*" + a if k % 2 else "")
+    return "(1.0/(%s))" % e if neg else "(%s)" % e
+
+
+def emit_dag(g: Graph, outs, in_name, indent="    "):
+    """Return (lines, refs): C statements computing every node reachable from
+    `outs`, and the C expression naming each requested output."""
+    lines = []
+    name = {}
+    for n in g.topo([o for o in outs if o is not None]):
+        if n.op == "const":
+            name[n.id] = lit(n.value)
+            if n.value < 0:
+                name[n.id] = "(" + name[n.id] + ")"
+        elif n.op == "in":
+            name[n.id] = in_name(n.name)
+        else:
+            a = [name[x.id] for x in n.args]
+            if n.op in _INFIX:
+                e = "%s %s %s" % (a[0], _INFIX[n.op], a[1])
+            elif n.op == "neg":
+                e = "-%s" % a[0]
+            elif n.op == "powi":
+                e = _powi_expr(a[0], n.value)
+            else:
+                e = "%s(%s)" % (_CFUN[n.op], ", ".join(a))
+            v = "t%d" % n.id
+            lines.append("%sconst double %s = %s;" % (indent, v, e))
+            name[n.id] = v
+    return lines, [name[o.id] if o is not None else "0.0" for o in outs]
+
+
+def _arr(vals, fmt=lit):
+    return "{" + ", ".join(fmt(v) for v in vals) + "}"
+
+
+def _arr2(rows, fmt=lit):
+    return "{" + ", ".join(_arr(r, fmt) for r in rows) + "}"
+
+
+def balance_flops(spec):
+    """Operation count of the hand-written balance code in csrc/rmt_kernels.cu
+    (`rmt_point` + `n1_eval` / the N2 node body), excluding the traced rates.
+    Returns dict(rhs=(alg, weighted), jac=(alg, weighted)); the Jacobian count is
+    for one evaluation of f AND its full n x n Jacobian.  Divisions weigh 10."""
+    nc, nr = spec.nc, spec.nr
+    nnz = int((spec.nu != 0).sum())
+    energy = 0 if spec.iso else 1
+    # un-scale, fractions, MW, EOS density
+    mul_add = nc + 3 + nc + 2*nc + 1 + 1
+    div = nc + 2
+    # formation rates, Cp polynomials + means + mixture, heats of reaction
+    mul_add += 2*nnz + 2 + 8*nc + 2*nc + energy*(8*nr + 2*nr + 1 + 3)
+    if spec.model == "N1":
+        mul_add += 3 + 7 + nc + energy*6      # velocities, Ergun, balances
+        div += 5 + 1 + 1 + nc + energy*3
+    else:
+        mul_add += 7 + 4*nc + 3 + energy*12   # Ergun march, upwind convection, balances
+        div += 1 + nc + 2 + energy*4
+    rhs = (mul_add + div, mul_add + 10*div)
+    n = spec.n if spec.model == "N1" else spec.n
+    percol_ma = 10 + 2*nr + 2*nnz + 2*nc + energy*(4*nr + 10)
+    percol_div = 2 + energy*3
+    jma = mul_add + 2*nr*nc + 6*nc + 6*nr + n*percol_ma
+    jdiv = div + 1 + n*percol_div
+    return {"rhs": rhs, "jac": (jma + jdiv, jma + 10*jdiv)}
+
+
+def model_flops(spec):
+    """Per-axial-point flop counts: traced rates + balance."""
+    k = spec.kin.flops()
+    b = balance_flops(spec)
+    return {
+        "rates_alg": k["rates_alg"], "rates_weighted": k["rates_weighted"],
+        "rates_jac_alg": k["rates_jac_alg"], "rates_jac_weighted": k["rates_jac_weighted"],
+        "rhs_alg": k["rates_alg"] + b["rhs"][0], "rhs_weighted": k["rates_weighted"] + b["rhs"][1],
+        "jac_alg": k["rates_jac_alg"] + b["jac"][0], "jac_weighted": k["rates_jac_weighted"] + b["jac"][1],
+    }
+
+
+def generate_model_header(spec, tableau="rodas4"):
+    kin, g = spec.kin, spec.kin.g
+    nc, nr, nkp = spec.nc, spec.nr, spec.nkp
+
+    def in_name(nm):
+        if nm in ("T", "P"):
+            return nm
+        if nm[0] == "y":
+            return "y[%s]" % nm[1:]
+        if nm[0] == "C":
+            return "C[%s]" % nm[1:]
+        if nm.startswith("kp"):
+            return "kp[%s]" % nm[2:]
+        raise KeyError(nm)
+
+    L = []
+    A = L.append
+    A("// generated by rmt_app_b200.codegen — do not edit")
+    A("// model %s, components %s, %s" % (spec.model, ",".join(spec.compList), "iso-thermal" if spec.iso else "non-iso-thermal"))
+    for j, r in enumerate(spec.reactions):
+        A("// reaction %d: %s   rate: RATES[%r]" % (j, r, kin.rate_names[j]))
+    A("#pragma once")
+    A("#define RMT_MODEL_%s 1" % spec.model)
+    A("#define RMT_NC %d" % nc)
+    A("#define RMT_NR %d" % nr)
+    A("#define RMT_NKP %d" % nkp)
+    A("#define RMT_ISO %d" % (1 if spec.iso else 0))
+    A("#define RMT_NIN %d" % spec.nin)
+    for k, nm in enumerate(kin.param_names):
+        A("// kinetic parameter slot %d = VARS[%r] (default %r)" % (k, nm, kin.param_defaults[k]))
+
+    # which inputs do the rates depend on (lets the balance code skip zero blocks)
+    P = kin.partials
+    dep = {
+        "T": any(d is not None for d in P["T"]),
+        "P": any(d is not None for d in P["P"]),
+        "Y": any(d is not None for i in range(nc) for d in P["y%d" % i]),
+        "C": any(d is not None for i in range(nc) for d in P["C%d" % i]),
+    }
+    for k, v in dep.items():
+        A("#define RMT_RATES_DEP_%s %d" % (k, 1 if v else 0))
+
+    fl = model_flops(spec)
+    A("// flops per evaluation at one axial point, recomputed from the traced DAG + the balance code")
+    A("// (ALG: 1 per +,-,*,/,sqrt,exp,log,pow;  WT: FP64-instruction weighted, see expr.FLOP_WEIGHT)")
+    A("#define RMT_FLOPS_RHS_ALG %d" % fl["rhs_alg"])
+    A("#define RMT_FLOPS_RHS_WT %d" % fl["rhs_weighted"])
+    A("#define RMT_FLOPS_JAC_ALG %d" % fl["jac_alg"])
+    A("#define RMT_FLOPS_JAC_WT %d" % fl["jac_weighted"])
+    A("#define RMT_FLOPS_RATES_ALG %d" % fl["rates_alg"])
+    A("#define RMT_FLOPS_RATES_WT %d" % fl["rates_weighted"])
+    A("#define RMT_FLOPS_RATESJAC_ALG %d" % fl["rates_jac_alg"])
+    A("#define RMT_FLOPS_RATESJAC_WT %d" % fl["rates_jac_weighted"])
+    A("")
+    A("// component table rows in compList order (PyREMOT/data/componentData.py)")
+    comps = spec.components
+    A("__device__ constexpr double RMT_MW[RMT_NC] = %s;" % _arr([c.MW for c in comps]))
+    A("__device__ constexpr double RMT_CP[RMT_NC][4] = %s;" % _arr2([c.cp for c in comps]))
+    from .componentdb import Tref
+    A("__device__ constexpr double RMT_CPREF[RMT_NC] = %s;  // Cp_i(Tref)" % _arr([c.cp_at(Tref) for c in comps]))
+    A("__device__ constexpr int RMT_VISC_EQ[RMT_NC] = %s;" % _arr([c.visc_eq for c in comps], fmt=lambda v: str(int(v))))
+    A("__device__ constexpr double RMT_VISC[RMT_NC][4] = %s;" % _arr2([c.visc for c in comps]))
+    A("// stoichiometry nu[j][i], standard heats of reaction [J/mol], dCp_j(T) cubic")
+    A("__device__ constexpr double RMT_NU[RMT_NR][RMT_NC] = %s;" % _arr2(spec.nu))
+    A("__device__ constexpr double RMT_DH25[RMT_NR] = %s;" % _arr(spec.dH25))
+    A("__device__ constexpr double RMT_DCP[RMT_NR][4] = %s;" % _arr2(spec.dcp))
+    A("")
+
+    # ---- rates -----------------------------------------------------------------
+    A("// traced RATES (rmtReaction.py:11-61 semantics): R[j] in mol/(m^3 s)")
+    A("__device__ __forceinline__ void rmt_rates(const double T, const double P, const double (&y)[RMT_NC],")
+    A("        const double (&C)[RMT_NC], const double* __restrict__ kp, double (&R)[RMT_NR])")
+    A("{")
+    lines, refs = emit_dag(g, kin.rates, in_name)
+    L.extend(lines)
+    for j, r in enumerate(refs):
+        A("    R[%d] = %s;" % (j, r))
+    A("}")
+    A("")
+    A("// rates + partial derivatives (symbolic differentiation of the same DAG)")
+    A("__device__ __forceinline__ void rmt_rates_jac(const double T, const double P, const double (&y)[RMT_NC],")
+    A("        const double (&C)[RMT_NC], const double* __restrict__ kp, double (&R)[RMT_NR],")
+    A("        double (&dRdT)[RMT_NR], double (&dRdP)[RMT_NR], double (&dRdy)[RMT_NR][RMT_NC], double (&dRdC)[RMT_NR][RMT_NC])")
+    A("{")
+    outs = list(kin.rates) + list(P["T"]) + list(P["P"])
+    for i in range(nc):
+        outs += list(P["y%d" % i])
+    for i in range(nc):
+        outs += list(P["C%d" % i])
+    lines, refs = emit_dag(g, outs, in_name)
+    L.extend(lines)
+    it = iter(refs)
+    for j in range(nr):
+        A("    R[%d] = %s;" % (j, next(it)))
+    for j in range(nr):
+        A("    dRdT[%d] = %s;" % (j, next(it)))
+    for j in range(nr):
+        A("    dRdP[%d] = %s;" % (j, next(it)))
+    for i in range(nc):
+        for j in range(nr):
+            A("    dRdy[%d][%d] = %s;" % (j, i, next(it)))
+    for i in range(nc):
+        for j in range(nr):
+            A("    dRdC[%d][%d] = %s;" % (j, i, next(it)))
+    A("}")
+    A("")
+
+    # ---- Rosenbrock tableau ------------------------------------------------------
+    tab = TABLEAUX[tableau]
+    s = tab["stages"]
+
+    def full(rows):
+        return [[(rows[i][j] if j < len(rows[i]) else 0.0) for j in range(s)] for i in range(s)]
+    A("// Rosenbrock tableau: %s (rmt_app_b200/tableau.py)" % tab["name"])
+    A("#define RMT_ROS_S %d" % s)
+    A("#define RMT_ROS_ORDER %d" % tab["order"])
+    A("__device__ constexpr double RMT_ROS_GAMMA = %s;" % lit(tab["gamma"]))
+    A("__device__ constexpr double RMT_ROS_A[RMT_ROS_S][RMT_ROS_S] = %s;" % _arr2(full(tab["a"])))
+    A("__device__ constexpr double RMT_ROS_C[RMT_ROS_S][RMT_ROS_S] = %s;" % _arr2(full(tab["c"])))
+    A("__device__ constexpr double RMT_ROS_M[RMT_ROS_S] = %s;" % _arr(tab["m"]))
+    A("__device__ constexpr double RMT_ROS_E[RMT_ROS_S] = %s;" % _arr(tab["e"]))
+    A("__device__ constexpr double RMT_ROS_D[2][RMT_ROS_S] = %s;" % _arr2(tab["dense"]))
+    A("")
+    return "\n".join(L) + "\n"

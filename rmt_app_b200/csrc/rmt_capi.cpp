@@ -1,0 +1,656 @@
+// rmt_capi.cpp — host side of librmtb200.so (C ABI declared in include/rmt_b200.h).
+//
+// NVRTC compiles the generated model header + the hand-written kernels for
+// sm_100a; the CUDA driver API (dlopen'ed, so that the library loads — and the
+// code generator back end works — on a machine without a GPU) loads the cubin
+// into the device's primary context and launches the kernels on the caller's
+// stream.  There is no CPU implementation of any compute entry point.
+#include "../../include/rmt_b200.h"
+
+#include <cuda.h>
+#include <nvrtc.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const char* fmt, ...)
+{
+    char buf[4096];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return 1;
+}
+
+// ---- driver API through dlopen ----------------------------------------------------
+#define RMT_STR2(x) #x
+#define RMT_STR(x) RMT_STR2(x)
+#define RMT_DRIVER_FUNCS(X) \
+    X(cuInit) X(cuDeviceGetCount) X(cuDeviceGet) X(cuDevicePrimaryCtxRetain) X(cuCtxSetCurrent) \
+    X(cuDeviceGetAttribute) X(cuModuleLoadDataEx) X(cuModuleUnload) X(cuModuleGetFunction) \
+    X(cuLaunchKernel) X(cuMemAlloc) X(cuMemFree) X(cuMemcpyHtoDAsync) \
+    X(cuMemcpyDtoHAsync) X(cuMemcpyDtoH) X(cuMemsetD8Async) X(cuStreamSynchronize) X(cuFuncSetAttribute) \
+    X(cuOccupancyMaxActiveBlocksPerMultiprocessor) X(cuGetErrorString) X(cuEventCreate) X(cuEventRecord) \
+    X(cuEventSynchronize) X(cuEventElapsedTime) X(cuEventDestroy) X(cuMemAllocHost) X(cuMemFreeHost) \
+    X(cuCtxSynchronize)
+
+struct Driver {
+    void* lib = nullptr;
+#define X(name) decltype(&name) p_##name = nullptr;
+    RMT_DRIVER_FUNCS(X)
+#undef X
+} drv;
+
+std::mutex g_mu;
+bool g_driver_ok = false;
+int g_device = -1;
+CUcontext g_ctx = nullptr;
+int g_sm_count = 0;
+
+int load_driver()
+{
+    if (g_driver_ok) return 0;
+    drv.lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (!drv.lib)
+        return fail("rmt_init: cannot load the CUDA driver (libcuda.so.1): %s — this library has no CPU fallback",
+                    dlerror());
+#define X(name)                                                                                  \
+    drv.p_##name = (decltype(&name))dlsym(drv.lib, RMT_STR(name));                               \
+    if (!drv.p_##name) return fail("rmt_init: CUDA driver lacks symbol %s", RMT_STR(name));
+    RMT_DRIVER_FUNCS(X)
+#undef X
+    g_driver_ok = true;
+    return 0;
+}
+
+int cu_fail(CUresult r, const char* what)
+{
+    const char* s = nullptr;
+    if (drv.p_cuGetErrorString) drv.p_cuGetErrorString(r, &s);
+    return fail("%s failed: CUDA error %d (%s)", what, (int)r, s ? s : "?");
+}
+#define CU(call)                                                  \
+    do {                                                          \
+        CUresult r_ = drv.p_##call;                               \
+        if (r_ != CUDA_SUCCESS) return cu_fail(r_, #call);        \
+    } while (0)
+
+int ensure_ctx()
+{
+    if (!g_driver_ok || !g_ctx) return fail("rmt_init(device) has not been called (no CUDA context)");
+    CU(cuCtxSetCurrent(g_ctx));
+    return 0;
+}
+
+// ---- blobs and modules ------------------------------------------------------------
+struct Blob {
+    std::vector<char> cubin;
+    std::string ptx, log;
+};
+
+struct Scratch {           // per-launch device scratch: queue counter + z_eval + obj_ref
+    CUdeviceptr p = 0;
+    size_t bytes = 0;
+};
+
+struct Module {
+    CUmodule mod = nullptr;
+    rmt_module_info info{};
+    CUfunction f_setup = nullptr, f_n1_rhs = nullptr, f_n1_jac = nullptr, f_n1_solve = nullptr;
+    CUfunction f_n2_rhs = nullptr, f_n2_solve = nullptr, f_reduce = nullptr, f_peak = nullptr;
+    int solve_blocks_per_sm = 0;
+    size_t solve_smem = 0;
+    Scratch ring[8];
+    int ring_next = 0;
+    // grow-only workspaces of the *_host entry points and the reductions
+    CUdeviceptr ws[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    size_t ws_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+std::map<uint64_t, Blob*> g_blobs;
+std::map<uint64_t, Module*> g_modules;
+uint64_t g_next_id = 1;
+
+Blob* get_blob(rmt_blob_t b)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_blobs.find(b);
+    return it == g_blobs.end() ? nullptr : it->second;
+}
+Module* get_module(rmt_module_t m)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_modules.find(m);
+    return it == g_modules.end() ? nullptr : it->second;
+}
+
+int ws_reserve(Module* M, int slot, size_t bytes, CUdeviceptr* out)
+{
+    if (M->ws_bytes[slot] < bytes) {
+        if (M->ws[slot]) { CU(cuCtxSynchronize()); CU(cuMemFree(M->ws[slot])); M->ws[slot] = 0; M->ws_bytes[slot] = 0; }
+        size_t want = bytes + bytes/8 + 256;
+        CU(cuMemAlloc(&M->ws[slot], want));
+        M->ws_bytes[slot] = want;
+    }
+    *out = M->ws[slot];
+    return 0;
+}
+
+int scratch_get(Module* M, size_t bytes, CUdeviceptr* out)
+{
+    Scratch& s = M->ring[M->ring_next];
+    M->ring_next = (M->ring_next + 1) % 8;
+    if (s.bytes < bytes) {
+        if (s.p) { CU(cuCtxSynchronize()); CU(cuMemFree(s.p)); s.p = 0; s.bytes = 0; }
+        size_t want = std::max<size_t>(bytes, 64*1024);
+        CU(cuMemAlloc(&s.p, want));
+        s.bytes = want;
+    }
+    *out = s.p;
+    return 0;
+}
+
+// kernel-parameter mirrors of the device structs in rmt_kernels.cu ---------------------
+struct SolveArgsN1 {
+    CUdeviceptr consts;
+    long long B;
+    CUdeviceptr z_eval;
+    int n_eval;
+    int out_mode;
+    double rtol, atol;
+    int max_steps;
+    int dense;
+    CUdeviceptr out, status, stats, queue, obj_ref, obj;
+};
+static_assert(sizeof(SolveArgsN1) == 104, "SolveArgs layout");
+
+struct SolveArgsN2 {
+    CUdeviceptr consts;
+    long long B;
+    int zNo, tNo;
+    double period;
+    double rtol, atol;
+    int max_steps;
+    int out_mode;
+    CUdeviceptr out, status, stats, work, queue;
+};
+static_assert(sizeof(SolveArgsN2) == 96, "SolveArgsN2 layout");
+
+// RmtInputs { const double* rows; i64 B; int map[NIN]; double u[NIN]; }
+std::vector<char> pack_inputs(const Module* M, CUdeviceptr rows, long long B, const int32_t* map, const double* u)
+{
+    const int nin = M->info.nin;
+    size_t off_u = 16 + ((4*(size_t)nin + 7)/8)*8;
+    std::vector<char> buf(off_u + 8*(size_t)nin, 0);
+    memcpy(&buf[0], &rows, 8);
+    memcpy(&buf[8], &B, 8);
+    memcpy(&buf[16], map, 4*(size_t)nin);
+    memcpy(&buf[off_u], u, 8*(size_t)nin);
+    return buf;
+}
+
+int check_rows(const Module* M, int32_t n_rows, const int32_t* row_map, const double* uniform, const void* rows)
+{
+    if (!row_map || !uniform) return fail("rmt_setup: row_map and uniform must not be NULL");
+    for (int q = 0; q < M->info.nin; ++q) {
+        if (row_map[q] >= n_rows) return fail("rmt_setup: row_map[%d]=%d but only %d rows were passed", q, row_map[q], n_rows);
+        if (row_map[q] >= 0 && !rows) return fail("rmt_setup: row_map[%d]=%d but rows is NULL", q, row_map[q]);
+    }
+    return 0;
+}
+
+int launch(CUfunction f, unsigned grid, unsigned block, size_t smem, CUstream st, void** params, const char* name)
+{
+    if (!f) return fail("%s: kernel not present in this module (compiled for the other model?)", name);
+    CUresult r = drv.p_cuLaunchKernel(f, grid, 1, 1, block, 1, 1, (unsigned)smem, st, params, nullptr);
+    if (r != CUDA_SUCCESS) return cu_fail(r, name);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rmt_last_error(void) { return g_err.c_str(); }
+const char* rmt_version(void) { return "rmt_app_b200 0.1 (sm_100a, NVRTC)"; }
+
+int rmt_init(int device)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (load_driver()) return 1;
+    CUresult r = drv.p_cuInit(0);
+    if (r != CUDA_SUCCESS) return cu_fail(r, "cuInit");
+    int n = 0;
+    CU(cuDeviceGetCount(&n));
+    if (device < 0 || device >= n) return fail("rmt_init: device %d out of range (%d CUDA devices)", device, n);
+    if (g_ctx && g_device == device) { CU(cuCtxSetCurrent(g_ctx)); return 0; }
+    if (g_ctx && g_device != device)
+        return fail("rmt_init: this process is already bound to device %d (one process per GPU)", g_device);
+    CUdevice dev;
+    CU(cuDeviceGet(&dev, device));
+    CU(cuDevicePrimaryCtxRetain(&g_ctx, dev));
+    CU(cuCtxSetCurrent(g_ctx));
+    CU(cuDeviceGetAttribute(&g_sm_count, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, dev));
+    g_device = device;
+    return 0;
+}
+
+int rmt_device_count(int* count)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (load_driver()) return 1;
+    CUresult r = drv.p_cuInit(0);
+    if (r != CUDA_SUCCESS) return cu_fail(r, "cuInit");
+    CU(cuDeviceGetCount(count));
+    return 0;
+}
+
+int rmt_shutdown(void)
+{
+    std::vector<uint64_t> ids;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        for (auto& kv : g_modules) ids.push_back(kv.first);
+    }
+    for (uint64_t id : ids) rmt_module_free(id);
+    return 0;
+}
+
+// ---- NVRTC ---------------------------------------------------------------------------
+int rmt_nvrtc_compile(const char* model_src, const char* kernels_src, const char* arch, int block,
+                      const char* const* extra_opts, int n_extra_opts, rmt_blob_t* blob_out)
+{
+    if (!model_src || !kernels_src || !blob_out) return fail("rmt_nvrtc_compile: NULL argument");
+    nvrtcProgram prog;
+    const char* hdr_src[1] = {model_src};
+    const char* hdr_name[1] = {"rmt_model.cuh"};
+    nvrtcResult r = nvrtcCreateProgram(&prog, kernels_src, "rmt_kernels.cu", 1, hdr_src, hdr_name);
+    if (r != NVRTC_SUCCESS) return fail("nvrtcCreateProgram: %s", nvrtcGetErrorString(r));
+    std::string a = std::string("--gpu-architecture=") + (arch && *arch ? arch : "sm_100a");
+    std::string b = "-DRMT_BLOCK=" + std::to_string(block > 0 ? block : 128);
+    std::vector<const char*> opts = {a.c_str(), b.c_str(), "--std=c++17", "-lineinfo", "--fmad=true",
+                                     "-default-device"};
+    opts.pop_back();   // "-default-device" is not wanted: all device code is annotated explicitly
+    for (int i = 0; i < n_extra_opts; ++i) opts.push_back(extra_opts[i]);
+    r = nvrtcCompileProgram(prog, (int)opts.size(), opts.data());
+    Blob* B = new Blob;
+    size_t n = 0;
+    nvrtcGetProgramLogSize(prog, &n);
+    if (n > 1) { B->log.resize(n); nvrtcGetProgramLog(prog, &B->log[0]); }
+    if (r != NVRTC_SUCCESS) {
+        fail("NVRTC compilation failed (%s):\n%s", nvrtcGetErrorString(r), B->log.c_str());
+        delete B;
+        nvrtcDestroyProgram(&prog);
+        return 1;
+    }
+    if (nvrtcGetCUBINSize(prog, &n) != NVRTC_SUCCESS || n == 0) {
+        fail("NVRTC produced no cubin for %s (need a real architecture, e.g. sm_100a)", a.c_str());
+        delete B;
+        nvrtcDestroyProgram(&prog);
+        return 1;
+    }
+    B->cubin.resize(n);
+    nvrtcGetCUBIN(prog, B->cubin.data());
+    if (nvrtcGetPTXSize(prog, &n) == NVRTC_SUCCESS && n > 1) { B->ptx.resize(n); nvrtcGetPTX(prog, &B->ptx[0]); }
+    nvrtcDestroyProgram(&prog);
+    std::lock_guard<std::mutex> lk(g_mu);
+    uint64_t id = g_next_id++;
+    g_blobs[id] = B;
+    *blob_out = id;
+    return 0;
+}
+
+int rmt_blob_data(rmt_blob_t blob, const void** data, size_t* size)
+{
+    Blob* B = get_blob(blob);
+    if (!B) return fail("invalid blob handle");
+    *data = B->cubin.data();
+    *size = B->cubin.size();
+    return 0;
+}
+
+const char* rmt_blob_log(rmt_blob_t blob)
+{
+    Blob* B = get_blob(blob);
+    return B ? B->log.c_str() : "";
+}
+
+int rmt_blob_ptx(rmt_blob_t blob, const char** ptx, size_t* size)
+{
+    Blob* B = get_blob(blob);
+    if (!B) return fail("invalid blob handle");
+    *ptx = B->ptx.c_str();
+    *size = B->ptx.size();
+    return 0;
+}
+
+int rmt_blob_free(rmt_blob_t blob)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_blobs.find(blob);
+    if (it == g_blobs.end()) return fail("invalid blob handle");
+    delete it->second;
+    g_blobs.erase(it);
+    return 0;
+}
+
+// ---- modules -------------------------------------------------------------------------
+int rmt_module_load(const void* cubin, size_t size, rmt_module_t* module_out)
+{
+    if (ensure_ctx()) return 1;
+    if (!cubin || !size) return fail("rmt_module_load: empty image");
+    Module* M = new Module;
+    CUresult r = drv.p_cuModuleLoadDataEx(&M->mod, cubin, 0, nullptr, nullptr);
+    if (r != CUDA_SUCCESS) { delete M; return cu_fail(r, "cuModuleLoadDataEx"); }
+    int32_t mv[16] = {0};
+    {
+        CUfunction fm = nullptr;
+        CUdeviceptr dmeta = 0;
+        if (drv.p_cuModuleGetFunction(&fm, M->mod, "rmt_meta") != CUDA_SUCCESS || !fm) {
+            drv.p_cuModuleUnload(M->mod); delete M; return fail("module has no rmt_meta kernel (not an rmt_app_b200 image)");
+        }
+        r = drv.p_cuMemAlloc(&dmeta, sizeof mv);
+        if (r != CUDA_SUCCESS) { drv.p_cuModuleUnload(M->mod); delete M; return cu_fail(r, "cuMemAlloc"); }
+        void* params[] = {&dmeta};
+        r = drv.p_cuLaunchKernel(fm, 1, 1, 1, 32, 1, 1, 0, nullptr, params, nullptr);
+        if (r == CUDA_SUCCESS) r = drv.p_cuMemcpyDtoH(mv, dmeta, sizeof mv);
+        drv.p_cuMemFree(dmeta);
+        if (r != CUDA_SUCCESS) { drv.p_cuModuleUnload(M->mod); delete M; return cu_fail(r, "rmt_meta"); }
+    }
+    rmt_module_info& I = M->info;
+    I.model = mv[0]; I.n = mv[1]; I.nc = mv[2]; I.nr = mv[3]; I.nin = mv[4]; I.nconst = mv[5]; I.nkp = mv[6];
+    I.stages = mv[7]; I.block = mv[8]; I.iso = mv[9];
+    I.flops_rhs_alg = mv[10]; I.flops_rhs_wt = mv[11]; I.flops_jac_alg = mv[12]; I.flops_jac_wt = mv[13];
+    auto get = [&](const char* name) { CUfunction f = nullptr; drv.p_cuModuleGetFunction(&f, M->mod, name); return f; };
+    M->f_setup = get("rmt_setup");
+    M->f_n1_rhs = get("rmt_n1_rhs");
+    M->f_n1_jac = get("rmt_n1_jac");
+    M->f_n1_solve = get("rmt_n1_solve");
+    M->f_n2_rhs = get("rmt_n2_rhs");
+    M->f_n2_solve = get("rmt_n2_solve");
+    M->f_reduce = get("rmt_reduce_partials");
+    M->f_peak = get("rmt_dfma_peak");
+    if (!M->f_setup) { drv.p_cuModuleUnload(M->mod); delete M; return fail("module lacks rmt_setup"); }
+    CUfunction fs = I.model == 1 ? M->f_n1_solve : M->f_n2_solve;
+    if (fs && I.model == 1) {
+        M->solve_smem = (size_t)I.block*8*((size_t)I.n*I.n + (size_t)I.stages*I.n);
+        CU(cuFuncSetAttribute(fs, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)M->solve_smem));
+        CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&M->solve_blocks_per_sm, fs, I.block, M->solve_smem));
+        if (M->solve_blocks_per_sm < 1) { drv.p_cuModuleUnload(M->mod); delete M; return fail("integrator kernel does not fit on an SM (smem %zu B)", M->solve_smem); }
+    } else if (fs) {
+        CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&M->solve_blocks_per_sm, fs, I.block, 0));
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
+    uint64_t id = g_next_id++;
+    g_modules[id] = M;
+    *module_out = id;
+    return 0;
+}
+
+int rmt_module_get_info(rmt_module_t m, rmt_module_info* info)
+{
+    Module* M = get_module(m);
+    if (!M) return fail("invalid module handle");
+    *info = M->info;
+    return 0;
+}
+
+int rmt_module_free(rmt_module_t m)
+{
+    Module* M;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_modules.find(m);
+        if (it == g_modules.end()) return fail("invalid module handle");
+        M = it->second;
+        g_modules.erase(it);
+    }
+    if (g_ctx && drv.p_cuCtxSetCurrent) {
+        drv.p_cuCtxSetCurrent(g_ctx);
+        drv.p_cuCtxSynchronize();
+        for (auto& s : M->ring) if (s.p) drv.p_cuMemFree(s.p);
+        for (auto& w : M->ws) if (w) drv.p_cuMemFree(w);
+        if (M->mod) drv.p_cuModuleUnload(M->mod);
+    }
+    delete M;
+    return 0;
+}
+
+// ---- compute entry points ------------------------------------------------------------
+int rmt_setup(rmt_module_t m, int64_t B, const double* d_rows, int32_t n_rows, const int32_t* row_map,
+              const double* uniform, double* d_consts, void* stream)
+{
+    Module* M = get_module(m);
+    if (!M) return fail("invalid module handle");
+    if (ensure_ctx()) return 1;
+    if (B <= 0) return fail("rmt_setup: B must be positive");
+    if (check_rows(M, n_rows, row_map, uniform, d_rows)) return 1;
+    std::vector<char> in = pack_inputs(M, (CUdeviceptr)d_rows, B, row_map, uniform);
+    CUdeviceptr c = (CUdeviceptr)d_consts;
+    void* params[] = {in.data(), &c};
+    return launch(M->f_setup, (unsigned)((B + 127)/128), 128, 0, (CUstream)stream, params, "rmt_setup");
+}
+
+int rmt_n1_rhs(rmt_module_t m, int64_t B, const double* d_consts, const double* d_y, double* d_f, void* stream)
+{
+    Module* M = get_module(m);
+    if (!M) return fail("invalid module handle");
+    if (ensure_ctx()) return 1;
+    CUdeviceptr c = (CUdeviceptr)d_consts, y = (CUdeviceptr)d_y, f = (CUdeviceptr)d_f;
+    long long b = B;
+    void* params[] = {&c, &b, &y, &f};
+    return launch(M->f_n1_rhs, (unsigned)((B + 127)/128), 128, 0, (CUstream)stream, params, "rmt_n1_rhs");
+}
+
+int rmt_n1_jac(rmt_module_t m, int64_t B, const double* d_consts, const double* d_y, double* d_f, double* d_J,
+               void* stream)
+{
+    Module* M = get_module(m);
+    if (!M) return fail("invalid module handle");
+    if (ensure_ctx()) return 1;
+    CUdeviceptr c = (CUdeviceptr)d_consts, y = (CUdeviceptr)d_y, f = (CUdeviceptr)d_f, J = (CUdeviceptr)d_J;
+    long long b = B;
+    void* params[] = {&c, &b, &y, &f, &J};
+    return launch(M->f_n1_jac, (unsigned)((B + 127)/128), 128, 0, (CUstream)stream, params, "rmt_n1_jac");
+}
+
+int rmt_n1_solve(rmt_module_t m, int64_t B, const double* d_consts, int32_t n_eval, const double* z_eval,
+                 double rtol, double atol, int32_t max_steps, int32_t dense, int32_t out_mode,
+                 double* d_out, int32_t* d_status, int32_t* d_stats,
+                 const double* obj_ref, double* d_obj, void* stream)
+{
+    Module* M = get_module(m);
+    if (!M) return fail("invalid module handle");
+    if (ensure_ctx()) return 1;
+    if (M->info.model != 1) return fail("rmt_n1_solve: module was generated for model N2");
+    if (B <= 0 || n_eval < 1 || !z_eval) return fail("rmt_n1_solve: need B > 0 and at least one output position");
+    for (int e = 1; e < n_eval; ++e)
+        if (!(z_eval[e] > z_eval[e - 1])) return fail("rmt_n1_solve: z_eval must be strictly increasing");
+    if (!(z_eval[n_eval - 1] > 0.0)) return fail("rmt_n1_solve: the last output position must be > 0");
+    if (!(rtol > 0.0) || !(atol >= 0.0)) return fail("rmt_n1_solve: rtol must be > 0 and atol >= 0");
+    if ((obj_ref == nullptr) != (d_obj == nullptr)) return fail("rmt_n1_solve: obj_ref and d_obj go together");
+    CUstream st = (CUstream)stream;
+    const int n = M->info.n;
+    size_t need = 64 + 8*(size_t)n_eval + 8*(size_t)n;
+    CUdeviceptr scr;
+    if (scratch_get(M, need, &scr)) return 1;
+    CU(cuMemsetD8Async(scr, 0, 64, st));
+    CU(cuMemcpyHtoDAsync(scr + 64, z_eval, 8*(size_t)n_eval, st));
+    if (obj_ref) CU(cuMemcpyHtoDAsync(scr + 64 + 8*(size_t)n_eval, obj_ref, 8*(size_t)n, st));
+    SolveArgsN1 a;
+    a.consts = (CUdeviceptr)d_consts; a.B = B; a.z_eval = scr + 64; a.n_eval = n_eval; a.out_mode = out_mode;
+    a.rtol = rtol; a.atol = atol; a.max_steps = max_steps > 0 ? max_steps : 100000; a.dense = dense ? 1 : 0;
+    a.out = (CUdeviceptr)d_out; a.status = (CUdeviceptr)d_status; a.stats = (CUdeviceptr)d_stats; a.queue = scr;
+    a.obj_ref = obj_ref ? scr + 64 + 8*(size_t)n_eval : 0; a.obj = (CUdeviceptr)d_obj;
+    const int block = M->info.block;
+    long long want = (B + block - 1)/block;
+    long long cap = (long long)g_sm_count*M->solve_blocks_per_sm;
+    unsigned grid = (unsigned)std::max<long long>(1, std::min(want, cap));
+    void* params[] = {&a};
+    return launch(M->f_n1_solve, grid, block, M->solve_smem, st, params, "rmt_n1_solve");
+}
+
+int rmt_n1_solve_host(rmt_module_t m, int64_t B, const double* h_rows, int32_t n_rows, const int32_t* row_map,
+                      const double* uniform, int32_t n_eval, const double* z_eval,
+                      double rtol, double atol, int32_t max_steps, int32_t dense, int32_t out_mode,
+                      double* h_out, int32_t* h_status, int32_t* h_stats,
+                      const double* obj_ref, double* h_obj)
+{
+    Module* M = get_module(m);
+    if (!M) return fail("invalid module handle");
+    if (ensure_ctx()) return 1;
+    if (B <= 0) return fail("rmt_n1_solve_host: B must be positive");
+    if (check_rows(M, n_rows, row_map, uniform, h_rows)) return 1;
+    if (!h_out || !h_status) return fail("rmt_n1_solve_host: h_out and h_status are required");
+    const int n = M->info.n;
+    const size_t bytes_rows = 8*(size_t)std::max(n_rows, 0)*B, bytes_consts = 8*(size_t)M->info.nconst*B;
+    const size_t bytes_out = 8*(size_t)n_eval*(out_mode == 2 ? 2*n + M->info.nc : n)*B;
+    CUdeviceptr d_rows = 0, d_consts, d_out, d_status, d_stats, d_obj = 0;
+    if (n_rows > 0 && ws_reserve(M, 0, bytes_rows, &d_rows)) return 1;
+    if (ws_reserve(M, 1, bytes_consts, &d_consts)) return 1;
+    if (ws_reserve(M, 2, bytes_out, &d_out)) return 1;
+    if (ws_reserve(M, 3, 4*(size_t)B, &d_status)) return 1;
+    if (ws_reserve(M, 4, 16*(size_t)B, &d_stats)) return 1;
+    if (obj_ref && ws_reserve(M, 5, 8*(size_t)B, &d_obj)) return 1;
+    CUstream st = nullptr;
+    if (n_rows > 0) CU(cuMemcpyHtoDAsync(d_rows, h_rows, bytes_rows, st));
+    if (rmt_setup(m, B, (const double*)d_rows, n_rows, row_map, uniform, (double*)d_consts, st)) return 1;
+    if (rmt_n1_solve(m, B, (const double*)d_consts, n_eval, z_eval, rtol, atol, max_steps, dense, out_mode,
+                     (double*)d_out, (int32_t*)d_status, (int32_t*)d_stats, obj_ref, (double*)d_obj, st)) return 1;
+    CU(cuMemcpyDtoHAsync(h_out, d_out, bytes_out, st));
+    CU(cuMemcpyDtoHAsync(h_status, d_status, 4*(size_t)B, st));
+    if (h_stats) CU(cuMemcpyDtoHAsync(h_stats, d_stats, 16*(size_t)B, st));
+    if (obj_ref && h_obj) CU(cuMemcpyDtoHAsync(h_obj, d_obj, 8*(size_t)B, st));
+    CU(cuStreamSynchronize(st));
+    return 0;
+}
+
+int rmt_n2_rhs(rmt_module_t m, int64_t B, int32_t zNo, const double* d_consts, const double* d_y, double* d_f,
+               void* stream)
+{
+    Module* M = get_module(m);
+    if (!M) return fail("invalid module handle");
+    if (ensure_ctx()) return 1;
+    if (M->info.model != 2) return fail("rmt_n2_rhs: module was generated for model N1");
+    if (zNo < 2) return fail("rmt_n2_rhs: zNo must be >= 2");
+    CUdeviceptr c = (CUdeviceptr)d_consts, y = (CUdeviceptr)d_y, f = (CUdeviceptr)d_f;
+    long long b = B;
+    int z = zNo;
+    void* params[] = {&c, &b, &z, &y, &f};
+    return launch(M->f_n2_rhs, (unsigned)((B + 63)/64), 64, 0, (CUstream)stream, params, "rmt_n2_rhs");
+}
+
+int64_t rmt_n2_work_doubles(rmt_module_t m, int64_t B, int32_t zNo)
+{
+    Module* M = get_module(m);
+    if (!M) { fail("invalid module handle"); return -1; }
+    const int64_t n = M->info.n, s = M->info.stages;
+    // per node: state n, stages s*n, LU n*n, dF/dP n, dE/dy n+1, pivots(as double) n  ; per instance extras
+    return ((int64_t)zNo*(n + s*n + n*n + n + (n + 1) + 1) + 16)*B;
+}
+
+int rmt_n2_solve(rmt_module_t m, int64_t B, int32_t zNo, int32_t tNo, double period, const double* d_consts,
+                 double rtol, double atol, int32_t max_steps, int32_t out_mode,
+                 double* d_out, int32_t* d_status, int32_t* d_stats, double* d_work, void* stream)
+{
+    Module* M = get_module(m);
+    if (!M) return fail("invalid module handle");
+    if (ensure_ctx()) return 1;
+    if (M->info.model != 2) return fail("rmt_n2_solve: module was generated for model N1");
+    if (B <= 0 || zNo < 2 || tNo < 1 || !(period > 0.0)) return fail("rmt_n2_solve: need B > 0, zNo >= 2, tNo >= 1, period > 0");
+    if (!(rtol > 0.0) || !(atol >= 0.0)) return fail("rmt_n2_solve: rtol must be > 0 and atol >= 0");
+    if (!d_work) return fail("rmt_n2_solve: d_work is required (rmt_n2_work_doubles)");
+    CUstream st = (CUstream)stream;
+    CUdeviceptr scr;
+    if (scratch_get(M, 64, &scr)) return 1;
+    CU(cuMemsetD8Async(scr, 0, 64, st));
+    SolveArgsN2 a;
+    a.consts = (CUdeviceptr)d_consts; a.B = B; a.zNo = zNo; a.tNo = tNo; a.period = period;
+    a.rtol = rtol; a.atol = atol; a.max_steps = max_steps > 0 ? max_steps : 1000000; a.out_mode = out_mode;
+    a.out = (CUdeviceptr)d_out; a.status = (CUdeviceptr)d_status; a.stats = (CUdeviceptr)d_stats;
+    a.work = (CUdeviceptr)d_work; a.queue = scr;
+    const int block = M->info.block;
+    unsigned grid = (unsigned)((B + block - 1)/block);
+    void* params[] = {&a};
+    return launch(M->f_n2_solve, grid, block, 0, st, params, "rmt_n2_solve");
+}
+
+int rmt_reduce_objective(rmt_module_t m, int64_t n, const double* d_obj, int64_t index_offset,
+                         double* h_sum, double* h_min, int64_t* h_argmin, void* stream)
+{
+    Module* M = get_module(m);
+    if (!M) return fail("invalid module handle");
+    if (ensure_ctx()) return 1;
+    if (n <= 0) return fail("rmt_reduce_objective: n must be positive");
+    CUstream st = (CUstream)stream;
+    const unsigned blocks = (unsigned)std::min<long long>(256, (n + 255)/256);
+    CUdeviceptr part;
+    if (ws_reserve(M, 6, 3*8*(size_t)(blocks + 1), &part)) return 1;
+    CUdeviceptr v = (CUdeviceptr)d_obj, ps = part, pm = part + 8*(size_t)(blocks + 1), pa = part + 16*(size_t)(blocks + 1);
+    long long nn = n, off = index_offset;
+    void* params[] = {&v, &nn, &off, &ps, &pm, &pa};
+    if (launch(M->f_reduce, blocks, 256, 0, st, params, "rmt_reduce_partials")) return 1;
+    std::vector<double> hs(blocks), hm(blocks);
+    std::vector<long long> ha(blocks);
+    CU(cuMemcpyDtoHAsync(hs.data(), ps, 8*(size_t)blocks, st));
+    CU(cuMemcpyDtoHAsync(hm.data(), pm, 8*(size_t)blocks, st));
+    CU(cuMemcpyDtoHAsync(ha.data(), pa, 8*(size_t)blocks, st));
+    CU(cuStreamSynchronize(st));
+    double s = 0.0, mn = hm[0];
+    long long am = ha[0];
+    for (unsigned b = 0; b < blocks; ++b) {           // fixed order: deterministic
+        s += hs[b];
+        if (hm[b] < mn || (hm[b] == mn && ha[b] >= 0 && (am < 0 || ha[b] < am))) { mn = hm[b]; am = ha[b]; }
+    }
+    if (h_sum) *h_sum = s;
+    if (h_min) *h_min = mn;
+    if (h_argmin) *h_argmin = am;
+    return 0;
+}
+
+int rmt_fp64_peak(rmt_module_t m, int32_t iters, int32_t repeats, double* tflops_out)
+{
+    Module* M = get_module(m);
+    if (!M) return fail("invalid module handle");
+    if (ensure_ctx()) return 1;
+    if (!M->f_peak) return fail("module lacks rmt_dfma_peak");
+    const unsigned blocks = (unsigned)g_sm_count*8, threads = 256;
+    CUdeviceptr out;
+    if (ws_reserve(M, 7, 8*(size_t)blocks*threads, &out)) return 1;
+    int it = iters > 0 ? iters : 4096;
+    double seed = 1.0;
+    void* params[] = {&out, &it, &seed};
+    CUevent e0, e1;
+    CU(cuEventCreate(&e0, 0));
+    CU(cuEventCreate(&e1, 0));
+    double best = 0.0;
+    for (int r = 0; r < std::max(repeats, 1) + 1; ++r) {
+        CU(cuEventRecord(e0, nullptr));
+        if (launch(M->f_peak, blocks, threads, 0, nullptr, params, "rmt_dfma_peak")) return 1;
+        CU(cuEventRecord(e1, nullptr));
+        CU(cuEventSynchronize(e1));
+        float ms = 0.f;
+        CU(cuEventElapsedTime(&ms, e0, e1));
+        double fl = 2.0*8.0*(double)it*(double)blocks*threads;
+        if (r > 0) best = std::max(best, fl/(ms*1e-3)/1e12);
+    }
+    CU(cuEventDestroy(e0));
+    CU(cuEventDestroy(e1));
+    *tflops_out = best;
+    return 0;
+}
+
+}  // extern "C"

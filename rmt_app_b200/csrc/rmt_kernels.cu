@@ -1,0 +1,828 @@
+// rmt_kernels.cu — hand-written FP64 kernels for the pseudo-homogeneous packed-bed
+// reactor models N1 (steady-state axial ODE) and N2 (dynamic, method of lines).
+//
+// This file is the model-independent half of the NVRTC translation unit.  The
+// model-dependent half, "rmt_model.cuh", is generated per (components,
+// reactions, kinetics) by rmt_app_b200/codegen.py and provides the sizes, the
+// component literals, the traced kinetics `rmt_rates` / `rmt_rates_jac` and the
+// Rosenbrock tableau.  Target: sm_100a (B200).  No tensor cores: the path is not
+// a contraction; the bound is the FP64 vector pipe (fused integrator) or HBM
+// (stand-alone RHS / Jacobian kernels).
+//
+// Reference arithmetic being restated (file:line relative to
+// /root/reference/PyREMOT/): setup docs/pbHomoReactor.py:2744-2852 (N1) and
+// :3370-3507 (N2); RHS modelEquationN1 :3017-3314, modelEquationN2 :3706-4134;
+// thermo docs/rmtThermo.py:16-101,258-369; utilities docs/rmtUtility.py:405-496;
+// viscosity docs/gasTransPor.py:137-274; un-scaling solvers/solResultAnalysis.py:191-301.
+//
+// Data layout: structure-of-arrays with the instance index fastest everywhere
+// (inputs [row][B], constants [row][B], states [var][B] or [var][node][B],
+// outputs [point][var][B]) so that a warp's lanes touch consecutive doubles.
+
+#include "rmt_model.cuh"
+
+#define RMT_R_CONST 8.314472            // core/constants.py:8
+#define RMT_TREF 298.15                 // core/constants.py:17-23
+#define RMT_PI 3.141592653589793        // core/constants.py:14
+#define RMT_EPS_CONST 1e-30             // core/constants.py:11
+
+#if defined(RMT_MODEL_N1)
+#define RMT_N (RMT_NC + (RMT_ISO ? 1 : 2))      // Ci..., P, (T)
+#else
+#define RMT_N (RMT_NC + (RMT_ISO ? 0 : 1))      // Ci..., (T) per node
+#endif
+#define RMT_NCONST_VALUE (19 + RMT_NC + RMT_NKP)
+#define RMT_IP RMT_NC                            // N1: index of P-hat
+#define RMT_IT (RMT_NC + 1)                      // N1: index of T-hat
+
+#ifndef RMT_BLOCK
+#define RMT_BLOCK 128
+#endif
+
+typedef long long i64;
+
+// self-description of the module, read back by rmt_module_load()
+extern "C" __global__ void rmt_meta(int* out)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+#if defined(RMT_MODEL_N1)
+    out[0] = 1;
+#else
+    out[0] = 2;
+#endif
+    out[1] = RMT_N; out[2] = RMT_NC; out[3] = RMT_NR; out[4] = RMT_NIN; out[5] = RMT_NCONST_VALUE;
+    out[6] = RMT_NKP; out[7] = RMT_ROS_S; out[8] = RMT_BLOCK; out[9] = RMT_ISO;
+    out[10] = RMT_FLOPS_RHS_ALG; out[11] = RMT_FLOPS_RHS_WT; out[12] = RMT_FLOPS_JAC_ALG; out[13] = RMT_FLOPS_JAC_WT;
+    out[14] = 0; out[15] = 0;
+}
+
+// ---------------------------------------------------------------------------------
+// primary per-instance inputs: the modelInput numbers a sweep may vary
+// ---------------------------------------------------------------------------------
+enum {
+    IN_T = 0, IN_P = 1, IN_C0 = 2,
+    IN_Q = 2 + RMT_NC, IN_D, IN_L, IN_DP, IN_EPS, IN_U, IN_TM,
+    IN_KP0
+};
+static_assert(IN_KP0 + RMT_NKP == RMT_NIN, "input row count");
+
+struct RmtInputs {
+    const double* rows;        // varying rows, [n_rows][B]
+    i64 B;
+    int map[RMT_NIN];          // row index into `rows`, or -1 -> uniform value u[q]
+    double u[RMT_NIN];
+};
+
+__device__ __forceinline__ double rmt_in(const RmtInputs& p, const int q, const i64 i)
+{
+    const int m = p.map[q];
+    return m >= 0 ? __ldg(p.rows + (i64)m*p.B + i) : p.u[q];
+}
+
+// ---------------------------------------------------------------------------------
+// per-instance constants (what runN1/runN2 put into paramsSet)
+// ---------------------------------------------------------------------------------
+enum {
+    K_CMAX = 0, K_TF, K_PF, K_C0, K_UI0, K_US0, K_RHO0, K_CPF, K_GM, K_GH, K_MU,
+    K_EPS, K_DP, K_ZF, K_U, K_A, K_TM, K_VF, K_MWF, K_IV0,
+    K_KP0 = K_IV0 + RMT_NC,
+    RMT_NCONST = K_KP0 + RMT_NKP
+};
+static_assert(RMT_NCONST == RMT_NCONST_VALUE, "constant row count");
+
+__device__ __forceinline__ double rmt_cp(const int i, const double T, const double T2, const double T3)
+{
+    // Cp string "a0 + a1*T + a2*(T**2) + a3*(T**3)", left to right (rmtThermo.py:37)
+    double v = RMT_CP[i][0] + RMT_CP[i][1]*T + RMT_CP[i][2]*T2;
+    if (RMT_CP[i][3] != 0.0) v = v + RMT_CP[i][3]*T3;
+    return v;
+}
+
+// setup: docs/pbHomoReactor.py:2744-2852 (runN1) / :3370-3507 (runN2)
+extern "C" __global__ void __launch_bounds__(128) rmt_setup(const RmtInputs in, double* __restrict__ consts)
+{
+    const i64 i = (i64)blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= in.B) return;
+    const i64 B = in.B;
+    const double T = rmt_in(in, IN_T, i), P = rmt_in(in, IN_P, i);
+    const double Q0 = rmt_in(in, IN_Q, i), D = rmt_in(in, IN_D, i), L = rmt_in(in, IN_L, i);
+    const double dp = rmt_in(in, IN_DP, i), eps = rmt_in(in, IN_EPS, i);
+    const double U = rmt_in(in, IN_U, i), Tm = rmt_in(in, IN_TM, i);
+    double C0i[RMT_NC], y0[RMT_NC];
+    double C0 = 0.0, Cmax = 0.0;
+#pragma unroll
+    for (int k = 0; k < RMT_NC; ++k) {
+        C0i[k] = rmt_in(in, IN_C0 + k, i);
+        C0 += C0i[k];
+        Cmax = k == 0 ? C0i[k] : fmax(Cmax, C0i[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < RMT_NC; ++k) y0[k] = C0i[k]/C0;
+    const double A = RMT_PI*(D*D)/4;                         // :2751
+    const double ui0 = Q0/(A*eps);                           // :3137 / :3391
+    const double us0 = ui0*eps;
+#if defined(RMT_MODEL_N1)
+    const double vf = Q0/A;                                  // :2763
+#else
+    const double vf = us0;                                   // :3452
+#endif
+    const double a = 4/D;                                    // :2778 (EfHeTrAr input ignored)
+    // pure-gas viscosities at feed T (gasTransPor.py:137-154, dataGasViscosity.py:133)
+    double mu[RMT_NC];
+#pragma unroll
+    for (int k = 0; k < RMT_NC; ++k) {
+        if (RMT_VISC_EQ[k] == 1)
+            mu[k] = RMT_VISC[k][0]*1e-6*pow(T, RMT_VISC[k][1])/(1 + RMT_VISC[k][2]*(1/T) + RMT_VISC[k][3]*(1.0/(T*T)));
+        else
+            mu[k] = RMT_VISC[k][0]*pow(T, RMT_VISC[k][1])/(1 + (RMT_VISC[k][2]/T));
+    }
+    // Wilke mixing rule (gasTransPor.py:229-274)
+    double mumix = 0.0;
+#pragma unroll
+    for (int p = 0; p < RMT_NC; ++p) {
+        double den = 0.0;
+#pragma unroll
+        for (int q = 0; q < RMT_NC; ++q) {
+            double phi;
+            if (p == q) phi = 1.0;
+            else {
+                const int lo = p < q ? p : q, hi = p < q ? q : p;
+                const double A1 = 1 + sqrt(mu[lo]/mu[hi])*sqrt(sqrt(RMT_MW[hi]/RMT_MW[lo]));
+                const double up = (A1*A1)/sqrt(8*(1 + (RMT_MW[lo]/RMT_MW[hi])));
+                phi = p < q ? up : (mu[p]/mu[q])*(RMT_MW[q]/RMT_MW[p])*up;
+            }
+            den += y0[q]*phi;
+        }
+        mumix += (mu[p]*y0[p])/den;
+    }
+    const double T2 = T*T, T3 = T*T*T;
+    double Cpf = 0.0, MWf = 0.0;
+#pragma unroll
+    for (int k = 0; k < RMT_NC; ++k) {
+        const double cpm = (RMT_CPREF[k] + rmt_cp(k, T, T2, T3))*0.50;     // rmtThermo.py:52-75
+        Cpf += y0[k]*cpm;
+        MWf += y0[k]*RMT_MW[k];
+    }
+    MWf = MWf*1e-3;                                           // rmtUtility.py:57-95, "kg/mol"
+    const double rho0 = MWf*C0;                               // :2796
+    const double Gm = (vf/L)*Cmax;                            // :2819-2821 (GaMaCoTe0 == "MAX")
+    const double Gh = (rho0*vf*T*(Cpf/MWf)/L);                // :2823
+    double* c = consts + i;
+    c[(i64)K_CMAX*B] = Cmax; c[(i64)K_TF*B] = T;   c[(i64)K_PF*B] = P;     c[(i64)K_C0*B] = C0;
+    c[(i64)K_UI0*B] = ui0;   c[(i64)K_US0*B] = us0; c[(i64)K_RHO0*B] = rho0; c[(i64)K_CPF*B] = Cpf;
+    c[(i64)K_GM*B] = Gm;     c[(i64)K_GH*B] = Gh;   c[(i64)K_MU*B] = mumix;  c[(i64)K_EPS*B] = eps;
+    c[(i64)K_DP*B] = dp;     c[(i64)K_ZF*B] = L;    c[(i64)K_U*B] = U;       c[(i64)K_A*B] = a;
+    c[(i64)K_TM*B] = Tm;     c[(i64)K_VF*B] = vf;   c[(i64)K_MWF*B] = MWf;
+#pragma unroll
+    for (int k = 0; k < RMT_NC; ++k) c[(i64)(K_IV0 + k)*B] = C0i[k]/Cmax;     // :2833 / :3489
+#pragma unroll
+    for (int k = 0; k < RMT_NKP; ++k) c[(i64)(K_KP0 + k)*B] = rmt_in(in, IN_KP0 + k, i);
+}
+
+// hot constants kept in registers by the RHS / integrator
+struct Hot {
+    double Cmax, Tf, Pf, C0, ui0, us0, rho0, Cpf, Gm, Gh, ergA, ergC, Ua, Tm, eps;
+#if defined(RMT_MODEL_N1)
+    double beta;                 // Pf/zf
+#else
+    double F1, dz, invdz;        // 1/(eps*(zf/vf)), node spacing
+    double iv[RMT_NC];           // inlet boundary values C0_i/Cmax
+#endif
+    double kp[RMT_NKP > 0 ? RMT_NKP : 1];
+};
+
+__device__ __forceinline__ void rmt_load_hot(const double* __restrict__ consts, const i64 B, const i64 i, Hot& h)
+{
+    const double* c = consts + i;
+    h.Cmax = c[(i64)K_CMAX*B]; h.Tf = c[(i64)K_TF*B]; h.Pf = c[(i64)K_PF*B]; h.C0 = c[(i64)K_C0*B];
+    h.ui0 = c[(i64)K_UI0*B]; h.us0 = c[(i64)K_US0*B]; h.rho0 = c[(i64)K_RHO0*B]; h.Cpf = c[(i64)K_CPF*B];
+    h.Gm = c[(i64)K_GM*B]; h.Gh = c[(i64)K_GH*B];
+    const double mu = c[(i64)K_MU*B], eps = c[(i64)K_EPS*B], dp = c[(i64)K_DP*B], zf = c[(i64)K_ZF*B];
+    h.eps = eps;
+    // Ergun coefficients (pbHomoReactor.py:3214-3217): ergA*ergB = cA*us, ergC*ergD = cC*rho*us^2
+    h.ergA = 150*mu/(dp*dp)*(((1 - eps)*(1 - eps))/(eps*eps*eps));
+    h.ergC = 1.75/dp*((1 - eps)/(eps*eps*eps));
+    h.Ua = c[(i64)K_U*B]*c[(i64)K_A*B];
+    h.Tm = c[(i64)K_TM*B];
+#if defined(RMT_MODEL_N1)
+    h.beta = h.Pf/zf;
+#else
+    const double vf = c[(i64)K_VF*B];
+    h.F1 = 1/(eps*(zf/vf));
+#pragma unroll
+    for (int k = 0; k < RMT_NC; ++k) h.iv[k] = c[(i64)(K_IV0 + k)*B];
+#endif
+#pragma unroll
+    for (int k = 0; k < RMT_NKP; ++k) h.kp[k] = c[(i64)(K_KP0 + k)*B];
+}
+
+// ---------------------------------------------------------------------------------
+// point physics shared by N1 and N2: everything of the RHS that depends on the
+// local (C_i, T, P) only.  JAC adds the partial derivatives.
+// ---------------------------------------------------------------------------------
+struct Point {
+    double y[RMT_NC];      // mole fractions
+    double S;              // total concentration [mol/m^3]
+    double T, P;
+    double MWm, rho;       // mixture MW [kg/mol], EOS density
+    double R[RMT_NR];      // reaction rates
+    double r[RMT_NC];      // formation rates
+    double cpm[RMT_NC];    // mean heat capacities
+    double Cp;             // mixture mean heat capacity
+    double dH[RMT_NR];     // heats of reaction at T
+    double q, Qm;          // overall heat of reaction, coolant duty
+};
+
+struct PointJac {
+    double dRdT[RMT_NR], dRdP[RMT_NR], dRdy[RMT_NR][RMT_NC], dRdC[RMT_NR][RMT_NC];
+    double dCpdT;          // sum_i y_i * 0.5 * Cp_i'(T)
+    double ddHdT[RMT_NR];  // d(dH_j)/dT
+};
+
+template <bool JAC>
+__device__ __forceinline__ void rmt_point(const double (&C)[RMT_NC], const double T, const double P,
+                                          const Hot& h, Point& p, PointJac& pj)
+{
+    double S = 0.0;
+#pragma unroll
+    for (int i = 0; i < RMT_NC; ++i) S += C[i];
+    p.S = S; p.T = T; p.P = P;
+    double mw = 0.0;
+#pragma unroll
+    for (int i = 0; i < RMT_NC; ++i) { p.y[i] = C[i]/S; mw += p.y[i]*RMT_MW[i]; }
+    p.MWm = mw*1e-3;
+    p.rho = P/((RMT_R_CONST/p.MWm)*T);                       // rmtThermo.py:353-369
+    if (JAC) rmt_rates_jac(T, P, p.y, C, h.kp, p.R, pj.dRdT, pj.dRdP, pj.dRdy, pj.dRdC);
+    else rmt_rates(T, P, p.y, C, h.kp, p.R);
+#pragma unroll
+    for (int i = 0; i < RMT_NC; ++i) {                        // rmtReaction.py:64-97
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < RMT_NR; ++j) if (RMT_NU[j][i] != 0.0) acc += RMT_NU[j][i]*p.R[j];
+        p.r[i] = acc;
+    }
+    const double T2 = T*T, T3 = T2*T;
+    double Cp = 0.0, dCp = 0.0;
+#pragma unroll
+    for (int i = 0; i < RMT_NC; ++i) {
+        p.cpm[i] = (RMT_CPREF[i] + rmt_cp(i, T, T2, T3))*0.50;
+        Cp += p.y[i]*p.cpm[i];
+        if (JAC) dCp += p.y[i]*(0.5*(RMT_CP[i][1] + 2.0*RMT_CP[i][2]*T + 3.0*RMT_CP[i][3]*T2));
+    }
+    p.Cp = Cp;
+    if (JAC) pj.dCpdT = dCp;
+    const double dT = T - RMT_TREF;
+    double q = 0.0;
+#pragma unroll
+    for (int j = 0; j < RMT_NR; ++j) {                        // rmtThermo.py:258-312 + StHeRe25
+        const double dcp = RMT_DCP[j][0] + RMT_DCP[j][1]*T + RMT_DCP[j][2]*T2 + RMT_DCP[j][3]*T3;
+        p.dH[j] = dcp*dT + RMT_DH25[j];
+        q += p.R[j]*p.dH[j];
+        if (JAC) pj.ddHdT[j] = dcp + dT*(RMT_DCP[j][1] + 2.0*RMT_DCP[j][2]*T + 3.0*RMT_DCP[j][3]*T2);
+    }
+    p.q = q;
+    p.Qm = (h.Tm == 0.0) ? 0.0 : h.Ua*(h.Tm - T);             // rmtUtility.py:424-452
+}
+
+#if defined(RMT_MODEL_N1)
+// ---------------------------------------------------------------------------------
+// N1 right-hand side (modelEquationN1, pbHomoReactor.py:3017-3314) and its analytic
+// Jacobian.  `JS` receives J(i, j, value) = d f_i / d yhat_j.
+// ---------------------------------------------------------------------------------
+struct NoJac { __device__ __forceinline__ void operator()(int, int, double) const {} };
+
+template <bool JAC, class JS>
+__device__ __forceinline__ void n1_eval(const double (&yh)[RMT_N], const Hot& h, double (&f)[RMT_N], JS&& J)
+{
+    double C[RMT_NC];
+#pragma unroll
+    for (int i = 0; i < RMT_NC; ++i) C[i] = yh[i]*h.Cmax;    // :3159-3162
+    const double P = yh[RMT_IP]*h.Pf;                         // :3173
+#if RMT_ISO
+    const double T = 0.0*h.Tf + h.Tf;                         // :3155, :3170
+#else
+    const double T = yh[RMT_IT]*h.Tf + h.Tf;
+#endif
+    Point p; PointJac pj;
+    rmt_point<JAC>(C, T, P, h, p, pj);
+    // velocities (rmtUtility.py:405-421; :3180-3186)
+    const double ui = h.ui0*(p.S/h.C0)*(h.Pf/P);
+    const double uih = ui/h.ui0;
+    const double us = ui*h.eps;
+    const double ush = us/h.us0;
+    const double rhoh = p.rho/h.rho0;
+    // Ergun (:3214-3220)
+    f[RMT_IP] = -1*(h.ergA*us + h.ergC*p.rho*(us*us))/h.beta;
+    const double c1 = 1/ush;
+#pragma unroll
+    for (int i = 0; i < RMT_NC; ++i) f[i] = c1*(p.r[i]/h.Gm);    // :3283-3289
+#if !RMT_ISO
+    const double cpeffh = (p.Cp/h.Cpf)*h.eps;                 // :3252-3257
+    const double Dn = rhoh*cpeffh*uih;
+    const double Nn = (-p.q + p.Qm)/h.Gh;
+    f[RMT_IT] = (1/Dn)*Nn;                                    // :3284, :3298
+#endif
+    if (JAC) {
+        const double invS = 1.0/p.S;
+        // sum_i dRdy[j][i]*y_i, used by every species column
+        double sy[RMT_NR];
+#pragma unroll
+        for (int j = 0; j < RMT_NR; ++j) {
+            double a = 0.0;
+#if RMT_RATES_DEP_Y
+#pragma unroll
+            for (int i = 0; i < RMT_NC; ++i) a += pj.dRdy[j][i]*p.y[i];
+#endif
+            sy[j] = a;
+        }
+        const double inv_ushGm = c1/h.Gm;
+#pragma unroll
+        for (int col = 0; col < RMT_N; ++col) {
+            const bool isC = col < RMT_NC, isP = col == RMT_IP, isT = (!RMT_ISO) && col == RMT_IT;
+            // d ln w, d ln rho, dR_j for this column (already multiplied by the column scale)
+            double dlnw, dlnrho, dR[RMT_NR];
+            if (isC) {
+                dlnw = h.Cmax*invS;
+                dlnrho = h.Cmax*(1e-3*RMT_MW[col < RMT_NC ? col : 0] - p.MWm)*invS/p.MWm;
+#pragma unroll
+                for (int j = 0; j < RMT_NR; ++j) {
+                    double a = 0.0;
+#if RMT_RATES_DEP_Y
+                    a = (pj.dRdy[j][col < RMT_NC ? col : 0] - sy[j])*invS;
+#endif
+#if RMT_RATES_DEP_C
+                    a += pj.dRdC[j][col < RMT_NC ? col : 0];
+#endif
+                    dR[j] = h.Cmax*a;
+                }
+            } else if (isP) {
+                dlnw = -h.Pf/P;
+                dlnrho = h.Pf/P;
+#pragma unroll
+                for (int j = 0; j < RMT_NR; ++j) dR[j] = h.Pf*pj.dRdP[j];
+            } else {
+                dlnw = 0.0;
+                dlnrho = -h.Tf/T;
+#pragma unroll
+                for (int j = 0; j < RMT_NR; ++j) dR[j] = h.Tf*pj.dRdT[j];
+            }
+            const double dus = us*dlnw;
+            J(RMT_IP, col, -1*(h.ergA*dus + h.ergC*(p.rho*dlnrho*(us*us) + 2.0*p.rho*us*dus))/h.beta);
+#pragma unroll
+            for (int i = 0; i < RMT_NC; ++i) {
+                double dr = 0.0;
+#pragma unroll
+                for (int j = 0; j < RMT_NR; ++j) if (RMT_NU[j][i] != 0.0) dr += RMT_NU[j][i]*dR[j];
+                J(i, col, dr*inv_ushGm - f[i]*dlnw);
+            }
+#if !RMT_ISO
+            double dq = 0.0;
+#pragma unroll
+            for (int j = 0; j < RMT_NR; ++j) dq += dR[j]*p.dH[j];
+            double dCp, dQm = 0.0;
+            if (isC) dCp = h.Cmax*(p.cpm[col < RMT_NC ? col : 0] - p.Cp)*invS;
+            else if (isT) {
+                dCp = h.Tf*pj.dCpdT;
+#pragma unroll
+                for (int j = 0; j < RMT_NR; ++j) dq += p.R[j]*(h.Tf*pj.ddHdT[j]);
+                dQm = (h.Tm == 0.0) ? 0.0 : -h.Ua*h.Tf;
+            } else dCp = 0.0;
+            const double dN = (-dq + dQm)/h.Gh;
+            const double dlnD = dlnrho + dCp/p.Cp + dlnw;
+            J(RMT_IT, col, dN/Dn - f[RMT_IT]*dlnD);
+#endif
+        }
+    }
+}
+
+// stand-alone batched RHS: y [N][B] -> f [N][B]   (parity + "RHS evals/s" kernel)
+extern "C" __global__ void __launch_bounds__(128)
+rmt_n1_rhs(const double* __restrict__ consts, const i64 B, const double* __restrict__ y, double* __restrict__ f)
+{
+    const i64 i = (i64)blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    Hot h; rmt_load_hot(consts, B, i, h);
+    double yh[RMT_N], fo[RMT_N];
+#pragma unroll
+    for (int k = 0; k < RMT_N; ++k) yh[k] = y[(i64)k*B + i];
+    n1_eval<false>(yh, h, fo, NoJac());
+#pragma unroll
+    for (int k = 0; k < RMT_N; ++k) f[(i64)k*B + i] = fo[k];
+}
+
+struct GlobalJac {
+    double* J; i64 B, i;
+    __device__ __forceinline__ void operator()(int r, int c, double v) const { J[(i64)(r*RMT_N + c)*B + i] = v; }
+};
+
+// stand-alone batched Jacobian: y [N][B] -> f [N][B], J [N*N][B] (row-major d f_r / d y_c)
+extern "C" __global__ void __launch_bounds__(128)
+rmt_n1_jac(const double* __restrict__ consts, const i64 B, const double* __restrict__ y,
+           double* __restrict__ f, double* __restrict__ J)
+{
+    const i64 i = (i64)blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    Hot h; rmt_load_hot(consts, B, i, h);
+    double yh[RMT_N], fo[RMT_N];
+#pragma unroll
+    for (int k = 0; k < RMT_N; ++k) yh[k] = y[(i64)k*B + i];
+    GlobalJac gj{J, B, i};
+    n1_eval<true>(yh, h, fo, gj);
+#pragma unroll
+    for (int k = 0; k < RMT_N; ++k) f[(i64)k*B + i] = fo[k];
+}
+
+// ---------------------------------------------------------------------------------
+// N1 integrator: one reactor instance per lane, adaptive Rosenbrock (tableau from the
+// generated header), SciPy-style error test  rms(err / (atol + rtol*max(|y|,|y_new|))) <= 1.
+// The n x n iteration matrix W = I/(h*gamma) - J, its LU factors and the stage vectors
+// K_1..K_s live in shared memory, column-interleaved across the block ([slot][tid]) so
+// every access is conflict-free.  Lanes pull instances from a global queue, so a lane
+// that finishes early immediately starts another reactor instead of idling until the
+// slowest reactor of its warp is done.
+// ---------------------------------------------------------------------------------
+struct SolveArgs {
+    const double* consts;      // [NCONST][B]
+    i64 B;
+    const double* z_eval;      // [n_eval] increasing, last = end of domain
+    int n_eval;
+    int out_mode;              // 0: raw scaled state, 1: dataYs rows (y_i, P[Pa], T[K]), 2: raw | C_i | dataYs
+    double rtol, atol;
+    int max_steps;
+    int dense;                 // 1: interpolate eval points; 0: step onto each of them
+    double* out;               // [n_eval][N][B]
+    int* status;               // [B]
+    int* stats;                // [4][B]: accepted, rejected, nfev, njev
+    unsigned long long* queue; // work counter (zeroed by the host before launch)
+    // optional fused objective (parameter estimation): sum_k ((out_k - ref_k)/ref_k)^2 over the outlet
+    const double* obj_ref;     // [N] or null
+    double* obj;               // [B]
+};
+
+#define SM(slot) sm[(slot)*RMT_BLOCK]
+#define LU(r, c) SM((r)*RMT_N + (c))
+#define KS(s, i) SM(RMT_N*RMT_N + (s)*RMT_N + (i))
+#define RMT_SMEM_DOUBLES_PER_THREAD (RMT_N*RMT_N + RMT_ROS_S*RMT_N)
+
+struct SmemJac {
+    double* sm;
+    __device__ __forceinline__ void operator()(int r, int c, double v) const { LU(r, c) = v; }
+};
+
+// rows written per output point: mode 0 raw scaled state (sol.y); mode 1 dataYs rows
+// (y_i, P [Pa], T [K]); mode 2 everything runN1 packs: raw | C_i [mol/m^3] | dataYs rows
+__device__ __forceinline__ int n1_out_rows(const int mode) { return mode == 2 ? 2*RMT_N + RMT_NC : RMT_N; }
+
+__device__ __forceinline__ void n1_write_point(const SolveArgs& a, const Hot& h, const i64 inst, const int e,
+                                                const double (&v)[RMT_N])
+{
+    const int rows = n1_out_rows(a.out_mode);
+    double* o = a.out + ((i64)e*rows)*a.B + inst;
+    if (a.out_mode != 1) {
+#pragma unroll
+        for (int k = 0; k < RMT_N; ++k) o[(i64)k*a.B] = v[k];
+        o += (i64)RMT_N*a.B;
+    }
+    if (a.out_mode != 0) {
+        // sortResult4 (solResultAnalysis.py:191-249) + mole fractions (pbHomoReactor.py:2973-2983)
+        double S = 0.0, C[RMT_NC];
+#pragma unroll
+        for (int k = 0; k < RMT_NC; ++k) { C[k] = v[k]*h.Cmax; S += C[k]; }
+        if (a.out_mode == 2) {
+#pragma unroll
+            for (int k = 0; k < RMT_NC; ++k) o[(i64)k*a.B] = C[k];
+            o += (i64)RMT_NC*a.B;
+        }
+#pragma unroll
+        for (int k = 0; k < RMT_NC; ++k) o[(i64)k*a.B] = C[k]/S;
+        o[(i64)RMT_IP*a.B] = v[RMT_IP]*h.Pf;
+#if !RMT_ISO
+        o[(i64)RMT_IT*a.B] = v[RMT_IT]*h.Tf + h.Tf;
+#endif
+    }
+}
+
+extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const SolveArgs a)
+{
+    extern __shared__ double smem[];
+    double* sm = smem + threadIdx.x;
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+
+    i64 inst = -1;
+    bool exhausted = false;
+    Hot h;
+    double y[RMT_N];
+    double t = 0.0, hstep = 0.0, hacc = 0.0, erracc = 0.0, tend = 0.0;
+    int nacc = 0, nrej = 0, next_e = 0, nanrej = 0;
+    bool last_rejected = false, fresh = false;
+
+    while (true) {
+        // ---- refill idle lanes from the queue (warp-aggregated atomic) ----
+        const bool need = (inst < 0) && !exhausted;
+        const unsigned m = __ballot_sync(FULL, need);
+        if (m) {
+            unsigned long long base = 0;
+            const int leader = __ffs(m) - 1;
+            if (lane == leader) base = atomicAdd(a.queue, (unsigned long long)__popc(m));
+            base = __shfl_sync(FULL, base, leader);
+            if (need) {
+                const i64 cand = (i64)base + __popc(m & ((1u << lane) - 1));
+                if (cand >= a.B) exhausted = true;
+                else {
+                    inst = cand;
+                    rmt_load_hot(a.consts, a.B, inst, h);
+#pragma unroll
+                    for (int k = 0; k < RMT_NC; ++k) y[k] = a.consts[(i64)(K_IV0 + k)*a.B + inst];
+                    y[RMT_IP] = 1.0;                          // P/Pf, :2834
+#if !RMT_ISO
+                    y[RMT_IT] = 0.0;                          // (T-Tf)/Tf, :2838
+#endif
+                    t = 0.0; nacc = 0; nrej = 0; nanrej = 0; next_e = 0; last_rejected = false; fresh = true;
+                    hacc = 0.0; erracc = 1e-2;
+                    tend = a.z_eval[a.n_eval - 1];
+                    while (next_e < a.n_eval && a.z_eval[next_e] <= 0.0) { n1_write_point(a, h, inst, next_e, y); ++next_e; }
+                }
+            }
+        }
+        if (__all_sync(FULL, inst < 0)) break;
+        if (inst < 0) continue;
+
+        // ---- one step attempt ----
+        double f0[RMT_N];
+        SmemJac sj{sm};
+        n1_eval<true>(y, h, f0, sj);                          // f(y_n) and J into LU(.,.)
+
+        if (fresh) {
+            // initial step (Hairer-Wanner II.4 with the exact y'' = J f)
+            double d0 = 0.0, d1 = 0.0, d2 = 0.0;
+#pragma unroll
+            for (int i = 0; i < RMT_N; ++i) {
+                const double sc = a.atol + a.rtol*fabs(y[i]);
+                double jf = 0.0;
+#pragma unroll
+                for (int j = 0; j < RMT_N; ++j) jf += LU(i, j)*f0[j];
+                d0 += (y[i]/sc)*(y[i]/sc); d1 += (f0[i]/sc)*(f0[i]/sc); d2 += (jf/sc)*(jf/sc);
+            }
+            d0 = sqrt(d0/RMT_N); d1 = sqrt(d1/RMT_N); d2 = sqrt(d2/RMT_N);
+            const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01*d0/d1;
+            const double dm = fmax(d1, d2);
+            const double h1 = dm <= 1e-15 ? fmax(1e-6, h0*1e-3) : pow(0.01/dm, 1.0/(RMT_ROS_ORDER + 1));
+            hstep = fmin(fmin(100.0*h0, h1), tend);
+            fresh = false;
+        }
+        // clip to the end of the domain / next output point
+        double hlim = tend - t;
+        if (!a.dense && next_e < a.n_eval) hlim = a.z_eval[next_e] - t;
+        const bool clipped = hstep*1.01 >= hlim;
+        const double hh = clipped ? hlim : hstep;
+
+        // W = I/(h*gamma) - J, LU with partial pivoting (row permutation kept in registers)
+        const double dg = 1.0/(hh*RMT_ROS_GAMMA);
+#pragma unroll
+        for (int i = 0; i < RMT_N; ++i)
+#pragma unroll
+            for (int j = 0; j < RMT_N; ++j) LU(i, j) = (i == j ? dg : 0.0) - LU(i, j);
+        int perm[RMT_N];
+#pragma unroll
+        for (int i = 0; i < RMT_N; ++i) perm[i] = i;
+#pragma unroll
+        for (int k = 0; k < RMT_N; ++k) {
+            double best = fabs(LU(perm[k], k));
+            int bi = k;
+#pragma unroll
+            for (int i = k + 1; i < RMT_N; ++i) {
+                const double v = fabs(LU(perm[i], k));
+                if (v > best) { best = v; bi = i; }
+            }
+#pragma unroll
+            for (int i = k + 1; i < RMT_N; ++i)
+                if (i == bi) { const int tp = perm[k]; perm[k] = perm[i]; perm[i] = tp; }
+            const int pk = perm[k];
+            const double piv = 1.0/LU(pk, k);
+            LU(pk, k) = piv;                                  // store reciprocal pivot
+            double urow[RMT_N];
+#pragma unroll
+            for (int j = k + 1; j < RMT_N; ++j) urow[j] = LU(pk, j);
+#pragma unroll
+            for (int i = k + 1; i < RMT_N; ++i) {
+                const int pi = perm[i];
+                const double l = LU(pi, k)*piv;
+                LU(pi, k) = l;
+#pragma unroll
+                for (int j = k + 1; j < RMT_N; ++j) LU(pi, j) -= l*urow[j];
+            }
+        }
+
+        // stages
+        double ynew[RMT_N], errv[RMT_N];
+#pragma unroll
+        for (int i = 0; i < RMT_N; ++i) { ynew[i] = y[i]; errv[i] = 0.0; }
+        const double invh = 1.0/hh;
+#pragma unroll
+        for (int s = 0; s < RMT_ROS_S; ++s) {
+            double rhs[RMT_N];
+            if (s == 0) {
+#pragma unroll
+                for (int i = 0; i < RMT_N; ++i) rhs[i] = f0[i];
+            } else {
+                double u[RMT_N];
+#pragma unroll
+                for (int i = 0; i < RMT_N; ++i) u[i] = y[i];
+#pragma unroll
+                for (int j = 0; j < s; ++j)
+                    if (RMT_ROS_A[s][j] != 0.0) {
+#pragma unroll
+                        for (int i = 0; i < RMT_N; ++i) u[i] += RMT_ROS_A[s][j]*KS(j, i);
+                    }
+                n1_eval<false>(u, h, rhs, NoJac());
+#pragma unroll
+                for (int j = 0; j < s; ++j)
+                    if (RMT_ROS_C[s][j] != 0.0) {
+                        const double cj = RMT_ROS_C[s][j]*invh;
+#pragma unroll
+                        for (int i = 0; i < RMT_N; ++i) rhs[i] += cj*KS(j, i);
+                    }
+            }
+            // solve W k = rhs : stash rhs in the K_s slot so the permuted access is an address, not a register index
+#pragma unroll
+            for (int i = 0; i < RMT_N; ++i) KS(s, i) = rhs[i];
+            double x[RMT_N];
+#pragma unroll
+            for (int i = 0; i < RMT_N; ++i) {
+                double v = KS(s, perm[i]);
+#pragma unroll
+                for (int j = 0; j < i; ++j) v -= LU(perm[i], j)*x[j];
+                x[i] = v;
+            }
+#pragma unroll
+            for (int i = RMT_N - 1; i >= 0; --i) {
+                double v = x[i];
+#pragma unroll
+                for (int j = i + 1; j < RMT_N; ++j) v -= LU(perm[i], j)*x[j];
+                x[i] = v*LU(perm[i], i);
+            }
+#pragma unroll
+            for (int i = 0; i < RMT_N; ++i) {
+                KS(s, i) = x[i];
+                if (RMT_ROS_M[s] != 0.0) ynew[i] += RMT_ROS_M[s]*x[i];
+                if (RMT_ROS_E[s] != 0.0) errv[i] += RMT_ROS_E[s]*x[i];
+            }
+        }
+
+        // error norm (scipy/integrate/_ivp/common.py:63-65 rms norm; radau.py scale)
+        double err = 0.0;
+        bool bad = false;
+#pragma unroll
+        for (int i = 0; i < RMT_N; ++i) {
+            const double sc = a.atol + a.rtol*fmax(fabs(y[i]), fabs(ynew[i]));
+            const double e = errv[i]/sc;
+            err += e*e;
+            bad = bad || !(fabs(ynew[i]) <= 1.7e308);
+        }
+        err = sqrt(err/RMT_N);
+        if (bad || !(err == err)) err = 1e30;
+
+        // step-size controller: Hairer-Wanner with Gustafsson's predictive correction
+        const double SAFE = 0.9, FAC1 = 5.0, FAC2 = 1.0/6.0;
+        double fac = fmax(FAC2, fmin(FAC1, pow(err, 1.0/(RMT_ROS_ORDER))/SAFE));
+        double hnew = hh/fac;
+        int fin = -1;
+        if (err <= 1.0) {
+            if (nacc > 0) {
+                double facgus = (hacc/hh)*pow(err*err/erracc, 1.0/(RMT_ROS_ORDER))/SAFE;
+                facgus = fmax(FAC2, fmin(FAC1, facgus));
+                fac = fmax(fac, facgus);
+                hnew = hh/fac;
+            }
+            hacc = hh; erracc = fmax(1e-2, err);
+            ++nacc; nanrej = 0;
+            const double tnew = clipped ? (a.dense || next_e >= a.n_eval ? tend : a.z_eval[next_e]) : t + hh;
+            // output points inside (t, tnew]
+            if (a.dense) {
+                while (next_e < a.n_eval && a.z_eval[next_e] <= tnew) {
+                    const double ze = a.z_eval[next_e];
+                    double v[RMT_N];
+                    if (ze >= tnew) {
+#pragma unroll
+                        for (int i = 0; i < RMT_N; ++i) v[i] = ynew[i];
+                    } else {
+                        const double th = (ze - t)*invh, th1 = 1.0 - th;
+#pragma unroll
+                        for (int i = 0; i < RMT_N; ++i) {
+                            double d2 = 0.0, d3 = 0.0;
+#pragma unroll
+                            for (int s = 0; s < RMT_ROS_S; ++s) {
+                                if (RMT_ROS_D[0][s] != 0.0) d2 += RMT_ROS_D[0][s]*KS(s, i);
+                                if (RMT_ROS_D[1][s] != 0.0) d3 += RMT_ROS_D[1][s]*KS(s, i);
+                            }
+                            v[i] = y[i]*th1 + th*(ynew[i] + th1*(d2 + th*d3));
+                        }
+                    }
+                    n1_write_point(a, h, inst, next_e, v);
+                    ++next_e;
+                }
+            } else if (clipped && next_e < a.n_eval) {
+                n1_write_point(a, h, inst, next_e, ynew);
+                ++next_e;
+            }
+            t = tnew;
+#pragma unroll
+            for (int i = 0; i < RMT_N; ++i) y[i] = ynew[i];
+            if (last_rejected) hnew = fmin(hnew, hh);
+            last_rejected = false;
+            // a clipped step says nothing about the step the error would allow
+            hstep = clipped ? fmax(hnew, hstep) : hnew;
+            if (t >= tend) fin = 0;
+            else if (nacc + nrej >= a.max_steps) fin = 1;
+        } else {
+            ++nrej;
+            if (err >= 1e29) { ++nanrej; hnew = hh*0.1; }
+            last_rejected = true;
+            hstep = hnew;
+            if (nacc + nrej >= a.max_steps) fin = 1;
+            else if (hstep < 1e-14*fmax(tend, 1.0)) fin = 2;
+            else if (nanrej > 30) fin = 3;
+        }
+        if (fin >= 0) {
+            a.status[inst] = fin;
+            a.stats[inst] = nacc; a.stats[a.B + inst] = nrej;
+            a.stats[2*a.B + inst] = (nacc + nrej)*(RMT_ROS_S - 1); a.stats[3*a.B + inst] = nacc + nrej;
+            if (fin != 0) {
+                // make failures loud in the data as well: NaN for every point not yet written
+                double v[RMT_N];
+#pragma unroll
+                for (int i = 0; i < RMT_N; ++i) v[i] = __longlong_as_double(0x7ff8000000000000LL);
+                const int rows = n1_out_rows(a.out_mode);
+                for (; next_e < a.n_eval; ++next_e) {
+                    double* o = a.out + ((i64)next_e*rows)*a.B + inst;
+                    for (int k = 0; k < rows; ++k) o[(i64)k*a.B] = v[0];
+                }
+            }
+            if (a.obj) {
+                double ob = 0.0;
+                if (fin == 0) {
+                    double S = 0.0, C[RMT_NC];
+#pragma unroll
+                    for (int k = 0; k < RMT_NC; ++k) { C[k] = y[k]*h.Cmax; S += C[k]; }
+#pragma unroll
+                    for (int k = 0; k < RMT_NC; ++k) { const double d = (C[k]/S - a.obj_ref[k])/a.obj_ref[k]; ob += d*d; }
+#if !RMT_ISO
+                    { const double d = ((y[RMT_IT]*h.Tf + h.Tf) - a.obj_ref[RMT_IT])/a.obj_ref[RMT_IT]; ob += d*d; }
+#endif
+                } else ob = __longlong_as_double(0x7ff0000000000000LL);
+                a.obj[inst] = ob;
+            }
+            inst = -1;
+        }
+    }
+}
+#endif  // RMT_MODEL_N1
+
+// ---------------------------------------------------------------------------------
+// deterministic objective reduction: per-block (sum, min, argmin) partials, then one
+// block folds the partials.  The cross-GPU step is an all-reduce of these 3 numbers.
+// ---------------------------------------------------------------------------------
+extern "C" __global__ void __launch_bounds__(256)
+rmt_reduce_partials(const double* __restrict__ v, const i64 n, const i64 index_offset,
+                    double* __restrict__ psum, double* __restrict__ pmin, i64* __restrict__ parg)
+{
+    __shared__ double ssum[256], smin[256];
+    __shared__ i64 sarg[256];
+    double s = 0.0, mn = __longlong_as_double(0x7ff0000000000000LL);
+    i64 am = -1;
+    for (i64 i = (i64)blockIdx.x*blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x*blockDim.x) {
+        const double x = v[i];
+        s += x;
+        if (x < mn) { mn = x; am = i + index_offset; }
+    }
+    ssum[threadIdx.x] = s; smin[threadIdx.x] = mn; sarg[threadIdx.x] = am;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w) {
+            ssum[threadIdx.x] += ssum[threadIdx.x + w];
+            const double o = smin[threadIdx.x + w];
+            const i64 oa = sarg[threadIdx.x + w];
+            if (o < smin[threadIdx.x] || (o == smin[threadIdx.x] && oa >= 0 && (sarg[threadIdx.x] < 0 || oa < sarg[threadIdx.x]))) {
+                smin[threadIdx.x] = o; sarg[threadIdx.x] = oa;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { psum[blockIdx.x] = ssum[0]; pmin[blockIdx.x] = smin[0]; parg[blockIdx.x] = sarg[0]; }
+}
+
+// ---------------------------------------------------------------------------------
+// FP64 pipe peak: dependent-chain-free DFMA loop, used to measure the roofline
+// denominator on the box (MEASURED_PEAKS.json has no FP64 figure).
+// ---------------------------------------------------------------------------------
+extern "C" __global__ void __launch_bounds__(256) rmt_dfma_peak(double* __restrict__ out, const int iters, const double seed)
+{
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 0.999999, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[(i64)blockIdx.x*blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}

@@ -1,0 +1,185 @@
+"""Public API — same names, arguments and result layout as the reference's
+`PyREMOT/rmt.py` for the N1 / N2 branch of `rmtCoreClass.modExe`
+(PyREMOT/docs/rmtCore.py:124-127).
+
+    rmtExe(modelInput) -> {"resModel": dataPack | resPack, "comTime": float}
+    rmtCom()           -> "CO2,H2,CH3OH,..."
+
+`rmtExeBatch` is the ensemble extension: the same modelInput plus per-instance
+arrays for any operating / feed / reactor input or scalar VARS entry.
+"""
+from timeit import default_timer as timer
+
+import numpy as np
+
+from . import engine
+from .componentdb import componentSymbolList
+from .engine import solverSetting
+
+STATUS_TEXT = {0: "ok", 1: "max_steps reached", 2: "step size underflow", 3: "non-finite state"}
+
+
+def _component_list(FeCom):
+    """rmtUtility.buildComponentList (docs/rmtUtility.py:313-340)."""
+    comp = []
+    for part in ("shell", "tube", "medium"):
+        v = FeCom.get(part)
+        if v:
+            comp.extend(v)
+    return list(dict.fromkeys(comp))
+
+
+def _check_components(modelInput):
+    for c in _component_list(modelInput['feed']['components']):
+        if c not in componentSymbolList:
+            raise Exception("Component database is not up to date!")      # rmt.py:55-57
+
+
+def rmtExe(modelInput):
+    """Drop-in for PyREMOT.rmtExe (rmt.py:21-80) on models "N1" and "N2"."""
+    try:
+        tic = timer()
+        modelType = modelInput['model']
+        _check_components(modelInput)
+        if modelType == "N1":
+            resModel = _runN1(modelInput)
+        elif modelType == "N2":
+            resModel = _runN2(modelInput)
+        else:
+            raise NotImplementedError(
+                "model %r: this build accelerates the pseudo-homogeneous packed-bed models N1/N2 only" % (modelType,))
+        return {"resModel": resModel, "comTime": (timer() - tic)*1000}
+    except Exception as e:
+        print(e)
+        raise
+
+
+def rmtCom():
+    """rmt.py:83-92."""
+    return ",".join(componentSymbolList)
+
+
+def _display(modelInput):
+    return modelInput.get('solver-config', {}).get('display-result', "False") == "True"
+
+
+def _runN1(modelInput):
+    """runN1 (pbHomoReactor.py:2694-3015): one reactor, 101 output points."""
+    start = timer()
+    cm = engine.compile_model(modelInput)
+    spec = cm.spec
+    nc, n = spec.nc, spec.n
+    times = np.linspace(0, 1, solverSetting['N1']['zNo'] + 1)                # :2858-2862
+    res = engine.n1_solve_ensemble(cm, modelInput, None, 1, z_eval=times, out_mode=2)
+    if int(res.status[0]) != 0:
+        print('ODE Error')                                                    # :2944-2947
+        raise RuntimeError("ODE Error: integrator status %d (%s)" % (res.status[0], STATUS_TEXT.get(int(res.status[0]))))
+    o = res.out[:, :, 0].T                       # [rows][n_eval]
+    raw, C, allv = o[:n], o[n:n + nc], o[n + nc:]
+    ncol = times.size
+    processType = modelInput['operating-conditions']['process-type']
+    labelList = list(spec.compList) + ["Pressure"] + ([] if spec.iso else ["Temperature"])
+    Td = raw[nc + 1, :] if not spec.iso else np.repeat(0, ncol).reshape(ncol)
+    Tr = (allv[nc + 1, :] if not spec.iso else np.repeat(float(modelInput['operating-conditions']['temperature']), ncol)
+          ).reshape(1, ncol)
+    dataPack = [{
+        "modelId": modelInput['model'],
+        "processType": processType,
+        "successStatus": True,
+        "computation-time": np.round(timer() - start, 3),
+        "dataShape": times.shape,
+        "labelList": labelList,
+        "indexList": [nc, nc, nc + 1],
+        "dataTime": [],
+        "dataXs": times,
+        "dataYCons1": raw[0:nc, :],
+        "dataYCons2": C,
+        "dataYTemp1": Td,
+        "dataYTemp2": Tr,
+        "dataYs": allv,
+        "solverStats": {k: int(v) for k, v in zip(("accepted", "rejected", "nfev", "njev"), res.stats[:, 0])},
+    }]
+    if _display(modelInput):
+        from .plotting import plotResultsSteadyState
+        plotResultsSteadyState(dataPack)
+    return dataPack
+
+
+def _runN2(modelInput):
+    from .engine import n2_solve_ensemble
+    start = timer()
+    cm = engine.compile_model(modelInput)
+    spec = cm.spec
+    nc, n = spec.nc, spec.n
+    zNo, tNo = solverSetting['N2']['zNo'], solverSetting['N2']['tNo']
+    opT = modelInput['operating-conditions']['period']
+    res = n2_solve_ensemble(cm, modelInput, None, 1, zNo=zNo, tNo=tNo, period=opT, out_mode=2)
+    if int(res.status[0]) != 0:
+        raise RuntimeError("ODE Error: integrator status %d (%s)" % (res.status[0], STATUS_TEXT.get(int(res.status[0]))))
+    opTSpan = np.linspace(0, opT, tNo + 1)
+    dataXs = np.linspace(0, 1, zNo)
+    processType = modelInput['operating-conditions']['process-type']
+    dataPack = []
+    for i in range(tNo):
+        o = res.out[i, :, :, 0]                 # [rows][zNo]
+        raw, C, allv = o[:n], o[n:n + nc], o[n + nc:]
+        dataPack.append({
+            "modelId": modelInput['model'],
+            "processType": processType,
+            "successStatus": True,
+            "dataShape": np.array(opTSpan[i + 1]).shape,
+            "labelList": list(spec.compList) + ["Temperature"],
+            "indexList": [nc, nc + 1, nc],
+            "dataTime": opTSpan[i + 1],
+            "dataXs": dataXs,
+            "dataYCons1": raw[:-1] if not spec.iso else raw[:-1],       # :3638 (kept, incl. the iso slicing quirk)
+            "dataYCons2": C,
+            "dataYTemp1": raw[-1] if not spec.iso else np.repeat(0, zNo).reshape(zNo),
+            "dataYTemp2": allv[-1].reshape(1, zNo) if not spec.iso else np.repeat(
+                float(modelInput['operating-conditions']['temperature']), zNo).reshape(1, zNo),
+            "dataYs": allv,
+        })
+    resPack = {"computation-time": np.round(timer() - start, 3), "dataPack": dataPack}
+    if _display(modelInput):
+        from .plotting import plotResultsDynamic
+        plotResultsDynamic(resPack, tNo)
+    return resPack
+
+
+def rmtExeBatch(modelInput, sweep=None, B=None, *, rtol=None, atol=None, profile=False, z_eval=None,
+                objective_ref=None, dense=True, max_steps=100000, keep_on_device=False):
+    """Ensemble form of rmtExe for model "N1": B independent reactors that share
+    `modelInput` except for the per-instance arrays in `sweep` (keys:
+    "temperature", "pressure", "concentration" [B, nc], "volumetric-flowrate",
+    "ReInDi", "ReLe", "PaDi", "BeVoFr", "OvHeTrCo", "MeTe", or any scalar VARS name).
+
+    Returns {"dataYs": [B, n] outlet (or [B, n, n_eval] with profile/z_eval),
+             "status": [B], "success": [B] bool, "stats": [4, B], "dataXs": z_eval,
+             "objective": [B] or None, "comTime": ms}.
+    Failed instances are flagged in `status` and never abort the ensemble."""
+    tic = timer()
+    _check_components(modelInput)
+    if modelInput['model'] != "N1":
+        raise NotImplementedError("rmtExeBatch covers model N1; use rmtExeBatchN2 for the dynamic model")
+    if B is None:
+        if not sweep:
+            raise ValueError("give B or a non-empty sweep")
+        first = next(iter(sweep.values()))
+        B = int(np.asarray(first).shape[0])
+    cm = engine.compile_model(modelInput)
+    if z_eval is None:
+        z_eval = np.linspace(0, 1, solverSetting['N1']['zNo'] + 1) if profile else np.array([1.0])
+    res = engine.n1_solve_ensemble(cm, modelInput, sweep, B, z_eval=z_eval, rtol=rtol, atol=atol, out_mode=1,
+                                   dense=dense, max_steps=max_steps, objective_ref=objective_ref,
+                                   keep_on_device=keep_on_device)
+    if keep_on_device:
+        out = res.out.permute(2, 1, 0)
+        data = out[:, :, 0] if out.shape[2] == 1 else out
+        success = res.status == 0
+    else:
+        out = np.transpose(res.out, (2, 1, 0))           # [B][n][n_eval]
+        data = out[:, :, 0] if out.shape[2] == 1 else out
+        success = res.status == 0
+    return {"dataYs": data, "status": res.status, "success": success, "stats": res.stats, "dataXs": res.z_eval,
+            "objective": res.objective, "labelList": list(cm.spec.compList) + ["Pressure"] + (
+                [] if cm.spec.iso else ["Temperature"]), "comTime": (timer() - tic)*1000}

@@ -1,0 +1,89 @@
+"""Rosenbrock tableaux used by the device integrators.
+
+Single source of truth: `codegen.py` emits these numbers as `constexpr`
+arrays into the CUDA translation unit, `tests/test_tableau.py` checks order of
+convergence, stiff accuracy and the dense-output polynomial numerically.
+
+Formulation (Hairer & Wanner, "Solving ODEs II", IV.7, the form implemented in
+their RODAS code), autonomous y' = f(y), J = f'(y_n):
+
+    (I/(h*gamma) - J) k_i = f(y_n + sum_{j<i} a_ij k_j) + sum_{j<i} (c_ij/h) k_j
+    y_{n+1} = y_n + sum_i m_i k_i ,   err = sum_i e_i k_i
+
+The reactor models are autonomous in the integration variable (no explicit z
+or t in modelEquationN1/N2, PyREMOT/docs/pbHomoReactor.py:3017, :3706), so the
+c_i / d_i time-derivative coefficients of the non-autonomous form are not
+needed.
+
+Dense output (RODAS form), s = (x - x_n)/h:
+    y(x) = y_n (1-s) + s ( y_{n+1} + (1-s) ( D2 + s D3 ) ),  Dq = sum_i d_qi k_i
+"""
+
+RODAS4 = {
+    "name": "rodas4",
+    "stages": 6,
+    "order": 4,
+    "gamma": 0.25,
+    # a[i][j], i = 1..5 (0-based row i = stage i+1), strictly lower
+    "a": [
+        [],
+        [0.1544000000000000e+01],
+        [0.9466785280815826e+00, 0.2557011698983284e+00],
+        [0.3314825187068521e+01, 0.2896124015972201e+01, 0.9986419139977817e+00],
+        [0.1221224509226641e+01, 0.6019134481288629e+01, 0.1253708332932087e+02, -0.6878860361058950e+00],
+        # stage 6 argument = stage-5 argument + k5
+        [0.1221224509226641e+01, 0.6019134481288629e+01, 0.1253708332932087e+02, -0.6878860361058950e+00, 1.0],
+    ],
+    "c": [
+        [],
+        [-0.5668800000000000e+01],
+        [-0.2430093356833875e+01, -0.2063599157091915e+00],
+        [-0.1073529058151375e+00, -0.9594562251023355e+01, -0.2047028614809616e+02],
+        [0.7496443313967647e+01, -0.1024680431464352e+02, -0.3399990352819905e+02, 0.1170890893206160e+02],
+        [0.8083246795921522e+01, -0.7981132988064893e+01, -0.3152159432874371e+02, 0.1631930543123136e+02,
+         -0.6058818238834054e+01],
+    ],
+    # y_{n+1} = (stage-6 argument) + k6
+    "m": [0.1221224509226641e+01, 0.6019134481288629e+01, 0.1253708332932087e+02, -0.6878860361058950e+00, 1.0, 1.0],
+    "e": [0.0, 0.0, 0.0, 0.0, 0.0, 1.0],
+    "dense": [
+        [0.1012623508344586e+02, -0.7487995877610167e+01, -0.3480091861555747e+02, -0.7992771707568823e+01,
+         0.1025137723295662e+01, 0.0],
+        [-0.6762803392801253e+00, 0.6087714651680015e+01, 0.1643084320892478e+02, 0.2476722511418386e+02,
+         -0.6594389125716872e+01, 0.0],
+    ],
+}
+
+TABLEAUX = {"rodas4": RODAS4}
+
+
+def reference_step(tab, f, jac, y, h):
+    """NumPy statement of one step (used by tests and by the host-side
+    documentation of the kernel; the device code is generated from the same
+    coefficient tables).  Returns (y_new, err, K)."""
+    import numpy as np
+    n = len(y)
+    s = tab["stages"]
+    W = np.eye(n)/(h*tab["gamma"]) - jac(y)
+    K = []
+    for i in range(s):
+        yi = np.array(y, dtype=float)
+        for j in range(len(tab["a"][i])):
+            yi = yi + tab["a"][i][j]*K[j]
+        rhs = np.array(f(yi), dtype=float)
+        for j in range(len(tab["c"][i])):
+            rhs = rhs + (tab["c"][i][j]/h)*K[j]
+        K.append(np.linalg.solve(W, rhs))
+    ynew = np.array(y, dtype=float)
+    err = np.zeros(n)
+    for i in range(s):
+        ynew = ynew + tab["m"][i]*K[i]
+        err = err + tab["e"][i]*K[i]
+    return ynew, err, K
+
+
+def dense_eval(tab, y0, y1, K, s):
+    import numpy as np
+    D2 = sum(d*k for d, k in zip(tab["dense"][0], K))
+    D3 = sum(d*k for d, k in zip(tab["dense"][1], K))
+    return np.asarray(y0)*(1 - s) + s*(np.asarray(y1) + (1 - s)*(D2 + s*D3))

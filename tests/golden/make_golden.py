@@ -1,0 +1,280 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under tests/golden/ by RUNNING THE REFERENCE.
+
+The reference (PyREMOT, /root/reference) is imported unmodified — with a stub
+`matplotlib` because the image has none and every model module imports it at
+import time (PyREMOT/library/plot.py:7) — and driven through its own public
+entry point `rmtExe` (PyREMOT/rmt.py:21).  `scipy.integrate.solve_ivp` as seen
+by `PyREMOT/docs/pbHomoReactor.py` is wrapped so we can (i) capture the RHS
+callable + paramsSet the reference builds, (ii) inject rtol/atol/method, and
+(iii) record nfev/njev.  Nothing from the reference is copied into the repo:
+only numbers it produced.
+
+This script can only run where /root/reference exists (the build container);
+the GPU box consumes the committed .npz files.
+
+usage: python tests/golden/make_golden.py <part> [...]
+parts: n1 corners n2rhs n2sol_ch4 n2sol_m20_lsoda n2sol_m20_bdf n2sol_m50_bdf
+       n2sol_m20_tight all_fast
+"""
+import io
+import os
+import sys
+import time
+import types
+import contextlib
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+import cases  # noqa: E402
+
+REF_ROOT = os.environ.get("RMT_REFERENCE", "/root/reference")
+
+
+def load_reference():
+    for n in ("matplotlib", "matplotlib.pyplot"):
+        m = types.ModuleType(n)
+        m.__getattr__ = lambda k: (lambda *a, **kw: None)
+        sys.modules.setdefault(n, m)
+    if REF_ROOT not in sys.path:
+        sys.path.insert(0, REF_ROOT)
+    warnings.simplefilter("ignore")
+    import PyREMOT  # noqa
+    import PyREMOT.docs.pbHomoReactor as H
+    from PyREMOT.solvers import solverSetting
+    H.printProgressBar = lambda *a, **k: None
+    return PyREMOT, H, solverSetting
+
+
+class Capture:
+    """Wraps the solve_ivp symbol inside pbHomoReactor."""
+
+    def __init__(self, H, **inject):
+        self.H = H
+        self.inject = inject
+        self.calls = []
+        self._orig = H.solve_ivp
+
+    def __enter__(self):
+        def patched(fun, t_span, y0, **kw):
+            kw = dict(kw)
+            kw.update(self.inject)
+            sol = self._orig(fun, t_span, y0, **kw)
+            self.calls.append(dict(fun=fun, t_span=np.array(t_span, float), y0=np.array(y0, float),
+                                   args=kw.get("args"), nfev=sol.nfev, njev=sol.njev,
+                                   nlu=sol.nlu, t=sol.t, y=sol.y, method=kw.get("method")))
+            return sol
+        self.H.solve_ivp = patched
+        return self
+
+    def __exit__(self, *a):
+        self.H.solve_ivp = self._orig
+
+
+def run_ref(PyREMOT, mi):
+    buf = io.StringIO()
+    t0 = time.perf_counter()
+    with contextlib.redirect_stdout(buf):
+        res = PyREMOT.rmtExe(mi)
+    return res, time.perf_counter() - t0
+
+
+def consts_from_params(paramsSet):
+    """Flatten the numeric constants of the reference's paramsSet tuple."""
+    FunParam, DA = paramsSet[2], paramsSet[3]
+    out = {}
+    for k in ("CrSeAr", "GaMiVi", "varNo"):
+        out["const_" + k] = np.array(FunParam["const"][k], dtype=float)
+    out["const_StHeRe25"] = np.array(FunParam["const"]["StHeRe25"], float)
+    out["const_MoWei"] = np.array(FunParam["const"]["MoWei"], float)
+    for k in ("SpCo0", "GaDe0", "GaCpMeanMix0", "P0", "T0", "VoFlRa0"):
+        out["bc_" + k] = np.array(FunParam["constBC1"][k], float)
+    out["bc_SpCoi0"] = np.array(FunParam["constBC1"]["SpCoi0"], float)
+    for k in ("Cf", "Tf", "Pf", "vf", "zf", "Cpf", "GaHeCoTe0"):
+        out["da_" + k] = np.array(DA[k], float)
+    for k in ("Cif", "Cpif", "GaMaCoTe0"):
+        out["da_" + k] = np.array(DA[k], float)
+    out["exhe_EfHeTrAr"] = np.array(FunParam["ExHe"]["EfHeTrAr"], float)
+    return out
+
+
+def n1_case_inputs():
+    return {
+        "methanol_readme": cases.methanol_readme_input("N1"),
+        "methanol_testfile": cases.methanol_testfile_input("N1"),
+        "ch4_noniso": cases.ch4_input("N1", "non-iso-thermal"),
+        "ch4_iso": cases.ch4_input("N1", "iso-thermal"),
+    }
+
+
+def part_n1():
+    PyREMOT, H, _ = load_reference()
+    rng = np.random.default_rng(7)
+    out = {}
+    for name, mi in n1_case_inputs().items():
+        # default tolerance, each solver
+        for meth in ("default", "BDF", "Radau"):
+            mi["solver-config"]["ivp"] = meth
+            with Capture(H) as cap:
+                res, wall = run_ref(PyREMOT, mi)
+            c = cap.calls[0]
+            dp = res["resModel"][0]
+            tag = f"{name}__{meth}"
+            out[tag + "__dataYs"] = np.array(dp["dataYs"])
+            out[tag + "__soly"] = np.array(c["y"])
+            out[tag + "__nfev_njev_wall"] = np.array([c["nfev"], c["njev"], wall])
+            if meth == "default":
+                out[name + "__dataXs"] = np.array(dp["dataXs"])
+                out[name + "__dataYCons1"] = np.array(dp["dataYCons1"])
+                out[name + "__dataYCons2"] = np.array(dp["dataYCons2"])
+                out[name + "__dataYTemp1"] = np.array(dp["dataYTemp1"])
+                out[name + "__dataYTemp2"] = np.array(dp["dataYTemp2"])
+                out[name + "__labelList"] = np.array(dp["labelList"])
+                out[name + "__indexList"] = np.array(dp["indexList"])
+                fun, ps, y0, traj = c["fun"], c["args"][0], c["y0"], c["y"]
+        mi["solver-config"]["ivp"] = "default"
+        # tight tolerance
+        for meth in ("LSODA", "BDF"):
+            with Capture(H, rtol=1e-10, atol=1e-12, method=meth) as cap:
+                res, wall = run_ref(PyREMOT, mi)
+            c = cap.calls[0]
+            tag = f"{name}__tight_{meth}"
+            out[tag + "__dataYs"] = np.array(res["resModel"][0]["dataYs"])
+            out[tag + "__soly"] = np.array(c["y"])
+            out[tag + "__nfev_njev_wall"] = np.array([c["nfev"], c["njev"], wall])
+        # RHS known answers: feed state, trajectory states, random perturbations
+        idx = [0, 1, 2, 3, 5, 10, 25, 50, 75, 100]
+        Y = [y0] + [traj[:, i] for i in idx[1:]]
+        for i in idx:
+            for _ in range(3):
+                Y.append(traj[:, i]*(1 + 0.05*rng.uniform(-1, 1, traj.shape[0])))
+        Y = np.array(Y)
+        F = np.array([fun(0.0, list(y), ps) for y in Y])
+        out[name + "__rhs_Y"] = Y
+        out[name + "__rhs_F"] = F
+        for k, v in consts_from_params(ps).items():
+            out[name + "__" + k] = v
+        print(name, "done", flush=True)
+    # rates known answer (SURVEY App. B.2 last entry) through the reference's reactionRateExe
+    from PyREMOT.docs.rmtReaction import reactionRateExe
+    y = np.array([0.45, 0.26, 0.024, 0.24, 0.007, 0.016]); y = y/y.sum()
+    kin = cases.methanol_kinetics(1982*(1 - 0.39))
+    Pt, Tt = 4.99e6, 620.0
+    C = y*Pt/(cases.R_CONST*Tt)
+    out["rates_ka__inputs"] = np.concatenate([[Tt, Pt], y, C])
+    out["rates_ka__R"] = np.array(reactionRateExe((Tt, Pt, y, C), kin["VARS"], kin["RATES"]))
+    import scipy
+    out["versions"] = np.array([np.__version__, scipy.__version__, sys.version.split()[0]])
+    np.savez_compressed(os.path.join(HERE, "n1_reference.npz"), **out)
+
+
+def part_corners():
+    PyREMOT, H, _ = load_reference()
+    base = cases.methanol_readme_input("N1")
+    sweep = cases.config3_corners()
+    B = len(sweep["temperature"])
+    dflt, tight, stats = [], [], []
+    for i in range(B):
+        mi = cases.instance_input(base, sweep, i)
+        with Capture(H) as cap:
+            res, wall = run_ref(PyREMOT, mi)
+        dflt.append(np.array(res["resModel"][0]["dataYs"]))
+        c0 = cap.calls[0]
+        with Capture(H, rtol=1e-10, atol=1e-12, method="LSODA") as cap:
+            res, wall_t = run_ref(PyREMOT, mi)
+        tight.append(np.array(res["resModel"][0]["dataYs"]))
+        stats.append([c0["nfev"], c0["njev"], wall, cap.calls[0]["nfev"], wall_t])
+        print("corner", i, stats[-1], flush=True)
+    np.savez_compressed(os.path.join(HERE, "n1_corners_reference.npz"),
+                        default_dataYs=np.array(dflt), tight_dataYs=np.array(tight),
+                        stats=np.array(stats), **{"sweep_" + k: v for k, v in sweep.items()})
+
+
+def _capture_n2(PyREMOT, H, mi, **inject):
+    with Capture(H, **inject) as cap:
+        res, wall = run_ref(PyREMOT, mi)
+    return res, wall, cap.calls
+
+
+def part_n2rhs():
+    from scipy.integrate import solve_ivp
+    PyREMOT, H, solverSetting = load_reference()
+    rng = np.random.default_rng(11)
+    out = {}
+    # capture by letting the reference run with a 1e-9 s period (cheap) so runN2 builds paramsSet
+    for name, mi, zNo in (("methanol_testfile_z20", cases.methanol_testfile_input("N2"), 20),
+                          ("methanol_readme_z50", cases.methanol_readme_input("N2"), 50),
+                          ("ch4_z20", cases.ch4_input("N2"), 20)):
+        solverSetting['N2']['zNo'] = zNo
+        mi["operating-conditions"]["period"] = 1e-9
+        res, wall, calls = _capture_n2(PyREMOT, H, mi)
+        fun, ps, y0 = calls[0]["fun"], calls[0]["args"][0], calls[0]["y0"]
+        # a real mid-transient state: integrate the captured reference RHS for a short time
+        tmid = 0.05 if "ch4" not in name else 2.0
+        sol = solve_ivp(fun, [0, tmid], y0, method="BDF", args=(ps,), rtol=1e-5, atol=1e-8)
+        ymid = sol.y[:, -1]
+        Y = [y0, ymid, sol.y[:, len(sol.t)//2]]
+        for base in (y0, ymid):
+            for _ in range(3):
+                Y.append(base*(1 + 0.05*rng.uniform(-1, 1, base.size)) + 1e-4*rng.uniform(0, 1, base.size))
+        # clamp exercise: a few non-positive concentrations
+        yneg = ymid.copy(); yneg[2*zNo + 3] = -1e-7; yneg[4*zNo + 5] = 0.0
+        Y.append(yneg)
+        Y = np.array(Y)
+        F = np.array([fun(0.0, y, ps) for y in Y])
+        out[name + "__rhs_Y"] = Y
+        out[name + "__rhs_F"] = F
+        out[name + "__zNo"] = np.array(zNo)
+        print(name, "rhs done", sol.nfev, flush=True)
+    solverSetting['N2']['zNo'] = 20
+    np.savez_compressed(os.path.join(HERE, "n2_rhs_reference.npz"), **out)
+
+
+def _n2_pack(res, calls, wall):
+    dps = res["resModel"]["dataPack"]
+    return dict(dataYs=np.array([d["dataYs"] for d in dps]),
+                dataTime=np.array([d["dataTime"] for d in dps]),
+                dataXs=np.array(dps[0]["dataXs"]),
+                soly_last=np.array([c["y"][:, -1] for c in calls]),
+                nfev=np.array([c["nfev"] for c in calls]), njev=np.array([c["njev"] for c in calls]),
+                wall=np.array(wall))
+
+
+def part_n2sol(which):
+    PyREMOT, H, solverSetting = load_reference()
+    cfg = {
+        "ch4": ("ch4", 20, {}, "n2_sol_ch4_reference.npz"),
+        "ch4_tight": ("ch4", 20, dict(rtol=1e-10, atol=1e-12, method="LSODA"), "n2_sol_ch4_tight_reference.npz"),
+        "m20_lsoda": ("methanol_testfile", 20, {}, "n2_sol_m20_lsoda_reference.npz"),
+        "m20_bdf": ("methanol_testfile", 20, dict(method="BDF"), "n2_sol_m20_bdf_reference.npz"),
+        "m50_bdf": ("methanol_readme", 50, dict(method="BDF"), "n2_sol_m50_bdf_reference.npz"),
+        "m20_tight": ("methanol_testfile", 20, dict(method="BDF", rtol=1e-8, atol=1e-10), "n2_sol_m20_tight_reference.npz"),
+        "mr20_lsoda": ("methanol_readme", 20, {}, "n2_sol_mr20_lsoda_reference.npz"),
+    }[which]
+    name, zNo, inject, fname = cfg
+    mi = {"ch4": cases.ch4_input, "methanol_testfile": cases.methanol_testfile_input,
+          "methanol_readme": cases.methanol_readme_input}[name]("N2")
+    solverSetting['N2']['zNo'] = zNo
+    res, wall, calls = _capture_n2(PyREMOT, H, mi, **inject)
+    solverSetting['N2']['zNo'] = 20
+    out = _n2_pack(res, calls, wall)
+    out["zNo"] = np.array(zNo)
+    print(which, "wall", wall, "nfev", out["nfev"], flush=True)
+    np.savez_compressed(os.path.join(HERE, fname), **out)
+
+
+if __name__ == "__main__":
+    for part in sys.argv[1:]:
+        if part == "n1":
+            part_n1()
+        elif part == "corners":
+            part_corners()
+        elif part == "n2rhs":
+            part_n2rhs()
+        elif part.startswith("n2sol_"):
+            part_n2sol(part[len("n2sol_"):])
+        else:
+            raise SystemExit("unknown part " + part)

@@ -108,11 +108,14 @@ int rmt_n1_jac(rmt_module_t m, int64_t B, const double* d_consts, const double* 
  * d_out [n_eval][rows][B], d_status [B], d_stats [4][B] = accepted steps, rejected
  * steps, RHS evaluations, Jacobian(+RHS) evaluations.
  * obj_ref (host, [n], may be NULL) + d_obj [B]: fused least-squares objective of
- * the outlet against obj_ref (parameter-estimation populations). */
+ * the outlet against obj_ref (parameter-estimation populations).
+ * ctrl (host, [6], may be NULL = defaults): step-size controller {safety, max
+ * shrink factor, max growth factor, kappa, PI beta, initial-step factor}; the error test is
+ * rms(err / (kappa*(atol + rtol*max(|y|,|y_new|)))) <= 1. */
 int rmt_n1_solve(rmt_module_t m, int64_t B, const double* d_consts, int32_t n_eval, const double* z_eval,
                  double rtol, double atol, int32_t max_steps, int32_t dense, int32_t out_mode,
                  double* d_out, int32_t* d_status, int32_t* d_stats,
-                 const double* obj_ref, double* d_obj, void* stream);
+                 const double* obj_ref, double* d_obj, const double* ctrl, void* stream);
 
 /* Same path with HOST buffers: copies inputs in, runs setup + solve, copies
  * results back, synchronises.  h_rows [n_rows][B], h_out [n_eval][rows][B]. */
@@ -120,7 +123,7 @@ int rmt_n1_solve_host(rmt_module_t m, int64_t B, const double* h_rows, int32_t n
                       const double* uniform, int32_t n_eval, const double* z_eval,
                       double rtol, double atol, int32_t max_steps, int32_t dense, int32_t out_mode,
                       double* h_out, int32_t* h_status, int32_t* h_stats,
-                      const double* obj_ref, double* h_obj);
+                      const double* obj_ref, double* h_obj, const double* ctrl);
 
 /* ---- N2: modelEquationN2 (:3706-4134) and the slab loop of runN2 (:3589-3685) ---
  * States are variable-major like the reference's reshape (:3873): d_y, d_f
@@ -139,6 +142,10 @@ int rmt_n2_solve(rmt_module_t m, int64_t B, int32_t zNo, int32_t tNo, double per
  * these three numbers, done by the caller's torch.distributed group) ------------- */
 int rmt_reduce_objective(rmt_module_t m, int64_t n, const double* d_obj, int64_t index_offset,
                          double* h_sum, double* h_min, int64_t* h_argmin, void* stream);
+
+/* ---- diagnostics: log the step sequence of one instance of the next N1 solves:
+ * d_trace [cap][4] = (t, h, err, accepted) per attempt; NULL switches it off. ------ */
+int rmt_debug_trace(double* d_trace, int32_t cap, int64_t instance);
 
 /* ---- measurement helper: FP64 FMA throughput of the device (TFLOP/s) ------------ */
 int rmt_fp64_peak(rmt_module_t m, int32_t iters, int32_t repeats, double* tflops_out);

@@ -52,13 +52,14 @@ SIGNATURES = {
     "rmt_n1_rhs": (C.c_int, [_u64, _i64, _vp, _vp, _vp, _vp]),
     "rmt_n1_jac": (C.c_int, [_u64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "rmt_n1_solve": (C.c_int, [_u64, _i64, _vp, _i32, _pdbl, _dbl, _dbl, _i32, _i32, _i32, _vp, _vp, _vp, _pdbl,
-                               _vp, _vp]),
+                               _vp, _pdbl, _vp]),
     "rmt_n1_solve_host": (C.c_int, [_u64, _i64, _vp, _i32, _pi32, _pdbl, _i32, _pdbl, _dbl, _dbl, _i32, _i32, _i32,
-                                    _vp, _vp, _vp, _pdbl, _vp]),
+                                    _vp, _vp, _vp, _pdbl, _vp, _pdbl]),
     "rmt_n2_rhs": (C.c_int, [_u64, _i64, _i32, _vp, _vp, _vp, _vp]),
     "rmt_n2_work_doubles": (_i64, [_u64, _i64, _i32]),
     "rmt_n2_solve": (C.c_int, [_u64, _i64, _i32, _i32, _dbl, _vp, _dbl, _dbl, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "rmt_reduce_objective": (C.c_int, [_u64, _i64, _vp, _i64, _pdbl, _pdbl, C.POINTER(_i64), _vp]),
+    "rmt_debug_trace": (C.c_int, [_vp, _i32, _i64]),
     "rmt_fp64_peak": (C.c_int, [_u64, _i32, _i32, _pdbl]),
 }
 
@@ -95,6 +96,10 @@ def device_count():
     n = C.c_int(0)
     _check(lib().rmt_device_count(C.byref(n)))
     return n.value
+
+
+def debug_trace(d_trace, cap=0, instance=-1):
+    _check(lib().rmt_debug_trace(_ptr(d_trace), cap, instance))
 
 
 def kernels_source():
@@ -191,23 +196,28 @@ class Module:
         _check(lib().rmt_n1_jac(self.handle, B, _ptr(d_consts), _ptr(d_y), _ptr(d_f), _ptr(d_J), stream))
 
     def n1_solve(self, B, d_consts, z_eval, rtol, atol, d_out, d_status, d_stats, max_steps=100000, dense=True,
-                 out_mode=1, obj_ref=None, d_obj=None, stream=None):
+                 out_mode=1, obj_ref=None, d_obj=None, ctrl=None, stream=None):
         z = np.ascontiguousarray(z_eval, dtype=np.float64)
         ref = None if obj_ref is None else np.ascontiguousarray(obj_ref, dtype=np.float64)
+        ctl = None if ctrl is None else np.ascontiguousarray(ctrl, dtype=np.float64)
+        assert ctl is None or ctl.size == 6
         _check(lib().rmt_n1_solve(self.handle, B, _ptr(d_consts), z.size, _dptr(z), rtol, atol, max_steps,
                                   1 if dense else 0, out_mode, _ptr(d_out), _ptr(d_status), _ptr(d_stats),
-                                  None if ref is None else _dptr(ref), _ptr(d_obj), stream))
+                                  None if ref is None else _dptr(ref), _ptr(d_obj),
+                                  None if ctl is None else _dptr(ctl), stream))
 
     def n1_solve_host(self, B, h_rows, n_rows, row_map, uniform, z_eval, rtol, atol, h_out, h_status, h_stats=None,
-                      max_steps=100000, dense=True, out_mode=1, obj_ref=None, h_obj=None):
+                      max_steps=100000, dense=True, out_mode=1, obj_ref=None, h_obj=None, ctrl=None):
         row_map = np.ascontiguousarray(row_map, dtype=np.int32)
         uniform = np.ascontiguousarray(uniform, dtype=np.float64)
         z = np.ascontiguousarray(z_eval, dtype=np.float64)
         ref = None if obj_ref is None else np.ascontiguousarray(obj_ref, dtype=np.float64)
+        ctl = None if ctrl is None else np.ascontiguousarray(ctrl, dtype=np.float64)
         _check(lib().rmt_n1_solve_host(self.handle, B, _ptr(h_rows), n_rows, row_map.ctypes.data_as(_pi32),
                                        _dptr(uniform), z.size, _dptr(z), rtol, atol, max_steps, 1 if dense else 0,
                                        out_mode, _ptr(h_out), _ptr(h_status), _ptr(h_stats),
-                                       None if ref is None else _dptr(ref), _ptr(h_obj)))
+                                       None if ref is None else _dptr(ref), _ptr(h_obj),
+                                       None if ctl is None else _dptr(ctl)))
 
     def n2_rhs(self, B, zNo, d_consts, d_y, d_f, stream=None):
         _check(lib().rmt_n2_rhs(self.handle, B, zNo, _ptr(d_consts), _ptr(d_y), _ptr(d_f), stream))

@@ -173,6 +173,9 @@ def generate_model_header(spec, tableau="rodas4"):
     for k, v in dep.items():
         A("#define RMT_RATES_DEP_%s %d" % (k, 1 if v else 0))
 
+    pos = kin.positive_species()
+    A("// species that must stay > 0 for the traced kinetics to be defined (denominators, log, sqrt, pow)")
+    A("__device__ constexpr bool RMT_POSITIVE[RMT_NC] = %s;" % _arr(pos, fmt=lambda v: "true" if v else "false"))
     fl = model_flops(spec)
     A("// flops per evaluation at one axial point, recomputed from the traced DAG + the balance code")
     A("// (ALG: 1 per +,-,*,/,sqrt,exp,log,pow;  WT: FP64-instruction weighted, see expr.FLOP_WEIGHT)")

@@ -163,6 +163,15 @@ int scratch_get(Module* M, size_t bytes, CUdeviceptr* out)
     return 0;
 }
 
+// default step-size controller: safety, max shrink, max growth, tolerance scale kappa, PI beta,
+// initial-step factor (applied to the Hairer-Wanner starting step)
+const double RMT_DEFAULT_CTRL[6] = {0.8, 5.0, 6.0, 1.0, 0.08, 0.1};
+
+// diagnostics: step log of one instance (rmt_debug_trace)
+double* g_trace_buf = nullptr;
+long long g_trace_inst = -1;
+int g_trace_cap = 0;
+
 // kernel-parameter mirrors of the device structs in rmt_kernels.cu ---------------------
 struct SolveArgsN1 {
     CUdeviceptr consts;
@@ -174,8 +183,12 @@ struct SolveArgsN1 {
     int max_steps;
     int dense;
     CUdeviceptr out, status, stats, queue, obj_ref, obj;
+    double ctrl[6];
+    CUdeviceptr trace;
+    long long trace_inst;
+    int trace_cap;
 };
-static_assert(sizeof(SolveArgsN1) == 104, "SolveArgs layout");
+static_assert(sizeof(SolveArgsN1) == 176, "SolveArgs layout");
 
 struct SolveArgsN2 {
     CUdeviceptr consts;
@@ -470,7 +483,7 @@ int rmt_n1_jac(rmt_module_t m, int64_t B, const double* d_consts, const double* 
 int rmt_n1_solve(rmt_module_t m, int64_t B, const double* d_consts, int32_t n_eval, const double* z_eval,
                  double rtol, double atol, int32_t max_steps, int32_t dense, int32_t out_mode,
                  double* d_out, int32_t* d_status, int32_t* d_stats,
-                 const double* obj_ref, double* d_obj, void* stream)
+                 const double* obj_ref, double* d_obj, const double* ctrl, void* stream)
 {
     Module* M = get_module(m);
     if (!M) return fail("invalid module handle");
@@ -495,6 +508,11 @@ int rmt_n1_solve(rmt_module_t m, int64_t B, const double* d_consts, int32_t n_ev
     a.rtol = rtol; a.atol = atol; a.max_steps = max_steps > 0 ? max_steps : 100000; a.dense = dense ? 1 : 0;
     a.out = (CUdeviceptr)d_out; a.status = (CUdeviceptr)d_status; a.stats = (CUdeviceptr)d_stats; a.queue = scr;
     a.obj_ref = obj_ref ? scr + 64 + 8*(size_t)n_eval : 0; a.obj = (CUdeviceptr)d_obj;
+    a.trace = (CUdeviceptr)g_trace_buf; a.trace_inst = g_trace_inst; a.trace_cap = g_trace_cap;
+    for (int k = 0; k < 6; ++k) a.ctrl[k] = ctrl ? ctrl[k] : RMT_DEFAULT_CTRL[k];
+    if (!(a.ctrl[0] > 0.0 && a.ctrl[0] <= 1.0) || !(a.ctrl[1] > 1.0) || !(a.ctrl[2] > 1.0) || !(a.ctrl[3] > 0.0))
+        return fail("rmt_n1_solve: controller needs 0 < safety <= 1, max shrink > 1, max growth > 1, kappa > 0");
+    if (!(a.ctrl[5] > 0.0)) a.ctrl[5] = RMT_DEFAULT_CTRL[5];
     const int block = M->info.block;
     long long want = (B + block - 1)/block;
     long long cap = (long long)g_sm_count*M->solve_blocks_per_sm;
@@ -507,7 +525,7 @@ int rmt_n1_solve_host(rmt_module_t m, int64_t B, const double* h_rows, int32_t n
                       const double* uniform, int32_t n_eval, const double* z_eval,
                       double rtol, double atol, int32_t max_steps, int32_t dense, int32_t out_mode,
                       double* h_out, int32_t* h_status, int32_t* h_stats,
-                      const double* obj_ref, double* h_obj)
+                      const double* obj_ref, double* h_obj, const double* ctrl)
 {
     Module* M = get_module(m);
     if (!M) return fail("invalid module handle");
@@ -529,7 +547,7 @@ int rmt_n1_solve_host(rmt_module_t m, int64_t B, const double* h_rows, int32_t n
     if (n_rows > 0) CU(cuMemcpyHtoDAsync(d_rows, h_rows, bytes_rows, st));
     if (rmt_setup(m, B, (const double*)d_rows, n_rows, row_map, uniform, (double*)d_consts, st)) return 1;
     if (rmt_n1_solve(m, B, (const double*)d_consts, n_eval, z_eval, rtol, atol, max_steps, dense, out_mode,
-                     (double*)d_out, (int32_t*)d_status, (int32_t*)d_stats, obj_ref, (double*)d_obj, st)) return 1;
+                     (double*)d_out, (int32_t*)d_status, (int32_t*)d_stats, obj_ref, (double*)d_obj, ctrl, st)) return 1;
     CU(cuMemcpyDtoHAsync(h_out, d_out, bytes_out, st));
     CU(cuMemcpyDtoHAsync(h_status, d_status, 4*(size_t)B, st));
     if (h_stats) CU(cuMemcpyDtoHAsync(h_stats, d_stats, 16*(size_t)B, st));
@@ -618,6 +636,12 @@ int rmt_reduce_objective(rmt_module_t m, int64_t n, const double* d_obj, int64_t
     if (h_sum) *h_sum = s;
     if (h_min) *h_min = mn;
     if (h_argmin) *h_argmin = am;
+    return 0;
+}
+
+int rmt_debug_trace(double* d_trace, int32_t cap, int64_t instance)
+{
+    g_trace_buf = d_trace; g_trace_cap = d_trace ? cap : 0; g_trace_inst = d_trace ? instance : -1;
     return 0;
 }
 

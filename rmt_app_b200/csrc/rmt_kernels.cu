@@ -457,6 +457,13 @@ struct SolveArgs {
     // optional fused objective (parameter estimation): sum_k ((out_k - ref_k)/ref_k)^2 over the outlet
     const double* obj_ref;     // [N] or null
     double* obj;               // [B]
+    // step-size controller: safety, max shrink factor, max growth factor, tolerance scale kappa
+    // (error test uses kappa*(atol + rtol*|y|)), PI exponent beta (0 = Gustafsson only), initial-step factor
+    double ctrl[6];
+    // optional step log of one instance: rows of (t, h, err, accepted) — diagnostics only
+    double* trace;             // [trace_cap][4] or null
+    i64 trace_inst;
+    int trace_cap;
 };
 
 #define SM(slot) sm[(slot)*RMT_BLOCK]
@@ -558,7 +565,7 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
             double d0 = 0.0, d1 = 0.0, d2 = 0.0;
 #pragma unroll
             for (int i = 0; i < RMT_N; ++i) {
-                const double sc = a.atol + a.rtol*fabs(y[i]);
+                const double sc = a.ctrl[3]*(a.atol + a.rtol*fabs(y[i]));
                 double jf = 0.0;
 #pragma unroll
                 for (int j = 0; j < RMT_N; ++j) jf += LU(i, j)*f0[j];
@@ -568,7 +575,7 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
             const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01*d0/d1;
             const double dm = fmax(d1, d2);
             const double h1 = dm <= 1e-15 ? fmax(1e-6, h0*1e-3) : pow(0.01/dm, 1.0/(RMT_ROS_ORDER + 1));
-            hstep = fmin(fmin(100.0*h0, h1), tend);
+            hstep = fmin(a.ctrl[5]*fmin(100.0*h0, h1), tend);
             fresh = false;
         }
         // clip to the end of the domain / next output point
@@ -675,21 +682,36 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
         bool bad = false;
 #pragma unroll
         for (int i = 0; i < RMT_N; ++i) {
-            const double sc = a.atol + a.rtol*fmax(fabs(y[i]), fabs(ynew[i]));
+            const double sc = a.ctrl[3]*(a.atol + a.rtol*fmax(fabs(y[i]), fabs(ynew[i])));
             const double e = errv[i]/sc;
             err += e*e;
             bad = bad || !(fabs(ynew[i]) <= 1.7e308);
         }
         err = sqrt(err/RMT_N);
+        // domain guard: concentrations never change sign in the exact solution (a negative one can run away
+        // through second-order terms, e.g. -k*C^2); a species that sits in a denominator / log / sqrt of the
+        // kinetics must stay strictly positive.  A step that violates this is rejected like a failed error test.
+#pragma unroll
+        for (int i = 0; i < RMT_NC; ++i) bad = bad || (RMT_POSITIVE[i] ? !(ynew[i] > 0.0) : (ynew[i] < 0.0));
         if (bad || !(err == err)) err = 1e30;
 
         // step-size controller: Hairer-Wanner with Gustafsson's predictive correction
-        const double SAFE = 0.9, FAC1 = 5.0, FAC2 = 1.0/6.0;
-        double fac = fmax(FAC2, fmin(FAC1, pow(err, 1.0/(RMT_ROS_ORDER))/SAFE));
+        if (a.trace && inst == a.trace_inst && nacc + nrej < a.trace_cap) {
+            double* tr = a.trace + 4*(nacc + nrej);
+            tr[0] = t; tr[1] = hh; tr[2] = err; tr[3] = err <= 1.0 ? 1.0 : 0.0;
+        }
+        const double SAFE = a.ctrl[0], FAC1 = a.ctrl[1], FAC2 = 1.0/a.ctrl[2], BETA = a.ctrl[4];
+        const double errc = fmax(err, 1e-10);
+        double fac;
+        if (BETA > 0.0 && nacc > 0)            // PI controller (Gustafsson 1991): uses the previous accepted error
+            fac = pow(errc, 1.0/(RMT_ROS_ORDER) - 0.75*BETA)*pow(erracc, -BETA)/SAFE;   // note erracc^(-beta): small previous error -> grow
+        else
+            fac = pow(errc, 1.0/(RMT_ROS_ORDER))/SAFE;
+        fac = fmax(FAC2, fmin(FAC1, fac));
         double hnew = hh/fac;
         int fin = -1;
         if (err <= 1.0) {
-            if (nacc > 0) {
+            if (nacc > 0 && BETA <= 0.0) {
                 double facgus = (hacc/hh)*pow(err*err/erracc, 1.0/(RMT_ROS_ORDER))/SAFE;
                 facgus = fmax(FAC2, fmin(FAC1, facgus));
                 fac = fmax(fac, facgus);

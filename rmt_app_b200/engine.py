@@ -89,7 +89,9 @@ def uniform_inputs(spec, modelInput):
     vals = [float(oc["temperature"]), float(oc["pressure"])] + [float(c) for c in conc]
     vals += [float(feed["volumetric-flowrate"]), float(rs["ReInDi"]), float(rs["ReLe"]), float(rs["PaDi"]),
              float(rs["BeVoFr"]), float(eh["OvHeTrCo"]), float(eh["MeTe"])]
-    vals += [float(v) for v in spec.kin.param_defaults]
+    # scalar VARS entries of THIS modelInput (the compiled model is shared by every input with the same structure)
+    varis = modelInput["reaction-rates"]["VARS"]
+    vals += [float(varis[name]) for name in spec.kin.param_names]
     return np.array(vals, dtype=np.float64)
 
 
@@ -136,7 +138,7 @@ class N1Result:
 
 def n1_solve_ensemble(cm, modelInput, sweep=None, B=1, z_eval=None, rtol=None, atol=None, out_mode=1,
                       dense=True, max_steps=100000, objective_ref=None, device=None, keep_on_device=False,
-                      pinned=None):
+                      pinned=None, ctrl=None):
     """Solve B independent steady-state reactors on the current CUDA device.
 
     Returns an N1Result with out[n_eval][rows][B].  Raises capi.RmtError when the
@@ -174,7 +176,7 @@ def n1_solve_ensemble(cm, modelInput, sweep=None, B=1, z_eval=None, rtol=None, a
         d_obj = torch.empty((B,), dtype=torch.float64, device=dev) if objective_ref is not None else None
         mod.setup(B, d_rows, rows.shape[0], row_map, uniform, d_consts, stream=stream)
         mod.n1_solve(B, d_consts, z_eval, rtol, atol, d_out, d_status, d_stats, max_steps=max_steps, dense=dense,
-                     out_mode=out_mode, obj_ref=objective_ref, d_obj=d_obj, stream=stream)
+                     out_mode=out_mode, obj_ref=objective_ref, d_obj=d_obj, ctrl=ctrl, stream=stream)
         res = N1Result()
         res.z_eval, res.n, res.nc, res.out_mode, res.flops = z_eval, n, nc, out_mode, cm.flops
         if keep_on_device:

@@ -234,6 +234,40 @@ class KineticsIR:
         self.partials = out
         return out
 
+    def positive_species(self):
+        """Species whose concentration / mole fraction reaches a denominator, a
+        logarithm, a square root or a non-integer / negative power anywhere in
+        the rates: the kinetics are undefined (or change sign through a pole)
+        at non-positive values, so the integrator must keep them > 0 — in the
+        reference such a state raises (`math domain error`) or silently runs on
+        the wrong side of the pole."""
+        g = self.g
+        dep = {}
+        need = 0
+        for n in g.topo(self.rates):
+            if n.op == "in":
+                m = 0
+                if n.name[0] in "yC" and n.name[1:].isdigit():
+                    m = 1 << int(n.name[1:])
+                dep[n.id] = m
+                continue
+            if n.op == "const":
+                dep[n.id] = 0
+                continue
+            m = 0
+            for a in n.args:
+                m |= dep[a.id]
+            dep[n.id] = m
+            if n.op == "div":
+                need |= dep[n.args[1].id]
+            elif n.op in ("log", "log10", "log2", "sqrt", "log1p"):
+                need |= dep[n.args[0].id]
+            elif n.op == "pow":
+                need |= dep[n.args[0].id]
+            elif n.op == "powi" and n.value < 0:
+                need |= dep[n.args[0].id]
+        return [bool(need >> i & 1) for i in range(self.nc)]
+
     def evaluate(self, T, P, y, C, params=None):
         """Host interpreter of the traced rates (tests of the tracer only)."""
         env = {"T": T, "P": P}

@@ -221,7 +221,7 @@ def part_n2rhs():
             for _ in range(3):
                 Y.append(base*(1 + 0.05*rng.uniform(-1, 1, base.size)) + 1e-4*rng.uniform(0, 1, base.size))
         # clamp exercise: a few non-positive concentrations
-        yneg = ymid.copy(); yneg[2*zNo + 3] = -1e-7; yneg[4*zNo + 5] = 0.0
+        yneg = ymid.copy(); yneg[1*zNo + 3] = -1e-7; yneg[2*zNo + 5] = 0.0
         Y.append(yneg)
         Y = np.array(Y)
         F = np.array([fun(0.0, y, ps) for y in Y])
@@ -266,12 +266,41 @@ def part_n2sol(which):
     np.savez_compressed(os.path.join(HERE, fname), **out)
 
 
+def part_props():
+    """Component-table known answers: Cp_i(T), viscosity_i(T), dHf25, MW for all 12 species,
+    Wilke mixture viscosity and reaction parsing, straight from the reference's helpers."""
+    PyREMOT, H, _ = load_reference()
+    from PyREMOT.docs.rmtThermo import calHeatCapacityAtConstantPressure, calStandardEnthalpyOfReaction
+    from PyREMOT.docs.gasTransPor import calGasViscosity, calMixturePropertyM1
+    from PyREMOT.data import componentSymbolList, componentDataStore
+    from PyREMOT.docs.rmtUtility import rmtUtilityClass as U
+    syms = list(componentSymbolList)
+    Ts = np.array([298.15, 473.0, 523.0, 620.5, 973.0])
+    cp = np.array([calHeatCapacityAtConstantPressure(syms, T) for T in Ts])
+    mu = np.array([calGasViscosity(syms, T) for T in Ts])
+    MW = np.array([c["MW"] for c in componentDataStore["payload"]], float)
+    dHf = np.array([c["dHf25"]["val"] for c in componentDataStore["payload"]], float)
+    y = np.arange(1, 13, dtype=float); y /= y.sum()
+    wilke = np.array([calMixturePropertyM1(12, m, y, MW) for m in mu])
+    reactions = {"R1": "CO2 + 3H2 <=> CH3OH + H2O", "R2": "CO + H2O <=> H2 + CO2", "R3": "2CH3OH <=> DME + H2O",
+                 "R4": "2CH4 <=> C2H4 + 2H2", "R5": "C3H8 => C3H6 + H2", "R6": "0.5C4H10+1.5N2=C3H6 + CH4"}
+    dH = np.array([calStandardEnthalpyOfReaction(r) for r in reactions.values()])
+    vec = U.buildReactionCoeffVector(U.buildReactionCoefficient(reactions))
+    flat = np.array([[j, syms.index(s), v] for j, r in enumerate(vec) for s, v in r], float)
+    np.savez_compressed(os.path.join(HERE, "component_props_reference.npz"), symbols=np.array(syms), Ts=Ts, cp=cp, mu=mu,
+                        MW=MW, dHf25=dHf, wilke_y=y, wilke=wilke, reactions=np.array(list(reactions.values())),
+                        dH25=dH, stoich=flat, rmtCom=np.array(PyREMOT.rmtCom()))
+    print("props done")
+
+
 if __name__ == "__main__":
     for part in sys.argv[1:]:
         if part == "n1":
             part_n1()
         elif part == "corners":
             part_corners()
+        elif part == "props":
+            part_props()
         elif part == "n2rhs":
             part_n2rhs()
         elif part.startswith("n2sol_"):

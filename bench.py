@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""bench.py — reactor ODE solves/s on the BASELINE config-3 workload.
+
+Workload (BASELINE.json configs[2], SURVEY.md 8(d) "config 3"): an ensemble of
+steady-state pseudo-homogeneous packed-bed reactors (PyREMOT model N1,
+CO2-to-methanol/DME, 6 species / 3 reactions / 8 unknowns) sweeping feed
+temperature, pressure and composition; 2^20 reactors PER GPU (weak scaling),
+SciPy-default tolerances rtol=1e-3 / atol=1e-6 — what the reference's
+`solve_ivp` call uses (pbHomoReactor.py:2931) — outlet-only output.
+
+A "step" is one pass of the hot path over the batch: the per-reactor setup
+kernel (runN1 :2744-2852) + the fused adaptive-Rosenbrock integrator kernel
+(solve_ivp + modelEquationN1 + sortResult4).  `value` is timed with the inputs
+resident in HBM; `e2e` goes through the public `rmtExeBatch` call with host
+arrays (pinned staging + H2D + kernels + D2H inside the timed region).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import cases  # noqa: E402  (synthetic inputs shared with the tests)
+
+METRIC = "reactor_ode_solves_per_sec"
+UNIT = "solves/s"
+B_PER_GPU = 1 << 20
+SEED = 20240611
+RTOL, ATOL = 1e-3, 1e-6
+
+
+# ------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path on the host cores
+# ------------------------------------------------------------------------------------
+def _cpu_worker(idx_chunk):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import io
+    import contextlib
+    import warnings
+    warnings.simplefilter("ignore")
+    import pyremot_oracle as O
+    base = cases.methanol_readme_input("N1")
+    sweep = cases.config3_sweep(max(idx_chunk) + 1, SEED)
+    nfev, ok = 0, 0
+    for i in idx_chunk:
+        mi = cases.instance_input(base, sweep, i)
+        with contextlib.redirect_stdout(io.StringIO()):
+            try:
+                r = O.rmtExe(mi)
+                nfev += r["resModel"][0]["nfev"]
+                ok += 1
+            except Exception:
+                pass
+    return nfev, ok
+
+
+def cpu_solves(n_solves, pool, cores):
+    chunks = [list(range(c, n_solves, cores)) for c in range(cores)]
+    chunks = [c for c in chunks if c]
+    t0 = time.perf_counter()
+    res = pool.map(_cpu_worker, chunks)
+    dt = time.perf_counter() - t0
+    return dt, sum(r[0] for r in res), sum(r[1] for r in res)
+
+
+def run_reference_arm(args, rank, world):
+    """`--impl reference`: the reference's CPU algorithm (oracle port: same
+    equations, same SciPy LSODA call, same default tolerances) on all host cores."""
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    per_step = 8*cores
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        for _ in range(args.warmup):
+            cpu_solves(min(per_step, 2*cores), pool, cores)
+        t_total, nfev, ok = 0.0, 0, 0
+        for _ in range(args.steps):
+            dt, nf, k = cpu_solves(per_step, pool, cores)
+            t_total += dt; nfev += nf; ok += k
+    value = args.steps*per_step/t_total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3*t_total/args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(world, sample=per_step),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d config-3 reactors per step (first indices of seed %d), SciPy LSODA rtol=1e-3 atol=1e-6, "
+                                   "multiprocessing over %d cores; mean nfev %.0f; %d/%d converged"
+                                   % (per_step, SEED, cores, nfev/max(ok, 1), ok, args.steps*per_step)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(world, sample=None):
+    cfg = {
+        "workload": "config3: 2^20 steady-state PFR (PyREMOT N1, CO2->MeOH/DME, 6 comps, 3 rxns, 8 unknowns) per GPU; "
+                    "T0~U[473,573]K, P0~U[2,8]MPa, H2/COx~U[1,3], CO2/COx~U[0.2,0.8]; seed %d+rank" % SEED,
+        "instances_per_gpu": B_PER_GPU, "rtol": RTOL, "atol": ATOL, "output": "outlet (y_i, P, T)",
+        "integrator": "Rodas4(3), PI step control, analytic Jacobian", "parallelism": "ensemble-sharded x%d, no data-path collective" % world,
+        "cache": "inputs+constants+outputs 330 MB per step > 126 MB L2 (no flush needed)",
+    }
+    if sample is not None:
+        cfg["instances_per_step"] = sample
+    return cfg
+
+
+# ------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons, mx = [], set(), None
+        try:
+            for ln in open(self.path):
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx = float(f[2])
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------
+def solver_flops(info, stats, n):
+    """Algorithmic flops of one integrator launch from its per-instance counters.
+    Per attempt: 1 f+Jacobian, (s-1) RHS, one n x n LU, s triangular solves,
+    stage combinations and the error norm.  (alg: 1 flop per op; wt: FP64-
+    instruction weighted, rmt_app_b200/expr.py FLOP_WEIGHT.)"""
+    att = float(stats[3].sum())
+    nfev = float(stats[2].sum())
+    s = info.stages
+    lu = (2.0*n**3)/3.0 + n*n            # factorisation incl. forming W
+    tri = s*2.0*n*n
+    comb = 2.0*n*(s*(s - 1)) + 8.0*n      # a_ij / c_ij combinations, update, error norm
+    lin_alg = att*(lu + tri + comb)
+    lin_wt = lin_alg + att*9.0*n          # n reciprocal pivots
+    alg = nfev*info.flops_rhs_alg + att*info.flops_jac_alg + lin_alg
+    wt = nfev*info.flops_rhs_wt + att*info.flops_jac_wt + lin_wt
+    return alg, wt, att, nfev
+
+
+def run_gpu_arm(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from rmt_app_b200 import capi, engine, rmtExeBatch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # CPU baseline first (rank 0, N=1 only), before the timed GPU region
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import multiprocessing as mp
+        cores = os.cpu_count() or 1
+        S = 16*cores
+        with mp.get_context("spawn").Pool(cores) as pool:
+            cpu_solves(cores, pool, cores)                      # warm the workers (imports)
+            dt, nfev, ok = cpu_solves(S, pool, cores)
+        cpu_baseline = {"value": S/dt, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": "%d config-3 reactors (first indices of the same seed), oracle port of runN1/modelEquationN1 "
+                                  "+ SciPy LSODA rtol=1e-3 atol=1e-6, %d processes; mean nfev %.0f; %d/%d converged; "
+                                  "the unmodified reference is ~8x slower per solve (0.6 s vs 0.07 s, BASELINE.md)"
+                                  % (S, cores, nfev/max(ok, 1), ok, S)}
+
+    B = args.instances
+    base = cases.methanol_readme_input("N1")
+    sweep = cases.config3_sweep(B, SEED + rank)
+    cm = engine.compile_model(base)
+    mod = cm.load(local_rank)
+    info, spec = mod.info, cm.spec
+    n = info.n
+    stream = torch.cuda.current_stream().cuda_stream
+    ws = engine.Workspace()
+
+    # resident inputs
+    h_rows, n_rows, row_map = engine.sweep_rows_into(spec, sweep, B, ws)
+    uniform = engine.uniform_inputs(spec, base)
+    d_rows = h_rows.to(dev)
+    d_consts = torch.empty((info.nconst, B), dtype=torch.float64, device=dev)
+    d_out = torch.empty((1, n, B), dtype=torch.float64, device=dev)
+    d_status = torch.empty((B,), dtype=torch.int32, device=dev)
+    d_stats = torch.empty((4, B), dtype=torch.int32, device=dev)
+    z_eval = np.array([1.0])
+
+    def step(ev=None):
+        if ev is not None:
+            ev[0].record()
+        mod.setup(B, d_rows, n_rows, row_map, uniform, d_consts, stream=stream)
+        if ev is not None:
+            ev[1].record()
+        mod.n1_solve(B, d_consts, z_eval, RTOL, ATOL, d_out, d_status, d_stats, out_mode=1, stream=stream)
+        if ev is not None:
+            ev[2].record()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for k in range(args.steps):
+        step(evs[k])
+    t_end.record()
+    barrier()
+    clocks = sampler.stop()
+    elapsed_ms = t_start.elapsed_time(t_end)
+    setup_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
+    solve_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
+    if world > 1:
+        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+
+    status = d_status.cpu().numpy()
+    stats = d_stats.cpu().numpy()
+    n_ok = int((status == 0).sum())
+    alg, wt, att, nfev = solver_flops(info, stats, n)
+    if world > 1:
+        t = torch.tensor([n_ok, att, nfev], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        n_ok_all = int(t[0].item())
+    else:
+        n_ok_all = n_ok
+
+    # ---- e2e through the public API: host arrays in, host arrays out -----------------------------
+    for _ in range(2):
+        r = rmtExeBatch(base, sweep, workspace=ws, rtol=RTOL, atol=ATOL)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = rmtExeBatch(base, sweep, workspace=ws, rtol=RTOL, atol=ATOL)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    h2d, d2h = r["h2d_bytes"], r["d2h_bytes"]
+    e2e_ok = int(r["success"].sum())
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+
+    # ---- roofline denominators measured on this box ----------------------------------------------
+    fp64_peak = mod.fp64_peak(iters=16384, repeats=5)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+
+    # stand-alone RHS kernel (HBM-bound): nconst + n rows in, n rows out per evaluation
+    d_y = torch.rand((n, B), dtype=torch.float64, device=dev)*0.5 + 0.25
+    d_y[n - 2] = 1.0
+    d_y[n - 1] = 0.1
+    d_f = torch.empty((n, B), dtype=torch.float64, device=dev)
+    for _ in range(3):
+        mod.n1_rhs(B, d_consts, d_y, d_f, stream=stream)
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    reps = 10
+    e0.record()
+    for _ in range(reps):
+        mod.n1_rhs(B, d_consts, d_y, d_f, stream=stream)
+    e1.record()
+    torch.cuda.synchronize()
+    rhs_ms = e0.elapsed_time(e1)/reps
+    rhs_bytes = 8.0*(info.nconst + 2*n)*B
+
+    if rank == 0:
+        steps = args.steps
+        total = world*B*steps
+        solve_s = solve_ms*1e-3
+        line = {
+            "metric": METRIC, "value": total/(elapsed_ms*1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms/steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(world),
+            "clocks": clocks,
+            "e2e": {"value": world*B*steps/e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "api": "rmt_app_b200.rmtExeBatch(modelInput, sweep, workspace=...) with host numpy arrays",
+                    "converged": e2e_ok},
+            "gpu_launches": 2*steps,
+            "converged": n_ok_all, "instances": world*B,
+            "roofline": {
+                "kernel": "rmt_n1_solve", "bound": "fp64", "achieved": alg/solve_s/1e12, "peak": fp64_peak,
+                "unit": "TFLOP/s", "frac": alg/solve_s/1e12/fp64_peak, "traffic": None,
+                "achieved_weighted": wt/solve_s/1e12, "frac_weighted": wt/solve_s/1e12/fp64_peak,
+                "peak_source": "rmt_dfma_peak measured in this run (MEASURED_PEAKS.json has no FP64 figure; "
+                               "nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2)",
+                "kernel_ms": solve_ms, "kernel_share_of_step": solve_ms/(elapsed_ms/steps),
+                "flops_per_launch_alg": alg, "flops_per_launch_weighted": wt,
+                "attempts_per_solve": att/B, "rhs_evals_per_solve": (nfev + att)/B,
+                "note": "contract offers hbm|tensor; this kernel keeps all state on-chip (HBM traffic = 200 B in + 64 B "
+                        "out per reactor) and has no contraction, so the bounding pipe is FP64 FMA",
+            },
+            "roofline_rhs_kernel": {
+                "kernel": "rmt_n1_rhs", "bound": "hbm", "achieved": rhs_bytes/(rhs_ms*1e-3)/1e9, "peak": hbm_peak,
+                "unit": "GB/s", "frac": rhs_bytes/(rhs_ms*1e-3)/1e9/hbm_peak, "traffic": None, "peak_source": hbm_src,
+                "kernel_ms": rhs_ms, "rhs_evals_per_s": B/(rhs_ms*1e-3),
+                "fp64_tflops_weighted": B*info.flops_rhs_wt/(rhs_ms*1e-3)/1e12,
+            },
+            "rhs_evals_per_sec_in_solver": world*(nfev + att)/solve_s,
+            "setup_kernel_ms": setup_ms,
+        }
+        if cpu_baseline is not None:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--instances", type=int, default=B_PER_GPU, help="reactors per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1 and args.gpus > 1 and args.impl != "reference":
+        # convenience: relaunch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+    else:
+        run_gpu_arm(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -5,6 +5,6 @@ pseudo-homogeneous packed-bed reactor models N1 (steady state) and N2
     from rmt_app_b200 import rmtExe, rmtCom, rmtExeBatch
 """
 from .rmt import rmtExe, rmtCom, rmtExeBatch      # noqa: F401
-from .engine import solverSetting                  # noqa: F401
+from .engine import solverSetting, Workspace       # noqa: F401
 
-__all__ = ["rmtExe", "rmtCom", "rmtExeBatch", "solverSetting"]
+__all__ = ["rmtExe", "rmtCom", "rmtExeBatch", "solverSetting", "Workspace"]

@@ -63,8 +63,56 @@ def default_block(spec):
     return 32
 
 
+def _fn_sig(f):
+    cells = ()
+    if getattr(f, "__closure__", None):
+        out = []
+        for c in f.__closure__:
+            try:
+                v = c.cell_contents
+            except ValueError:
+                v = None
+            out.append(v if isinstance(v, (int, float, str, bool, type(None))) else id(v))
+        cells = tuple(out)
+    return (f.__code__, cells, repr(f.__defaults__), id(f.__globals__))
+
+
+def _fast_key(modelInput, block):
+    """Cheap identity of the model *structure* (no tracing): same components,
+    reactions, process type and the same code objects in VARS/RATES."""
+    import types
+    rr = modelInput["reaction-rates"]
+    sig = []
+    for k, v in rr["VARS"].items():
+        sig.append((k, _fn_sig(v)) if isinstance(v, types.FunctionType) else (k, type(v).__name__))
+    for k, v in rr["RATES"].items():
+        sig.append((k, _fn_sig(v)) if isinstance(v, types.FunctionType) else (k, type(v).__name__))
+    return (modelInput["model"], tuple(modelInput["feed"]["components"]["shell"]),
+            modelInput["operating-conditions"]["process-type"], tuple(modelInput["reactions"].values()),
+            tuple(sig), block)
+
+
+_fast = {}
+
+
 def compile_model(modelInput, block=None):
     """Trace + generate + (lazily) NVRTC-compile; cached per model structure."""
+    try:
+        fk = _fast_key(modelInput, block)
+        cm = _fast.get(fk)
+        if cm is not None:
+            return cm
+    except Exception:
+        fk = None
+    cm = _compile_model(modelInput, block)
+    if fk is not None:
+        if len(_fast) > 256:
+            _fast.clear()
+        _fast[fk] = cm
+    return cm
+
+
+def _compile_model(modelInput, block=None):
     spec = ModelSpec(modelInput)
     blk = block or default_block(spec)
     key = spec.key("b%d" % blk)
@@ -129,20 +177,94 @@ def sweep_rows(spec, sweep, B):
 
 
 # ----------------------------------------------------------------------------------
+# buffers
+# ----------------------------------------------------------------------------------
+class Workspace:
+    """Grow-only pinned-host and device buffers reused across ensemble calls.
+
+    Results returned from a call that was given a workspace are views into its
+    pinned buffers and stay valid until the next call with the same workspace."""
+
+    def __init__(self):
+        self._bufs = {}
+
+    def get(self, name, shape, dtype, device=None, pinned=False):
+        torch = _torch()
+        need = int(np.prod(shape)) if len(shape) else 1
+        key = (name, str(dtype), str(device), pinned)
+        buf = self._bufs.get(key)
+        if buf is None or buf.numel() < need:
+            cap = max(need, 1)
+            if device is not None:
+                buf = torch.empty((cap,), dtype=dtype, device=device)
+            else:
+                buf = torch.empty((cap,), dtype=dtype, pin_memory=pinned)
+            self._bufs[key] = buf
+        return buf[:need].view(*shape)
+
+
+def sweep_rows_into(spec, sweep, B, ws):
+    """Like sweep_rows but writes straight into a pinned staging buffer."""
+    torch = _torch()
+    nin = spec.nin
+    row_map = -np.ones(nin, dtype=np.int32)
+    scalar_index = {name: 2 + spec.nc + k for k, name in enumerate(SCALAR_INPUTS[2:])}
+    scalar_index["temperature"], scalar_index["pressure"] = 0, 1
+    kp_index = {name: 2 + spec.nc + len(SCALAR_INPUTS) - 2 + k for k, name in enumerate(spec.kin.param_names)}
+    plan = []
+    for key, val in (sweep or {}).items():
+        if key == "concentration":
+            shp = tuple(val.shape)
+            if shp != (B, spec.nc):
+                raise ValueError("sweep['concentration'] must have shape (B, nc) = (%d, %d)" % (B, spec.nc))
+            for i in range(spec.nc):
+                row_map[2 + i] = len(plan)
+                plan.append((val, i))
+            continue
+        if tuple(np.shape(val)) != (B,):
+            raise ValueError("sweep[%r] must have shape (B,) = (%d,)" % (key, B))
+        if key in scalar_index:
+            q = scalar_index[key]
+        elif key in kp_index:
+            q = kp_index[key]
+        else:
+            raise KeyError("sweep key %r is neither an operating/feed/reactor input %r nor a scalar VARS entry %r"
+                           % (key, ["temperature", "pressure", "concentration"] + list(SCALAR_INPUTS[2:]),
+                              spec.kin.param_names))
+        row_map[q] = len(plan)
+        plan.append((val, None))
+    n_rows = len(plan)
+    if n_rows == 0:
+        return None, 0, row_map
+    stage = ws.get("h_rows", (n_rows, B), torch.float64, pinned=True)
+    view = stage.numpy()
+    for r, (val, col) in enumerate(plan):
+        if torch.is_tensor(val):
+            stage[r].copy_(val if col is None else val[:, col])
+        else:
+            a = np.asarray(val)
+            np.copyto(view[r], a if col is None else a[:, col], casting="same_kind")
+    return stage, n_rows, row_map
+
+
+# ----------------------------------------------------------------------------------
 # N1 ensemble
 # ----------------------------------------------------------------------------------
 class N1Result:
     """Arrays of one ensemble solve (host numpy unless `keep_on_device`)."""
-    __slots__ = ("out", "status", "stats", "z_eval", "objective", "n", "nc", "out_mode", "flops", "seconds")
+    __slots__ = ("out", "status", "stats", "z_eval", "objective", "n", "nc", "out_mode", "flops", "consts",
+                 "h2d_bytes", "d2h_bytes")
 
 
 def n1_solve_ensemble(cm, modelInput, sweep=None, B=1, z_eval=None, rtol=None, atol=None, out_mode=1,
                       dense=True, max_steps=100000, objective_ref=None, device=None, keep_on_device=False,
-                      pinned=None, ctrl=None):
+                      workspace=None, ctrl=None, want_stats=True):
     """Solve B independent steady-state reactors on the current CUDA device.
 
-    Returns an N1Result with out[n_eval][rows][B].  Raises capi.RmtError when the
-    CUDA library/driver is unavailable (no CPU path exists)."""
+    Per call: stage the varying inputs in pinned memory -> H2D -> `rmt_setup`
+    (per-reactor constants) -> `rmt_n1_solve` -> D2H.  Returns an N1Result with
+    out[n_eval][rows][B].  Raises capi.RmtError when the CUDA library/driver is
+    unavailable (no CPU path exists)."""
     torch = _torch()
     if not torch.cuda.is_available():
         raise capi.RmtError("rmt_app_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -156,36 +278,51 @@ def n1_solve_ensemble(cm, modelInput, sweep=None, B=1, z_eval=None, rtol=None, a
         z_eval = np.array([1.0])
     z_eval = np.ascontiguousarray(z_eval, dtype=np.float64)
     uniform = uniform_inputs(spec, modelInput)
-    rows, row_map = sweep_rows(spec, sweep, B)
+    ws = workspace if workspace is not None else Workspace()
     n, nc = spec.n, spec.nc
     out_rows = 2*n + nc if out_mode == 2 else n
+    res = N1Result()
+    res.z_eval, res.n, res.nc, res.out_mode, res.flops = z_eval, n, nc, out_mode, cm.flops
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream().cuda_stream
-        if rows.shape[0]:
-            h_rows = torch.from_numpy(rows)
-            if pinned is not None:
-                pinned[:rows.shape[0]].copy_(h_rows)
-                h_rows = pinned[:rows.shape[0]]
-            d_rows = h_rows.to(dev, non_blocking=True)
-        else:
-            d_rows = None
-        d_consts = torch.empty((mod.info.nconst, B), dtype=torch.float64, device=dev)
-        d_out = torch.empty((z_eval.size, out_rows, B), dtype=torch.float64, device=dev)
-        d_status = torch.empty((B,), dtype=torch.int32, device=dev)
-        d_stats = torch.empty((4, B), dtype=torch.int32, device=dev)
-        d_obj = torch.empty((B,), dtype=torch.float64, device=dev) if objective_ref is not None else None
-        mod.setup(B, d_rows, rows.shape[0], row_map, uniform, d_consts, stream=stream)
+        h_rows, n_rows, row_map = sweep_rows_into(spec, sweep, B, ws)
+        d_rows = None
+        res.h2d_bytes = 0
+        if n_rows:
+            d_rows = ws.get("d_rows", (n_rows, B), torch.float64, device=dev)
+            d_rows.copy_(h_rows, non_blocking=True)
+            res.h2d_bytes = h_rows.numel()*8
+        d_consts = ws.get("d_consts", (mod.info.nconst, B), torch.float64, device=dev)
+        d_out = ws.get("d_out", (z_eval.size, out_rows, B), torch.float64, device=dev)
+        d_status = ws.get("d_status", (B,), torch.int32, device=dev)
+        d_stats = ws.get("d_stats", (4, B), torch.int32, device=dev)
+        d_obj = ws.get("d_obj", (B,), torch.float64, device=dev) if objective_ref is not None else None
+        mod.setup(B, d_rows, n_rows, row_map, uniform, d_consts, stream=stream)
         mod.n1_solve(B, d_consts, z_eval, rtol, atol, d_out, d_status, d_stats, max_steps=max_steps, dense=dense,
                      out_mode=out_mode, obj_ref=objective_ref, d_obj=d_obj, ctrl=ctrl, stream=stream)
-        res = N1Result()
-        res.z_eval, res.n, res.nc, res.out_mode, res.flops = z_eval, n, nc, out_mode, cm.flops
+        res.consts = d_consts
         if keep_on_device:
             res.out, res.status, res.stats, res.objective = d_out, d_status, d_stats, d_obj
+            res.d2h_bytes = 0
         else:
-            res.out = d_out.cpu().numpy()
-            res.status = d_status.cpu().numpy()
-            res.stats = d_stats.cpu().numpy()
-            res.objective = None if d_obj is None else d_obj.cpu().numpy()
+            h_out = ws.get("h_out", tuple(d_out.shape), torch.float64, pinned=True)
+            h_status = ws.get("h_status", (B,), torch.int32, pinned=True)
+            h_out.copy_(d_out, non_blocking=True)
+            h_status.copy_(d_status, non_blocking=True)
+            res.d2h_bytes = h_out.numel()*8 + h_status.numel()*4
+            h_stats = h_obj = None
+            if want_stats:
+                h_stats = ws.get("h_stats", (4, B), torch.int32, pinned=True)
+                h_stats.copy_(d_stats, non_blocking=True)
+                res.d2h_bytes += h_stats.numel()*4
+            if d_obj is not None:
+                h_obj = ws.get("h_obj", (B,), torch.float64, pinned=True)
+                h_obj.copy_(d_obj, non_blocking=True)
+                res.d2h_bytes += h_obj.numel()*8
+            torch.cuda.current_stream().synchronize()
+            res.out, res.status = h_out.numpy(), h_status.numpy()
+            res.stats = None if h_stats is None else h_stats.numpy()
+            res.objective = None if h_obj is None else h_obj.numpy()
     return res
 
 

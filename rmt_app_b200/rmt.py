@@ -147,7 +147,7 @@ def _runN2(modelInput):
 
 
 def rmtExeBatch(modelInput, sweep=None, B=None, *, rtol=None, atol=None, profile=False, z_eval=None,
-                objective_ref=None, dense=True, max_steps=100000, keep_on_device=False):
+                objective_ref=None, dense=True, max_steps=100000, keep_on_device=False, workspace=None):
     """Ensemble form of rmtExe for model "N1": B independent reactors that share
     `modelInput` except for the per-instance arrays in `sweep` (keys:
     "temperature", "pressure", "concentration" [B, nc], "volumetric-flowrate",
@@ -156,7 +156,9 @@ def rmtExeBatch(modelInput, sweep=None, B=None, *, rtol=None, atol=None, profile
     Returns {"dataYs": [B, n] outlet (or [B, n, n_eval] with profile/z_eval),
              "status": [B], "success": [B] bool, "stats": [4, B], "dataXs": z_eval,
              "objective": [B] or None, "comTime": ms}.
-    Failed instances are flagged in `status` and never abort the ensemble."""
+    Failed instances are flagged in `status` and never abort the ensemble.
+    `workspace` (engine.Workspace) reuses pinned/device buffers across calls; the
+    returned arrays are then views valid until the next call with that workspace."""
     tic = timer()
     _check_components(modelInput)
     if modelInput['model'] != "N1":
@@ -171,7 +173,7 @@ def rmtExeBatch(modelInput, sweep=None, B=None, *, rtol=None, atol=None, profile
         z_eval = np.linspace(0, 1, solverSetting['N1']['zNo'] + 1) if profile else np.array([1.0])
     res = engine.n1_solve_ensemble(cm, modelInput, sweep, B, z_eval=z_eval, rtol=rtol, atol=atol, out_mode=1,
                                    dense=dense, max_steps=max_steps, objective_ref=objective_ref,
-                                   keep_on_device=keep_on_device)
+                                   keep_on_device=keep_on_device, workspace=workspace)
     if keep_on_device:
         out = res.out.permute(2, 1, 0)
         data = out[:, :, 0] if out.shape[2] == 1 else out
@@ -181,5 +183,5 @@ def rmtExeBatch(modelInput, sweep=None, B=None, *, rtol=None, atol=None, profile
         data = out[:, :, 0] if out.shape[2] == 1 else out
         success = res.status == 0
     return {"dataYs": data, "status": res.status, "success": success, "stats": res.stats, "dataXs": res.z_eval,
-            "objective": res.objective, "labelList": list(cm.spec.compList) + ["Pressure"] + (
+            "objective": res.objective, "h2d_bytes": res.h2d_bytes, "d2h_bytes": res.d2h_bytes, "labelList": list(cm.spec.compList) + ["Pressure"] + (
                 [] if cm.spec.iso else ["Temperature"]), "comTime": (timer() - tic)*1000}

@@ -1,0 +1,250 @@
+"""GPU parity tests for the N1 path (run with -m gpu on the B200 box).
+
+Level 1: RHS / constants / Jacobian against the oracle and the reference's golden vectors.
+Level 2: tight-tolerance solutions against the reference run at rtol=1e-10/atol=1e-12
+         (north_star tolerance: relative 1e-6 on outlet mole fractions and T profiles).
+Level 3: default-tolerance solutions within the reference's own default-vs-converged error.
+Every call goes through the C ABI (rmt_app_b200.capi -> librmtb200.so)."""
+import numpy as np
+import pytest
+
+import cases
+import pyremot_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+N1_CASES = {
+    "methanol_readme": lambda: cases.methanol_readme_input("N1"),
+    "methanol_testfile": lambda: cases.methanol_testfile_input("N1"),
+    "ch4_noniso": lambda: cases.ch4_input("N1", "non-iso-thermal"),
+    "ch4_iso": lambda: cases.ch4_input("N1", "iso-thermal"),
+}
+TIGHT = dict(rtol=1e-9, atol=1e-12)
+
+
+def _engine():
+    from rmt_app_b200 import engine
+    return engine
+
+
+def _ulp_sensitivity(o, y, f, rng):
+    """How much does the reference RHS itself move under 1-ulp input perturbations?
+    (near chemical equilibrium the rates cancel and amplify rounding)."""
+    dev = 0.0
+    for _ in range(6):
+        fp = np.array(o.rhs(0.0, y*(1 + 2.2e-16*rng.choice([-1, 0, 1], size=y.size))))
+        dev = max(dev, np.max(np.abs(fp - f)))
+    return dev
+
+
+@pytest.mark.parametrize("name", list(N1_CASES))
+def test_rhs_parity_with_reference_golden(golden_n1, name):
+    eng = _engine()
+    mi = N1_CASES[name]()
+    cm = eng.compile_model(mi)
+    Y, F = golden_n1[name + "__rhs_Y"], golden_n1[name + "__rhs_F"]
+    Fg, _, consts = eng.n1_rhs_batch(cm, mi, Y)
+    o = O.N1Oracle(mi)
+    rng = np.random.default_rng(5)
+    for y, f, fg in zip(Y, F, Fg):
+        tol = 1e-13*np.max(np.abs(f)) + 50*_ulp_sensitivity(o, y, f, rng)
+        assert np.max(np.abs(fg - f)) <= tol, (name, y, fg - f, tol)
+    # well-conditioned states (feed + perturbed): plain relative agreement
+    assert np.max(np.abs(Fg[0] - F[0])/np.abs(F[0])) < 1e-11
+    # setup constants written by rmt_setup vs the reference's paramsSet
+    g = lambda k: float(golden_n1[name + "__" + k])
+    np.testing.assert_allclose(consts[10, 0], g("const_GaMiVi"), rtol=1e-13)      # Wilke mixture viscosity
+    np.testing.assert_allclose(consts[9, 0], g("da_GaHeCoTe0"), rtol=1e-13)
+    np.testing.assert_allclose(consts[8, 0], golden_n1[name + "__da_GaMaCoTe0"][0], rtol=1e-13)
+    np.testing.assert_allclose(consts[6, 0], g("bc_GaDe0"), rtol=1e-13)
+    np.testing.assert_allclose(consts[7, 0], g("bc_GaCpMeanMix0"), rtol=1e-13)
+    np.testing.assert_allclose(consts[3, 0], g("bc_SpCo0"), rtol=1e-14)
+
+
+@pytest.mark.parametrize("name", ["methanol_readme", "ch4_iso", "ch4_noniso"])
+def test_analytic_jacobian_against_oracle_differences(golden_n1, name):
+    eng = _engine()
+    mi = N1_CASES[name]()
+    cm = eng.compile_model(mi)
+    o = O.N1Oracle(mi)
+    Y = golden_n1[name + "__rhs_Y"][[0, 10, 13, 20, 25]]
+    if name == "ch4_noniso":
+        Y = Y[:3]        # later states sit at T -> 0 K where differences are meaningless
+    _, J, _ = eng.n1_rhs_batch(cm, mi, Y, jac=True)
+    for y, Jg in zip(Y, J):
+        n = y.size
+        Jfd = np.zeros((n, n))
+        for j in range(n):
+            h = 1e-6*max(abs(y[j]), 1e-3)
+            yp, ym = y.copy(), y.copy()
+            yp[j] += h; ym[j] -= h
+            Jfd[:, j] = (np.array(o.rhs(0, yp)) - np.array(o.rhs(0, ym)))/(2*h)
+        assert np.max(np.abs(Jg - Jfd)) < 2e-6*np.max(np.abs(Jfd)), name
+
+
+@pytest.mark.parametrize("name", list(N1_CASES))
+def test_rmtexe_tight_matches_reference_tight(golden_n1, name):
+    """Level 2: outlet mole fractions and the 101-point T profile within 1e-6 (north_star)."""
+    from rmt_app_b200 import rmtExe
+    mi = N1_CASES[name]()
+    mi["solver-config"].update(TIGHT)
+    dp = rmtExe(mi)["resModel"][0]
+    ref = golden_n1[name + "__tight_LSODA__dataYs"]
+    assert dp["dataYs"].shape == ref.shape
+    rel = np.abs(dp["dataYs"] - ref)/np.abs(ref)
+    tol = 1e-6
+    assert rel[:, -1].max() < tol, rel[:, -1]
+    assert rel.max() < tol, rel.max()
+    # result schema of runN1 (pbHomoReactor.py:2991-3007)
+    for k in ("dataXs", "dataYCons1", "dataYCons2", "dataYTemp1", "dataYTemp2"):
+        assert np.asarray(dp[k]).shape == golden_n1[name + "__" + k].shape, k
+    assert dp["labelList"] == list(golden_n1[name + "__labelList"])
+    assert dp["indexList"] == list(golden_n1[name + "__indexList"])
+    assert dp["modelId"] == "N1" and dp["successStatus"] is True and dp["dataTime"] == []
+    soly = golden_n1[name + "__tight_LSODA__soly"]
+    nc = len(mi["feed"]["components"]["shell"])
+    np.testing.assert_allclose(dp["dataYCons1"], soly[:nc], rtol=2e-6, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", list(N1_CASES))
+def test_rmtexe_default_tolerance_level3(golden_n1, name):
+    """Level 3: at SciPy's default tolerances we must be no further from the converged
+    solution than the reference's own LSODA/BDF/Radau runs are."""
+    from rmt_app_b200 import rmtExe
+    dp = rmtExe(N1_CASES[name]())["resModel"][0]
+    tight = golden_n1[name + "__tight_LSODA__dataYs"]
+    ours = np.abs(dp["dataYs"][:, -1] - tight[:, -1])/np.abs(tight[:, -1])
+    theirs = max(np.max(np.abs(golden_n1["%s__%s__dataYs" % (name, m)][:, -1] - tight[:, -1])/np.abs(tight[:, -1]))
+                 for m in ("default", "BDF", "Radau"))
+    assert ours.max() < max(3*theirs, 2e-3), (ours, theirs)
+
+
+def test_config3_corners_tight_and_default(golden_corners):
+    from rmt_app_b200 import rmtExeBatch
+    base = cases.methanol_readme_input("N1")
+    sw = cases.config3_corners()
+    tight = golden_corners["tight_dataYs"]          # [36][8][101]
+    r = rmtExeBatch(base, sw, profile=True, **TIGHT)
+    assert r["success"].all()
+    rel = np.abs(r["dataYs"] - tight)/np.abs(tight)
+    assert rel[:, :, -1].max() < 1e-6               # outlets
+    assert rel[:, -1, :].max() < 1e-6               # temperature profiles
+    assert rel.max() < 5e-6                         # every species at every point (dense output of trace species)
+    # default tolerance: outlet error distribution no worse than the reference's LSODA
+    d = rmtExeBatch(base, sw)
+    assert d["success"].all()
+    ours = (np.abs(d["dataYs"] - tight[:, :, -1])/np.abs(tight[:, :, -1])).max(axis=1)
+    theirs = (np.abs(golden_corners["default_dataYs"][:, :, -1] - tight[:, :, -1])/np.abs(tight[:, :, -1])).max(axis=1)
+    assert np.median(ours) <= 2*np.median(theirs) and ours.max() <= theirs.max(), (np.median(ours), ours.max(), theirs.max())
+
+
+def test_random_sweep_against_oracle_port():
+    from rmt_app_b200 import rmtExeBatch
+    base = cases.methanol_readme_input("N1")
+    B = 4096
+    sw = cases.config3_sweep(B, seed=99)
+    r = rmtExeBatch(base, sw, **TIGHT)
+    assert r["success"].all()
+    np.testing.assert_allclose(r["dataYs"][:, :6].sum(axis=1), 1.0, rtol=1e-13)
+    for i in (0, 1234, 4095):
+        want = O.rmtExe(cases.instance_input(base, sw, i), method="LSODA", rtol=1e-10, atol=1e-12)["resModel"][0]["dataYs"][:, -1]
+        assert np.max(np.abs(r["dataYs"][i] - want)/np.abs(want)) < 1e-6
+
+
+def test_kinetic_parameter_sweep_and_objective():
+    """Config-4 style: Arrhenius parameters as per-instance VARS slots, fused objective, reduction."""
+    from rmt_app_b200 import engine
+    base = cases.methanol_readme_input("N1")
+    base["reaction-rates"] = cases.methanol_kinetics_param(1171.2)
+    B = 2048
+    pop = cases.config4_population(B)
+    cm = engine.compile_model(base)
+    nominal = engine.n1_solve_ensemble(cm, base, None, 1, **TIGHT).out[0, :, 0]
+    # nominal parameters through the parametrised kinetics == fixed-constant kinetics
+    plain = engine.n1_solve_ensemble(engine.compile_model(cases.methanol_readme_input("N1")),
+                                     cases.methanol_readme_input("N1"), None, 1, **TIGHT).out[0, :, 0]
+    np.testing.assert_allclose(nominal, plain, rtol=1e-9)
+    res = engine.n1_solve_ensemble(cm, base, pop, B, objective_ref=nominal, keep_on_device=True, **TIGHT)
+    out = res.out.cpu().numpy()[0]                    # [n][B]
+    obj = res.objective.cpu().numpy()
+    idx = [0, 1, 2, 3, 4, 5, 7]
+    want = (((out[idx] - nominal[idx, None])/nominal[idx, None])**2).sum(axis=0)
+    np.testing.assert_allclose(obj, want, rtol=1e-12)
+    s, mn, am = cm.module.reduce_objective(B, res.objective, index_offset=1000)
+    np.testing.assert_allclose(s, obj.sum(), rtol=1e-12)
+    assert mn == obj.min() and am == 1000 + int(obj.argmin())
+    # one perturbed instance against the oracle with the same parameters
+    i = 77
+    want = O.rmtExe(cases.instance_input(base, pop, i), method="LSODA", rtol=1e-10, atol=1e-12)["resModel"][0]["dataYs"][:, -1]
+    assert np.max(np.abs(out[:, i] - want)/np.abs(want)) < 1e-6
+
+
+def test_edge_cases_and_failure_reporting():
+    from rmt_app_b200 import rmtExeBatch, engine
+    base = cases.methanol_readme_input("N1")
+    # ragged sizes around the block size; a single instance; results independent of batch composition
+    sw = cases.config3_sweep(131, seed=5)
+    full = rmtExeBatch(base, sw)
+    for B in (1, 31, 129):
+        part = rmtExeBatch(base, {k: v[:B] for k, v in sw.items()})
+        np.testing.assert_array_equal(part["dataYs"], full["dataYs"][:B])      # bit-identical
+    again = rmtExeBatch(base, sw)
+    np.testing.assert_array_equal(again["dataYs"], full["dataYs"])             # deterministic
+    # one poisoned instance does not abort its neighbours
+    bad = {k: v.copy() for k, v in sw.items()}
+    bad["concentration"][7, 0] = -5.0
+    bad["temperature"][9] = np.nan
+    r = rmtExeBatch(base, bad)
+    assert r["status"][7] != 0 and r["status"][9] != 0
+    ok = np.ones(131, bool); ok[[7, 9]] = False
+    assert r["success"][ok].all()
+    np.testing.assert_array_equal(r["dataYs"][ok], full["dataYs"][ok])
+    assert np.isnan(r["dataYs"][7]).all()
+    # step budget exhausted -> status 1
+    r = rmtExeBatch(base, sw, max_steps=5)
+    assert (r["status"] == 1).all()
+    # no-dense mode lands on the output points: must agree with dense output at tight tolerance
+    z = np.linspace(0, 1, 11)
+    a = rmtExeBatch(base, {k: v[:8] for k, v in sw.items()}, z_eval=z, dense=True, **TIGHT)
+    b = rmtExeBatch(base, {k: v[:8] for k, v in sw.items()}, z_eval=z, dense=False, **TIGHT)
+    np.testing.assert_allclose(a["dataYs"], b["dataYs"], rtol=1e-7)
+    # argument validation errors come from the C ABI, loudly
+    from rmt_app_b200.capi import RmtError
+    with pytest.raises(RmtError, match="strictly increasing"):
+        rmtExeBatch(base, sw, z_eval=np.array([0.5, 0.5, 1.0]))
+    with pytest.raises(KeyError):
+        rmtExeBatch(base, {"nonsense": np.ones(4)})
+
+
+def test_host_buffer_entry_point_matches_device_path():
+    from rmt_app_b200 import engine
+    base = cases.methanol_readme_input("N1")
+    B = 777
+    sw = cases.config3_sweep(B, seed=3)
+    cm = engine.compile_model(base)
+    dev = engine.n1_solve_ensemble(cm, base, sw, B)
+    rows, row_map = engine.sweep_rows(cm.spec, sw, B)
+    uniform = engine.uniform_inputs(cm.spec, base)
+    out = np.empty((1, cm.spec.n, B)); status = np.empty(B, np.int32); stats = np.empty((4, B), np.int32)
+    cm.module.n1_solve_host(B, rows, rows.shape[0], row_map, uniform, np.array([1.0]), 1e-3, 1e-6, out, status, stats)
+    np.testing.assert_array_equal(out, dev.out)
+    np.testing.assert_array_equal(status, dev.status)
+    np.testing.assert_array_equal(stats, dev.stats)
+
+
+def test_full_size_ensemble_properties():
+    """BASELINE size (2^20 reactors): everything converges, outputs are physical and the
+    statistics match the 36-corner reference box (T_out within its extremes)."""
+    from rmt_app_b200 import rmtExeBatch
+    base = cases.methanol_readme_input("N1")
+    B = 1 << 20
+    sw = cases.config3_sweep(B)
+    r = rmtExeBatch(base, sw)
+    assert r["success"].all()
+    y = r["dataYs"]
+    np.testing.assert_allclose(y[:, :6].sum(axis=1), 1.0, rtol=1e-12)
+    assert (y[:, :6] > 0).all()
+    assert (y[:, 6] < sw["pressure"]).all() and (y[:, 6] > 0.99*sw["pressure"]).all()     # small Ergun pressure drop
+    assert y[:, 7].min() > 473.0 and y[:, 7].max() < 700.0                                # SURVEY App. B.4 extremes
+    st = r["stats"]
+    assert 30 < st[0].mean() < 80 and st[0].max() < 400

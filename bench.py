@@ -141,11 +141,28 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def mark(self, wait_s=4.0):
+        """Call right before the timed region: waits for the sampler's first line and remembers
+        how many lines precede the region."""
+        self.n0 = 0
+        if self.proc is None:
+            return
+        t0 = time.time()
+        while time.time() - t0 < wait_s:
+            try:
+                n = sum(1 for _ in open(self.path))
+            except Exception:
+                n = 0
+            if n > 0:
+                self.n0 = n
+                return
+            time.sleep(0.05)
+
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -153,7 +170,7 @@ class ClockSampler:
             self.proc.kill()
         sm, reasons, mx = [], set(), None
         try:
-            for ln in open(self.path):
+            for ln in list(open(self.path))[getattr(self, "n0", 0):]:
                 f = [x.strip() for x in ln.split(",")]
                 if len(f) < 9:
                     continue
@@ -256,12 +273,13 @@ def run_gpu_arm(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.mark()
     barrier()
     t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
     t_start.record()
@@ -379,7 +397,7 @@ def run_gpu_arm(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--instances", type=int, default=B_PER_GPU, help="reactors per GPU per step")

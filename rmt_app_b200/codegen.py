@@ -47,21 +47,54 @@ def _powi_expr(a, k):
     k = abs(k)
     if k > 16:
         return "pow(%s, %s)" % (a, lit(-k if neg else k))
+    if neg:
+        return "RMT_DIV(1.0, %s)" % _powi_expr(a, k)
     # square-and-multiply over a fully parenthesised chain
     e = "*".join([a]*k) if k <= 3 else None
     if e is None:
         half = _powi_expr(a, k//2)
         e = "((%s)*(%s)%s)" % (half, half, "*" + a if k % 2 else "")
-    return "(1.0/(%s))" % e if neg else "(%s)" % e
+    return "(%s)" % e
 
 
-def emit_dag(g: Graph, outs, in_name, indent="    "):
+class ConstPool:
+    """Full-mantissa double literals are fetched from constant memory (a c[bank][off]
+    operand of DFMA/DMUL) instead of being materialised with two UMOVs each; values
+    whose low 32 bits are zero (1.0, 0.5, 1000.0 ...) fit the instruction's immediate."""
+
+    def __init__(self, name="RMT_KC"):
+        self.name, self.index, self.values = name, {}, []
+
+    def ref(self, v):
+        import struct
+        v = float(v)
+        bits = struct.unpack("<Q", struct.pack("<d", v))[0]
+        if bits & 0xFFFFFFFF == 0 or v != v:
+            s = lit(v)
+            return "(" + s + ")" if v < 0 else s
+        k = self.index.get(bits)
+        if k is None:
+            k = self.index[bits] = len(self.values)
+            self.values.append(v)
+        return "RMT_KL(%d, %s)" % (k, lit(v))
+
+    def declaration(self):
+        vals = self.values or [0.0]
+        return ("__constant__ double %s[%d] = %s;\n"
+                "#if RMT_USE_CBANK\n#define RMT_KL(k, v) %s[k]\n#else\n#define RMT_KL(k, v) (v)\n#endif"
+                % (self.name, len(vals), _arr(vals), self.name))
+
+
+def emit_dag(g: Graph, outs, in_name, indent="    ", pool=None):
     """Return (lines, refs): C statements computing every node reachable from
     `outs`, and the C expression naming each requested output."""
     lines = []
     name = {}
     for n in g.topo([o for o in outs if o is not None]):
         if n.op == "const":
+            if pool is not None:
+                name[n.id] = pool.ref(n.value)
+                continue
             name[n.id] = lit(n.value)
             if n.value < 0:
                 name[n.id] = "(" + name[n.id] + ")"
@@ -69,7 +102,9 @@ def emit_dag(g: Graph, outs, in_name, indent="    "):
             name[n.id] = in_name(n.name)
         else:
             a = [name[x.id] for x in n.args]
-            if n.op in _INFIX:
+            if n.op == "div":
+                e = "RMT_DIV(%s, %s)" % (a[0], a[1])
+            elif n.op in _INFIX:
                 e = "%s %s %s" % (a[0], _INFIX[n.op], a[1])
             elif n.op == "neg":
                 e = "-%s" % a[0]
@@ -200,14 +235,22 @@ def generate_model_header(spec, tableau="rodas4"):
     A("__device__ constexpr double RMT_NU[RMT_NR][RMT_NC] = %s;" % _arr2(spec.nu))
     A("__device__ constexpr double RMT_DH25[RMT_NR] = %s;" % _arr(spec.dH25))
     A("__device__ constexpr double RMT_DCP[RMT_NR][4] = %s;" % _arr2(spec.dcp))
+    A("// constant-bank mirrors used as instruction operands (the constexpr copies drive compile-time structure)")
+    A("__constant__ double RMT_cMW[RMT_NC] = %s;" % _arr([c.MW for c in comps]))
+    A("__constant__ double RMT_cCP[RMT_NC][4] = %s;" % _arr2([c.cp for c in comps]))
+    A("__constant__ double RMT_cCPREF[RMT_NC] = %s;" % _arr([c.cp_at(Tref) for c in comps]))
+    A("__constant__ double RMT_cDH25[RMT_NR] = %s;" % _arr(spec.dH25))
+    A("__constant__ double RMT_cDCP[RMT_NR][4] = %s;" % _arr2(spec.dcp))
     A("")
 
     # ---- rates -----------------------------------------------------------------
+    decl_at = len(L)
     A("// traced RATES (rmtReaction.py:11-61 semantics): R[j] in mol/(m^3 s)")
     A("__device__ __forceinline__ void rmt_rates(const double T, const double P, const double (&y)[RMT_NC],")
     A("        const double (&C)[RMT_NC], const double* __restrict__ kp, double (&R)[RMT_NR])")
     A("{")
-    lines, refs = emit_dag(g, kin.rates, in_name)
+    pool = ConstPool()
+    lines, refs = emit_dag(g, kin.rates, in_name, pool=pool)
     L.extend(lines)
     for j, r in enumerate(refs):
         A("    R[%d] = %s;" % (j, r))
@@ -223,7 +266,7 @@ def generate_model_header(spec, tableau="rodas4"):
         outs += list(P["y%d" % i])
     for i in range(nc):
         outs += list(P["C%d" % i])
-    lines, refs = emit_dag(g, outs, in_name)
+    lines, refs = emit_dag(g, outs, in_name, pool=pool)
     L.extend(lines)
     it = iter(refs)
     for j in range(nr):
@@ -241,6 +284,8 @@ def generate_model_header(spec, tableau="rodas4"):
     A("}")
     A("")
 
+    L.insert(decl_at, "// literal pool of the traced kinetics (constant bank operands)\n" + pool.declaration())
+
     # ---- Rosenbrock tableau ------------------------------------------------------
     tab = TABLEAUX[tableau]
     s = tab["stages"]
@@ -256,5 +301,10 @@ def generate_model_header(spec, tableau="rodas4"):
     A("__device__ constexpr double RMT_ROS_M[RMT_ROS_S] = %s;" % _arr(tab["m"]))
     A("__device__ constexpr double RMT_ROS_E[RMT_ROS_S] = %s;" % _arr(tab["e"]))
     A("__device__ constexpr double RMT_ROS_D[2][RMT_ROS_S] = %s;" % _arr2(tab["dense"]))
+    A("__constant__ double RMT_cROS_A[RMT_ROS_S][RMT_ROS_S] = %s;" % _arr2(full(tab["a"])))
+    A("__constant__ double RMT_cROS_C[RMT_ROS_S][RMT_ROS_S] = %s;" % _arr2(full(tab["c"])))
+    A("__constant__ double RMT_cROS_M[RMT_ROS_S] = %s;" % _arr(tab["m"]))
+    A("__constant__ double RMT_cROS_E[RMT_ROS_S] = %s;" % _arr(tab["e"]))
+    A("__constant__ double RMT_cROS_D[2][RMT_ROS_S] = %s;" % _arr2(tab["dense"]))
     A("")
     return "\n".join(L) + "\n"

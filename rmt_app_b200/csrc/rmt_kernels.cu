@@ -19,6 +19,40 @@
 // (inputs [row][B], constants [row][B], states [var][B] or [var][node][B],
 // outputs [point][var][B]) so that a warp's lanes touch consecutive doubles.
 
+// Division.  IEEE `a/b` on sm_100a is a ~14-instruction sequence with a branch to a slow path
+// (BSSY/BSYNC + call) — with ~35 divisions per RHS that is a fifth of the instruction stream and a
+// steady source of instruction-fetch stalls.  The hot code therefore multiplies by a Newton-refined
+// reciprocal: MUFU.RCP64H seed (~2^-20) + two FMA iterations -> <= 2 ulp, branch free.  Zero / Inf /
+// NaN operands still end in Inf / NaN, which the integrator's domain guard turns into a rejected
+// step.  -DRMT_EXACT_DIV=1 restores IEEE division everywhere.
+#ifndef RMT_EXACT_DIV
+#define RMT_EXACT_DIV 0
+#endif
+__device__ __forceinline__ double rmt_rcp(const double x)
+{
+#if RMT_EXACT_DIV
+    return 1.0/x;
+#else
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+#endif
+}
+#if RMT_EXACT_DIV
+#define RMT_DIV(a, b) ((a)/(b))
+#else
+#define RMT_DIV(a, b) ((a)*rmt_rcp(b))
+#endif
+
+// full-mantissa literals of the generated kinetics: constant-bank operands (1) or instruction immediates (0)
+#ifndef RMT_USE_CBANK
+#define RMT_USE_CBANK 1
+#endif
+
 #include "rmt_model.cuh"
 
 #define RMT_R_CONST 8.314472            // core/constants.py:8
@@ -36,7 +70,16 @@
 #define RMT_IT (RMT_NC + 1)                      // N1: index of T-hat
 
 #ifndef RMT_BLOCK
-#define RMT_BLOCK 128
+#define RMT_BLOCK 256
+#endif
+// warps of a block are kept in (loose) lockstep so that they share instruction-cache lines:
+// 0 = free running, 1 = one block barrier per step attempt, 2 = one per Rosenbrock stage
+#ifndef RMT_SYNC
+#define RMT_SYNC 1
+#endif
+// 1 = the Rosenbrock stage loop is a real loop (one copy of the RHS code), 0 = fully unrolled
+#ifndef RMT_ROLL
+#define RMT_ROLL 1
 #endif
 
 typedef long long i64;
@@ -93,8 +136,8 @@ static_assert(RMT_NCONST == RMT_NCONST_VALUE, "constant row count");
 __device__ __forceinline__ double rmt_cp(const int i, const double T, const double T2, const double T3)
 {
     // Cp string "a0 + a1*T + a2*(T**2) + a3*(T**3)", left to right (rmtThermo.py:37)
-    double v = RMT_CP[i][0] + RMT_CP[i][1]*T + RMT_CP[i][2]*T2;
-    if (RMT_CP[i][3] != 0.0) v = v + RMT_CP[i][3]*T3;
+    double v = RMT_cCP[i][0] + RMT_cCP[i][1]*T + RMT_cCP[i][2]*T2;
+    if (RMT_CP[i][3] != 0.0) v = v + RMT_cCP[i][3]*T3;
     return v;
 }
 
@@ -181,9 +224,10 @@ extern "C" __global__ void __launch_bounds__(128) rmt_setup(const RmtInputs in, 
 
 // hot constants kept in registers by the RHS / integrator
 struct Hot {
-    double Cmax, Tf, Pf, C0, ui0, us0, rho0, Cpf, Gm, Gh, ergA, ergC, Ua, Tm, eps;
+    double Cmax, Tf, Pf, us0, ergA, ergC, Ua, Tm;
+    double invC0, invRho0, invGm, invGh, epsCpf;     // 1/C0, 1/rho0, 1/Gm, 1/Gh, eps/Cpf
 #if defined(RMT_MODEL_N1)
-    double beta;                 // Pf/zf
+    double invBeta;              // zf/Pf
 #else
     double F1, dz, invdz;        // 1/(eps*(zf/vf)), node spacing
     double iv[RMT_NC];           // inlet boundary values C0_i/Cmax
@@ -194,18 +238,19 @@ struct Hot {
 __device__ __forceinline__ void rmt_load_hot(const double* __restrict__ consts, const i64 B, const i64 i, Hot& h)
 {
     const double* c = consts + i;
-    h.Cmax = c[(i64)K_CMAX*B]; h.Tf = c[(i64)K_TF*B]; h.Pf = c[(i64)K_PF*B]; h.C0 = c[(i64)K_C0*B];
-    h.ui0 = c[(i64)K_UI0*B]; h.us0 = c[(i64)K_US0*B]; h.rho0 = c[(i64)K_RHO0*B]; h.Cpf = c[(i64)K_CPF*B];
-    h.Gm = c[(i64)K_GM*B]; h.Gh = c[(i64)K_GH*B];
+    h.Cmax = c[(i64)K_CMAX*B]; h.Tf = c[(i64)K_TF*B]; h.Pf = c[(i64)K_PF*B];
+    h.us0 = c[(i64)K_US0*B];
+    h.invC0 = 1.0/c[(i64)K_C0*B]; h.invRho0 = 1.0/c[(i64)K_RHO0*B];
+    h.invGm = 1.0/c[(i64)K_GM*B]; h.invGh = 1.0/c[(i64)K_GH*B];
     const double mu = c[(i64)K_MU*B], eps = c[(i64)K_EPS*B], dp = c[(i64)K_DP*B], zf = c[(i64)K_ZF*B];
-    h.eps = eps;
+    h.epsCpf = eps/c[(i64)K_CPF*B];
     // Ergun coefficients (pbHomoReactor.py:3214-3217): ergA*ergB = cA*us, ergC*ergD = cC*rho*us^2
     h.ergA = 150*mu/(dp*dp)*(((1 - eps)*(1 - eps))/(eps*eps*eps));
     h.ergC = 1.75/dp*((1 - eps)/(eps*eps*eps));
     h.Ua = c[(i64)K_U*B]*c[(i64)K_A*B];
     h.Tm = c[(i64)K_TM*B];
 #if defined(RMT_MODEL_N1)
-    h.beta = h.Pf/zf;
+    h.invBeta = zf/h.Pf;
 #else
     const double vf = c[(i64)K_VF*B];
     h.F1 = 1/(eps*(zf/vf));
@@ -222,7 +267,7 @@ __device__ __forceinline__ void rmt_load_hot(const double* __restrict__ consts, 
 // ---------------------------------------------------------------------------------
 struct Point {
     double y[RMT_NC];      // mole fractions
-    double S;              // total concentration [mol/m^3]
+    double S, invS;        // total concentration [mol/m^3] and its reciprocal
     double T, P;
     double MWm, rho;       // mixture MW [kg/mol], EOS density
     double R[RMT_NR];      // reaction rates
@@ -247,27 +292,33 @@ __device__ __forceinline__ void rmt_point(const double (&C)[RMT_NC], const doubl
 #pragma unroll
     for (int i = 0; i < RMT_NC; ++i) S += C[i];
     p.S = S; p.T = T; p.P = P;
+    const double invS = rmt_rcp(S);
+    p.invS = invS;
     double mw = 0.0;
 #pragma unroll
-    for (int i = 0; i < RMT_NC; ++i) { p.y[i] = C[i]/S; mw += p.y[i]*RMT_MW[i]; }
+    for (int i = 0; i < RMT_NC; ++i) { p.y[i] = C[i]*invS; mw += p.y[i]*RMT_cMW[i]; }
     p.MWm = mw*1e-3;
-    p.rho = P/((RMT_R_CONST/p.MWm)*T);                       // rmtThermo.py:353-369
+    p.rho = (P*p.MWm)*rmt_rcp(RMT_R_CONST*T);                 // P/((R/MW)*T), rmtThermo.py:353-369
     if (JAC) rmt_rates_jac(T, P, p.y, C, h.kp, p.R, pj.dRdT, pj.dRdP, pj.dRdy, pj.dRdC);
     else rmt_rates(T, P, p.y, C, h.kp, p.R);
 #pragma unroll
     for (int i = 0; i < RMT_NC; ++i) {                        // rmtReaction.py:64-97
         double acc = 0.0;
 #pragma unroll
-        for (int j = 0; j < RMT_NR; ++j) if (RMT_NU[j][i] != 0.0) acc += RMT_NU[j][i]*p.R[j];
+        for (int j = 0; j < RMT_NR; ++j) if (RMT_NU[j][i] != 0.0) acc += RMT_NU[j][i]*p.R[j];   // small integers: immediates
         p.r[i] = acc;
     }
     const double T2 = T*T, T3 = T2*T;
     double Cp = 0.0, dCp = 0.0;
 #pragma unroll
     for (int i = 0; i < RMT_NC; ++i) {
-        p.cpm[i] = (RMT_CPREF[i] + rmt_cp(i, T, T2, T3))*0.50;
+        p.cpm[i] = (RMT_cCPREF[i] + rmt_cp(i, T, T2, T3))*0.50;
         Cp += p.y[i]*p.cpm[i];
-        if (JAC) dCp += p.y[i]*(0.5*(RMT_CP[i][1] + 2.0*RMT_CP[i][2]*T + 3.0*RMT_CP[i][3]*T2));
+        if (JAC) {
+            double d = RMT_cCP[i][1] + 2.0*RMT_cCP[i][2]*T;
+            if (RMT_CP[i][3] != 0.0) d += 3.0*RMT_cCP[i][3]*T2;
+            dCp += p.y[i]*(0.5*d);
+        }
     }
     p.Cp = Cp;
     if (JAC) pj.dCpdT = dCp;
@@ -275,10 +326,10 @@ __device__ __forceinline__ void rmt_point(const double (&C)[RMT_NC], const doubl
     double q = 0.0;
 #pragma unroll
     for (int j = 0; j < RMT_NR; ++j) {                        // rmtThermo.py:258-312 + StHeRe25
-        const double dcp = RMT_DCP[j][0] + RMT_DCP[j][1]*T + RMT_DCP[j][2]*T2 + RMT_DCP[j][3]*T3;
-        p.dH[j] = dcp*dT + RMT_DH25[j];
+        const double dcp = RMT_cDCP[j][0] + RMT_cDCP[j][1]*T + RMT_cDCP[j][2]*T2 + RMT_cDCP[j][3]*T3;
+        p.dH[j] = dcp*dT + RMT_cDH25[j];
         q += p.R[j]*p.dH[j];
-        if (JAC) pj.ddHdT[j] = dcp + dT*(RMT_DCP[j][1] + 2.0*RMT_DCP[j][2]*T + 3.0*RMT_DCP[j][3]*T2);
+        if (JAC) pj.ddHdT[j] = dcp + dT*(RMT_cDCP[j][1] + 2.0*RMT_cDCP[j][2]*T + 3.0*RMT_cDCP[j][3]*T2);
     }
     p.q = q;
     p.Qm = (h.Tm == 0.0) ? 0.0 : h.Ua*(h.Tm - T);             // rmtUtility.py:424-452
@@ -305,25 +356,29 @@ __device__ __forceinline__ void n1_eval(const double (&yh)[RMT_N], const Hot& h,
 #endif
     Point p; PointJac pj;
     rmt_point<JAC>(C, T, P, h, p, pj);
-    // velocities (rmtUtility.py:405-421; :3180-3186)
-    const double ui = h.ui0*(p.S/h.C0)*(h.Pf/P);
-    const double uih = ui/h.ui0;
-    const double us = ui*h.eps;
-    const double ush = us/h.us0;
-    const double rhoh = p.rho/h.rho0;
+    // velocities (rmtUtility.py:405-421; :3180-3186): u/u0 = (C/C0)*(Pf/P) for both the interstitial
+    // and the superficial velocity (us = ui*eps, us0 = ui0*eps)
+    const double invP = rmt_rcp(P);
+    const double w = (p.S*h.invC0)*(h.Pf*invP);
+    const double us = h.us0*w;
+    const double rhoh = p.rho*h.invRho0;
     // Ergun (:3214-3220)
-    f[RMT_IP] = -1*(h.ergA*us + h.ergC*p.rho*(us*us))/h.beta;
-    const double c1 = 1/ush;
+    f[RMT_IP] = -1*(h.ergA*us + h.ergC*p.rho*(us*us))*h.invBeta;
+    const double c1 = rmt_rcp(w);
+    const double c1Gm = c1*h.invGm;
 #pragma unroll
-    for (int i = 0; i < RMT_NC; ++i) f[i] = c1*(p.r[i]/h.Gm);    // :3283-3289
+    for (int i = 0; i < RMT_NC; ++i) f[i] = p.r[i]*c1Gm;         // :3283-3289
 #if !RMT_ISO
-    const double cpeffh = (p.Cp/h.Cpf)*h.eps;                 // :3252-3257
-    const double Dn = rhoh*cpeffh*uih;
-    const double Nn = (-p.q + p.Qm)/h.Gh;
-    f[RMT_IT] = (1/Dn)*Nn;                                    // :3284, :3298
+    const double cpeffh = p.Cp*h.epsCpf;                       // (Cp/Cpf)*eps, :3252-3257
+    const double invDn = rmt_rcp(rhoh*cpeffh*w);
+    f[RMT_IT] = ((-p.q + p.Qm)*h.invGh)*invDn;                 // :3284, :3298
 #endif
     if (JAC) {
-        const double invS = 1.0/p.S;
+        const double invS = p.invS;
+        const double invT = rmt_rcp(T), invMW = rmt_rcp(p.MWm);
+#if !RMT_ISO
+        const double invCp = rmt_rcp(p.Cp);
+#endif
         // sum_i dRdy[j][i]*y_i, used by every species column
         double sy[RMT_NR];
 #pragma unroll
@@ -335,7 +390,7 @@ __device__ __forceinline__ void n1_eval(const double (&yh)[RMT_N], const Hot& h,
 #endif
             sy[j] = a;
         }
-        const double inv_ushGm = c1/h.Gm;
+        const double inv_ushGm = c1Gm;
 #pragma unroll
         for (int col = 0; col < RMT_N; ++col) {
             const bool isC = col < RMT_NC, isP = col == RMT_IP, isT = (!RMT_ISO) && col == RMT_IT;
@@ -343,7 +398,7 @@ __device__ __forceinline__ void n1_eval(const double (&yh)[RMT_N], const Hot& h,
             double dlnw, dlnrho, dR[RMT_NR];
             if (isC) {
                 dlnw = h.Cmax*invS;
-                dlnrho = h.Cmax*(1e-3*RMT_MW[col < RMT_NC ? col : 0] - p.MWm)*invS/p.MWm;
+                dlnrho = h.Cmax*(1e-3*RMT_cMW[col < RMT_NC ? col : 0] - p.MWm)*invS*invMW;
 #pragma unroll
                 for (int j = 0; j < RMT_NR; ++j) {
                     double a = 0.0;
@@ -356,18 +411,18 @@ __device__ __forceinline__ void n1_eval(const double (&yh)[RMT_N], const Hot& h,
                     dR[j] = h.Cmax*a;
                 }
             } else if (isP) {
-                dlnw = -h.Pf/P;
-                dlnrho = h.Pf/P;
+                dlnw = -h.Pf*invP;
+                dlnrho = h.Pf*invP;
 #pragma unroll
                 for (int j = 0; j < RMT_NR; ++j) dR[j] = h.Pf*pj.dRdP[j];
             } else {
                 dlnw = 0.0;
-                dlnrho = -h.Tf/T;
+                dlnrho = -h.Tf*invT;
 #pragma unroll
                 for (int j = 0; j < RMT_NR; ++j) dR[j] = h.Tf*pj.dRdT[j];
             }
             const double dus = us*dlnw;
-            J(RMT_IP, col, -1*(h.ergA*dus + h.ergC*(p.rho*dlnrho*(us*us) + 2.0*p.rho*us*dus))/h.beta);
+            J(RMT_IP, col, -1*(h.ergA*dus + h.ergC*(p.rho*dlnrho*(us*us) + 2.0*p.rho*us*dus))*h.invBeta);
 #pragma unroll
             for (int i = 0; i < RMT_NC; ++i) {
                 double dr = 0.0;
@@ -387,9 +442,9 @@ __device__ __forceinline__ void n1_eval(const double (&yh)[RMT_N], const Hot& h,
                 for (int j = 0; j < RMT_NR; ++j) dq += p.R[j]*(h.Tf*pj.ddHdT[j]);
                 dQm = (h.Tm == 0.0) ? 0.0 : -h.Ua*h.Tf;
             } else dCp = 0.0;
-            const double dN = (-dq + dQm)/h.Gh;
-            const double dlnD = dlnrho + dCp/p.Cp + dlnw;
-            J(RMT_IT, col, dN/Dn - f[RMT_IT]*dlnD);
+            const double dN = (-dq + dQm)*h.invGh;
+            const double dlnD = dlnrho + dCp*invCp + dlnw;
+            J(RMT_IT, col, dN*invDn - f[RMT_IT]*dlnD);
 #endif
         }
     }
@@ -518,7 +573,7 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
 
     i64 inst = -1;
     bool exhausted = false;
-    Hot h;
+    Hot h = {};
     double y[RMT_N];
     double t = 0.0, hstep = 0.0, hacc = 0.0, erracc = 0.0, tend = 0.0;
     int nacc = 0, nrej = 0, next_e = 0, nanrej = 0;
@@ -552,8 +607,18 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
                 }
             }
         }
+#if RMT_SYNC
+        if (__syncthreads_and(inst < 0)) break;      // block-uniform exit; also re-aligns the warps
+#else
         if (__all_sync(FULL, inst < 0)) break;
-        if (inst < 0) continue;
+#endif
+        // Lanes without work: in the free-running / per-attempt modes they skip the attempt; with per-stage
+        // barriers (RMT_SYNC == 2) they run it as ghosts on their stale state — all global writes below are
+        // predicated on `live` — so that every thread reaches every barrier converged.
+        const bool live = inst >= 0;
+#if RMT_SYNC != 2
+        if (!live) continue;
+#endif
 
         // ---- one step attempt ----
         double f0[RMT_N];
@@ -584,40 +649,44 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
         const bool clipped = hstep*1.01 >= hlim;
         const double hh = clipped ? hlim : hstep;
 
-        // W = I/(h*gamma) - J, LU with partial pivoting (row permutation kept in registers)
+        // W = I/(h*gamma) - J, LU with partial pivoting.  The row permutation lives in registers as the
+        // shared-memory address of each (pivoted) row, so every access is [row + immediate].
         const double dg = 1.0/(hh*RMT_ROS_GAMMA);
 #pragma unroll
         for (int i = 0; i < RMT_N; ++i)
 #pragma unroll
             for (int j = 0; j < RMT_N; ++j) LU(i, j) = (i == j ? dg : 0.0) - LU(i, j);
+        double* row[RMT_N];
         int perm[RMT_N];
 #pragma unroll
-        for (int i = 0; i < RMT_N; ++i) perm[i] = i;
+        for (int i = 0; i < RMT_N; ++i) { row[i] = sm + (i*RMT_N)*RMT_BLOCK; perm[i] = i; }
+#define ROW(i, j) row[i][(j)*RMT_BLOCK]
 #pragma unroll
         for (int k = 0; k < RMT_N; ++k) {
-            double best = fabs(LU(perm[k], k));
+            double best = fabs(ROW(k, k));
             int bi = k;
 #pragma unroll
             for (int i = k + 1; i < RMT_N; ++i) {
-                const double v = fabs(LU(perm[i], k));
+                const double v = fabs(ROW(i, k));
                 if (v > best) { best = v; bi = i; }
             }
 #pragma unroll
             for (int i = k + 1; i < RMT_N; ++i)
-                if (i == bi) { const int tp = perm[k]; perm[k] = perm[i]; perm[i] = tp; }
-            const int pk = perm[k];
-            const double piv = 1.0/LU(pk, k);
-            LU(pk, k) = piv;                                  // store reciprocal pivot
+                if (i == bi) {
+                    double* tr = row[k]; row[k] = row[i]; row[i] = tr;
+                    const int tp = perm[k]; perm[k] = perm[i]; perm[i] = tp;
+                }
+            const double piv = rmt_rcp(ROW(k, k));
+            ROW(k, k) = piv;                                  // store reciprocal pivot
             double urow[RMT_N];
 #pragma unroll
-            for (int j = k + 1; j < RMT_N; ++j) urow[j] = LU(pk, j);
+            for (int j = k + 1; j < RMT_N; ++j) urow[j] = ROW(k, j);
 #pragma unroll
             for (int i = k + 1; i < RMT_N; ++i) {
-                const int pi = perm[i];
-                const double l = LU(pi, k)*piv;
-                LU(pi, k) = l;
+                const double l = ROW(i, k)*piv;
+                ROW(i, k) = l;
 #pragma unroll
-                for (int j = k + 1; j < RMT_N; ++j) LU(pi, j) -= l*urow[j];
+                for (int j = k + 1; j < RMT_N; ++j) ROW(i, j) -= l*urow[j];
             }
         }
 
@@ -626,8 +695,15 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
 #pragma unroll
         for (int i = 0; i < RMT_N; ++i) { ynew[i] = y[i]; errv[i] = 0.0; }
         const double invh = 1.0/hh;
+#if RMT_ROLL
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
         for (int s = 0; s < RMT_ROS_S; ++s) {
+#if RMT_SYNC == 2
+            __syncthreads();
+#endif
             double rhs[RMT_N];
             if (s == 0) {
 #pragma unroll
@@ -636,46 +712,81 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
                 double u[RMT_N];
 #pragma unroll
                 for (int i = 0; i < RMT_N; ++i) u[i] = y[i];
+#if RMT_ROLL
+                // rolled form: one copy of the RHS / triangular-solve code for all stages (instruction-cache
+                // footprint); tableau rows are read from the constant bank with a runtime stage index
+                for (int j = 0; j < s; ++j) {
+                    const double aj = RMT_cROS_A[s][j];
+                    const double* kj = &KS(j, 0);
+#pragma unroll
+                    for (int i = 0; i < RMT_N; ++i) u[i] += aj*kj[i*RMT_BLOCK];
+                }
+#else
 #pragma unroll
                 for (int j = 0; j < s; ++j)
                     if (RMT_ROS_A[s][j] != 0.0) {
 #pragma unroll
-                        for (int i = 0; i < RMT_N; ++i) u[i] += RMT_ROS_A[s][j]*KS(j, i);
+                        for (int i = 0; i < RMT_N; ++i) u[i] += RMT_cROS_A[s][j]*KS(j, i);
                     }
+#endif
                 n1_eval<false>(u, h, rhs, NoJac());
+#if RMT_ROLL
+                for (int j = 0; j < s; ++j) {
+                    const double cj = RMT_cROS_C[s][j]*invh;
+                    const double* kj = &KS(j, 0);
+#pragma unroll
+                    for (int i = 0; i < RMT_N; ++i) rhs[i] += cj*kj[i*RMT_BLOCK];
+                }
+#else
 #pragma unroll
                 for (int j = 0; j < s; ++j)
                     if (RMT_ROS_C[s][j] != 0.0) {
-                        const double cj = RMT_ROS_C[s][j]*invh;
+                        const double cj = RMT_cROS_C[s][j]*invh;
 #pragma unroll
                         for (int i = 0; i < RMT_N; ++i) rhs[i] += cj*KS(j, i);
                     }
+#endif
             }
-            // solve W k = rhs : stash rhs in the K_s slot so the permuted access is an address, not a register index
+            // solve W k = rhs: the right-hand side is stashed in the K_s slot so that the permuted read
+            // is an address, not a register index
+            double* ks = &KS(s, 0);
 #pragma unroll
-            for (int i = 0; i < RMT_N; ++i) KS(s, i) = rhs[i];
+            for (int i = 0; i < RMT_N; ++i) ks[i*RMT_BLOCK] = rhs[i];
             double x[RMT_N];
 #pragma unroll
             for (int i = 0; i < RMT_N; ++i) {
-                double v = KS(s, perm[i]);
+                double v = ks[perm[i]*RMT_BLOCK];
 #pragma unroll
-                for (int j = 0; j < i; ++j) v -= LU(perm[i], j)*x[j];
+                for (int j = 0; j < i; ++j) v -= ROW(i, j)*x[j];
                 x[i] = v;
             }
 #pragma unroll
             for (int i = RMT_N - 1; i >= 0; --i) {
                 double v = x[i];
 #pragma unroll
-                for (int j = i + 1; j < RMT_N; ++j) v -= LU(perm[i], j)*x[j];
-                x[i] = v*LU(perm[i], i);
+                for (int j = i + 1; j < RMT_N; ++j) v -= ROW(i, j)*x[j];
+                x[i] = v*ROW(i, i);
             }
+#if RMT_ROLL
+            const double ms = RMT_cROS_M[s], es = RMT_cROS_E[s];
 #pragma unroll
             for (int i = 0; i < RMT_N; ++i) {
-                KS(s, i) = x[i];
-                if (RMT_ROS_M[s] != 0.0) ynew[i] += RMT_ROS_M[s]*x[i];
-                if (RMT_ROS_E[s] != 0.0) errv[i] += RMT_ROS_E[s]*x[i];
+                ks[i*RMT_BLOCK] = x[i];
+                ynew[i] += ms*x[i];
+                errv[i] += es*x[i];
             }
+#else
+#pragma unroll
+            for (int i = 0; i < RMT_N; ++i) {
+                ks[i*RMT_BLOCK] = x[i];
+                if (RMT_ROS_M[s] == 1.0) ynew[i] += x[i];
+                else if (RMT_ROS_M[s] != 0.0) ynew[i] += RMT_cROS_M[s]*x[i];
+                if (RMT_ROS_E[s] == 1.0) errv[i] += x[i];
+                else if (RMT_ROS_E[s] != 0.0) errv[i] += RMT_ROS_E[s]*x[i];
+            }
+#endif
         }
+#undef ROW
 
         // error norm (scipy/integrate/_ivp/common.py:63-65 rms norm; radau.py scale)
         double err = 0.0;
@@ -735,17 +846,17 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
                             double d2 = 0.0, d3 = 0.0;
 #pragma unroll
                             for (int s = 0; s < RMT_ROS_S; ++s) {
-                                if (RMT_ROS_D[0][s] != 0.0) d2 += RMT_ROS_D[0][s]*KS(s, i);
-                                if (RMT_ROS_D[1][s] != 0.0) d3 += RMT_ROS_D[1][s]*KS(s, i);
+                                if (RMT_ROS_D[0][s] != 0.0) d2 += RMT_cROS_D[0][s]*KS(s, i);
+                                if (RMT_ROS_D[1][s] != 0.0) d3 += RMT_cROS_D[1][s]*KS(s, i);
                             }
                             v[i] = y[i]*th1 + th*(ynew[i] + th1*(d2 + th*d3));
                         }
                     }
-                    n1_write_point(a, h, inst, next_e, v);
+                    if (live) n1_write_point(a, h, inst, next_e, v);
                     ++next_e;
                 }
             } else if (clipped && next_e < a.n_eval) {
-                n1_write_point(a, h, inst, next_e, ynew);
+                if (live) n1_write_point(a, h, inst, next_e, ynew);
                 ++next_e;
             }
             t = tnew;
@@ -766,7 +877,7 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
             else if (hstep < 1e-14*fmax(tend, 1.0)) fin = 2;
             else if (nanrej > 30) fin = 3;
         }
-        if (fin >= 0) {
+        if (fin >= 0 && live) {
             a.status[inst] = fin;
             a.stats[inst] = nacc; a.stats[a.B + inst] = nrej;
             a.stats[2*a.B + inst] = (nacc + nrej)*(RMT_ROS_S - 1); a.stats[3*a.B + inst] = nacc + nrej;

@@ -128,15 +128,18 @@ int rmt_n1_solve_host(rmt_module_t m, int64_t B, const double* h_rows, int32_t n
 /* ---- N2: modelEquationN2 (:3706-4134) and the slab loop of runN2 (:3589-3685) ---
  * States are variable-major like the reference's reshape (:3873): d_y, d_f
  * [n][zNo][B].  rmt_n2_solve integrates t in [0, period] and writes the state at
- * the end of each of the tNo slabs: d_out [tNo][n][zNo][B] (out_mode as above,
- * mode 1 rows = y_i, T [K]).  d_work is caller-provided scratch of
- * rmt_n2_work_doubles(m, B, zNo) doubles. */
+ * the end of each of the tNo slabs: d_out [tNo][rows][zNo][B] (out_mode as for N1;
+ * mode 1 rows = y_i, T [K]; mode 2 rows = raw | C_i | (y_i, T)).  The reference
+ * restarts solve_ivp at every slab (:3589-3685); here the integration continues and
+ * a step is clipped to end on each slab boundary.  d_work is caller-provided scratch
+ * of rmt_n2_work_doubles(m, B, zNo) doubles.  ctrl as in rmt_n1_solve. */
 int rmt_n2_rhs(rmt_module_t m, int64_t B, int32_t zNo, const double* d_consts, const double* d_y, double* d_f,
                void* stream);
 int64_t rmt_n2_work_doubles(rmt_module_t m, int64_t B, int32_t zNo);
 int rmt_n2_solve(rmt_module_t m, int64_t B, int32_t zNo, int32_t tNo, double period, const double* d_consts,
                  double rtol, double atol, int32_t max_steps, int32_t out_mode,
-                 double* d_out, int32_t* d_status, int32_t* d_stats, double* d_work, void* stream);
+                 double* d_out, int32_t* d_status, int32_t* d_stats, double* d_work, const double* ctrl,
+                 void* stream);
 
 /* ---- ensemble reductions (per GPU; the cross-GPU step is an NCCL all-reduce of
  * these three numbers, done by the caller's torch.distributed group) ------------- */

@@ -7,4 +7,6 @@ pseudo-homogeneous packed-bed reactor models N1 (steady state) and N2
 from .rmt import rmtExe, rmtCom, rmtExeBatch      # noqa: F401
 from .engine import solverSetting, Workspace       # noqa: F401
 
-__all__ = ["rmtExe", "rmtCom", "rmtExeBatch", "solverSetting", "Workspace"]
+from .ensemble import rmtExeBatchSharded            # noqa: F401
+
+__all__ = ["rmtExe", "rmtCom", "rmtExeBatch", "rmtExeBatchSharded", "solverSetting", "Workspace"]

@@ -57,7 +57,8 @@ SIGNATURES = {
                                     _vp, _vp, _vp, _pdbl, _vp, _pdbl]),
     "rmt_n2_rhs": (C.c_int, [_u64, _i64, _i32, _vp, _vp, _vp, _vp]),
     "rmt_n2_work_doubles": (_i64, [_u64, _i64, _i32]),
-    "rmt_n2_solve": (C.c_int, [_u64, _i64, _i32, _i32, _dbl, _vp, _dbl, _dbl, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "rmt_n2_solve": (C.c_int, [_u64, _i64, _i32, _i32, _dbl, _vp, _dbl, _dbl, _i32, _i32, _vp, _vp, _vp, _vp, _pdbl,
+                               _vp]),
     "rmt_reduce_objective": (C.c_int, [_u64, _i64, _vp, _i64, _pdbl, _pdbl, C.POINTER(_i64), _vp]),
     "rmt_debug_trace": (C.c_int, [_vp, _i32, _i64]),
     "rmt_fp64_peak": (C.c_int, [_u64, _i32, _i32, _pdbl]),
@@ -229,9 +230,11 @@ class Module:
         return n
 
     def n2_solve(self, B, zNo, tNo, period, d_consts, rtol, atol, d_out, d_status, d_stats, d_work,
-                 max_steps=1000000, out_mode=1, stream=None):
+                 max_steps=1000000, out_mode=1, ctrl=None, stream=None):
+        ctl = None if ctrl is None else np.ascontiguousarray(ctrl, dtype=np.float64)
         _check(lib().rmt_n2_solve(self.handle, B, zNo, tNo, period, _ptr(d_consts), rtol, atol, max_steps, out_mode,
-                                  _ptr(d_out), _ptr(d_status), _ptr(d_stats), _ptr(d_work), stream))
+                                  _ptr(d_out), _ptr(d_status), _ptr(d_stats), _ptr(d_work),
+                                  None if ctl is None else _dptr(ctl), stream))
 
     def reduce_objective(self, n, d_obj, index_offset=0, stream=None):
         s, mn, am = _dbl(0), _dbl(0), _i64(0)

@@ -199,8 +199,9 @@ struct SolveArgsN2 {
     int max_steps;
     int out_mode;
     CUdeviceptr out, status, stats, work, queue;
+    double ctrl[6];
 };
-static_assert(sizeof(SolveArgsN2) == 96, "SolveArgsN2 layout");
+static_assert(sizeof(SolveArgsN2) == 144, "SolveArgsN2 layout");
 
 // RmtInputs { const double* rows; i64 B; int map[NIN]; double u[NIN]; }
 std::vector<char> pack_inputs(const Module* M, CUdeviceptr rows, long long B, const int32_t* map, const double* u)
@@ -571,18 +572,29 @@ int rmt_n2_rhs(rmt_module_t m, int64_t B, int32_t zNo, const double* d_consts, c
     return launch(M->f_n2_rhs, (unsigned)((B + 63)/64), 64, 0, (CUstream)stream, params, "rmt_n2_rhs");
 }
 
+static int64_t n2_slots(const Module* M, int64_t B)
+{
+    const int block = M->info.block;
+    long long want = (B + block - 1)/block;
+    long long cap = (long long)g_sm_count*std::max(M->solve_blocks_per_sm, 1);
+    return (int64_t)std::max<long long>(1, std::min(want, cap))*block;
+}
+
 int64_t rmt_n2_work_doubles(rmt_module_t m, int64_t B, int32_t zNo)
 {
     Module* M = get_module(m);
     if (!M) { fail("invalid module handle"); return -1; }
+    if (B <= 0 || zNo < 2) { fail("rmt_n2_work_doubles: need B > 0 and zNo >= 2"); return -1; }
     const int64_t n = M->info.n, s = M->info.stages;
-    // per node: state n, stages s*n, LU n*n, dF/dP n, dE/dy n+1, pivots(as double) n  ; per instance extras
-    return ((int64_t)zNo*(n + s*n + n*n + n + (n + 1) + 1) + 16)*B;
+    // per node and integrator thread: y_n, y_{n+1}, s stage vectors, LU (n x n), upwind / pressure
+    // coupling vectors (3n), d E/d P, packed pivots
+    const int64_t rows = n*(5 + s + n) + 2;
+    return rows*(int64_t)zNo*n2_slots(M, B);
 }
 
 int rmt_n2_solve(rmt_module_t m, int64_t B, int32_t zNo, int32_t tNo, double period, const double* d_consts,
                  double rtol, double atol, int32_t max_steps, int32_t out_mode,
-                 double* d_out, int32_t* d_status, int32_t* d_stats, double* d_work, void* stream)
+                 double* d_out, int32_t* d_status, int32_t* d_stats, double* d_work, const double* ctrl, void* stream)
 {
     Module* M = get_module(m);
     if (!M) return fail("invalid module handle");
@@ -591,6 +603,7 @@ int rmt_n2_solve(rmt_module_t m, int64_t B, int32_t zNo, int32_t tNo, double per
     if (B <= 0 || zNo < 2 || tNo < 1 || !(period > 0.0)) return fail("rmt_n2_solve: need B > 0, zNo >= 2, tNo >= 1, period > 0");
     if (!(rtol > 0.0) || !(atol >= 0.0)) return fail("rmt_n2_solve: rtol must be > 0 and atol >= 0");
     if (!d_work) return fail("rmt_n2_solve: d_work is required (rmt_n2_work_doubles)");
+    if (M->info.n > 15) return fail("rmt_n2_solve: more than 15 unknowns per node are not supported (pivot packing)");
     CUstream st = (CUstream)stream;
     CUdeviceptr scr;
     if (scratch_get(M, 64, &scr)) return 1;
@@ -600,8 +613,12 @@ int rmt_n2_solve(rmt_module_t m, int64_t B, int32_t zNo, int32_t tNo, double per
     a.rtol = rtol; a.atol = atol; a.max_steps = max_steps > 0 ? max_steps : 1000000; a.out_mode = out_mode;
     a.out = (CUdeviceptr)d_out; a.status = (CUdeviceptr)d_status; a.stats = (CUdeviceptr)d_stats;
     a.work = (CUdeviceptr)d_work; a.queue = scr;
+    for (int k = 0; k < 6; ++k) a.ctrl[k] = ctrl ? ctrl[k] : RMT_DEFAULT_CTRL[k];
+    if (!(a.ctrl[0] > 0.0 && a.ctrl[0] <= 1.0) || !(a.ctrl[1] > 1.0) || !(a.ctrl[2] > 1.0) || !(a.ctrl[3] > 0.0))
+        return fail("rmt_n2_solve: controller needs 0 < safety <= 1, max shrink > 1, max growth > 1, kappa > 0");
+    if (!(a.ctrl[5] > 0.0)) a.ctrl[5] = RMT_DEFAULT_CTRL[5];
     const int block = M->info.block;
-    unsigned grid = (unsigned)((B + block - 1)/block);
+    unsigned grid = (unsigned)(n2_slots(M, B)/block);
     void* params[] = {&a};
     return launch(M->f_n2_solve, grid, block, 0, st, params, "rmt_n2_solve");
 }

@@ -229,7 +229,7 @@ struct Hot {
 #if defined(RMT_MODEL_N1)
     double invBeta;              // zf/Pf
 #else
-    double F1, dz, invdz;        // 1/(eps*(zf/vf)), node spacing
+    double F1, invZv;            // 1/(eps*(zf/vf)), vf/zf
     double iv[RMT_NC];           // inlet boundary values C0_i/Cmax
 #endif
     double kp[RMT_NKP > 0 ? RMT_NKP : 1];
@@ -254,6 +254,7 @@ __device__ __forceinline__ void rmt_load_hot(const double* __restrict__ consts, 
 #else
     const double vf = c[(i64)K_VF*B];
     h.F1 = 1/(eps*(zf/vf));
+    h.invZv = 1/(zf/vf);
 #pragma unroll
     for (int k = 0; k < RMT_NC; ++k) h.iv[k] = c[(i64)(K_IV0 + k)*B];
 #endif
@@ -911,6 +912,505 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
     }
 }
 #endif  // RMT_MODEL_N1
+
+#if defined(RMT_MODEL_N2)
+// ---------------------------------------------------------------------------------
+// N2: dynamic model by the method of lines (modelEquationN2, pbHomoReactor.py:3706-4134).
+// State yhat[(nc+1)][zNo] variable-major as in the reference (:3873); on the device
+// [var][node][B].  One reactor per thread; the nodes are swept in flow direction because
+// the pressure is marched node by node (:3979) and the convection is first-order upwind
+// (:4082-4128), so node k depends on nodes <= k only.
+// ---------------------------------------------------------------------------------
+#define RMT_ITN RMT_NC                       // N2: index of T-hat within a node
+
+struct NodeJac {                             // derivative blocks of one node
+    double A[RMT_N][RMT_N];                  // d f_k / d u_k
+    double g[RMT_N];                         // d f_k / d P_k
+    double L[RMT_N];                         // d f_k / d u_{k-1}  (diagonal: upwind differences)
+    double e[RMT_N];                         // d E_k / d u_k
+    double ep;                               // d E_k / d P_k
+};
+
+// f_k and the Ergun gradient E_k [Pa/m] at one node.  u: node state, ub: upwind node state (or the
+// inlet boundary values), P: pressure at the node.
+template <bool JAC>
+__device__ __forceinline__ void n2_node(const double (&u)[RMT_N], const double (&ub)[RMT_N], const bool inlet,
+                                        const double P, const double invdz, const Hot& h,
+                                        double (&f)[RMT_N], double& E, NodeJac& nj)
+{
+    double C[RMT_NC];
+#pragma unroll
+    for (int i = 0; i < RMT_NC; ++i) C[i] = fmax(u[i], RMT_EPS_CONST)*h.Cmax;      // :3897-3904
+#if RMT_ISO
+    const double T = 0.0*h.Tf + h.Tf;
+#else
+    const double T = u[RMT_ITN]*h.Tf + h.Tf;                                       // :3914
+#endif
+    Point p; PointJac pj;
+    rmt_point<JAC>(C, T, P, h, p, pj);
+    const double us = h.us0;                                                       // v_z frozen, :3937, :4066
+    E = -1*(h.ergA*us + h.ergC*p.rho*(us*us));                                     // :3970-3974 (not scaled)
+    const double rhoh = p.rho*h.invRho0;
+    // mass balances (:4082-4099): F1*(-v/vf*(Ci - Ci_b)/dz + ri/GaMaCoTe0), v/vf == 1
+#pragma unroll
+    for (int i = 0; i < RMT_NC; ++i) {
+        const double cb = inlet ? h.iv[i] : fmax(ub[i], RMT_EPS_CONST);
+        f[i] = h.F1*(-1*((u[i] - cb)*invdz) + p.r[i]*h.invGm);
+    }
+#if !RMT_ISO
+    // energy balance (:4102-4128)
+    const double cph_eps = p.Cp*h.epsCpf;                                          // (Cp/Cpf)*eps
+    const double invD = rmt_rcp(rhoh*cph_eps);
+    const double tb = inlet ? 0.0 : ub[RMT_ITN];                                   // (T0 - Tf)/Tf = 0 at the inlet
+    const double dTdz = (u[RMT_ITN] - tb)*invdz;
+    const double Nn = (-p.q + p.Qm)*h.invGh;
+    f[RMT_ITN] = h.invZv*(-dTdz + Nn*invD);
+#endif
+    if (JAC) {
+        const double invS = p.invS, invT = rmt_rcp(T), invMW = rmt_rcp(p.MWm), invP = rmt_rcp(P);
+#if !RMT_ISO
+        const double invCp = rmt_rcp(p.Cp);
+#endif
+        double sy[RMT_NR];
+#pragma unroll
+        for (int j = 0; j < RMT_NR; ++j) {
+            double a = 0.0;
+#if RMT_RATES_DEP_Y
+#pragma unroll
+            for (int i = 0; i < RMT_NC; ++i) a += pj.dRdy[j][i]*p.y[i];
+#endif
+            sy[j] = a;
+        }
+        const double F1Gm = h.F1*h.invGm;
+        const double ergE = -1*h.ergC*(us*us)*p.rho;            // dE = ergE * dlnrho
+        // columns: local species, local temperature, and the pressure (col == RMT_N)
+#pragma unroll
+        for (int col = 0; col <= RMT_N; ++col) {
+            const bool isC = col < RMT_NC, isP = col == RMT_N;
+            double dlnrho, dR[RMT_NR];
+            if (isC) {
+                const int c = col < RMT_NC ? col : 0;
+                const double sc = (u[c] > RMT_EPS_CONST) ? h.Cmax : 0.0;    // d max(u, eps)/du
+                dlnrho = sc*(1e-3*RMT_cMW[c] - p.MWm)*invS*invMW;
+#pragma unroll
+                for (int j = 0; j < RMT_NR; ++j) {
+                    double a = 0.0;
+#if RMT_RATES_DEP_Y
+                    a = (pj.dRdy[j][c] - sy[j])*invS;
+#endif
+#if RMT_RATES_DEP_C
+                    a += pj.dRdC[j][c];
+#endif
+                    dR[j] = sc*a;
+                }
+            } else if (isP) {
+                dlnrho = invP;
+#pragma unroll
+                for (int j = 0; j < RMT_NR; ++j) dR[j] = pj.dRdP[j];
+            } else {
+                dlnrho = -h.Tf*invT;
+#pragma unroll
+                for (int j = 0; j < RMT_NR; ++j) dR[j] = h.Tf*pj.dRdT[j];
+            }
+            if (isP) nj.ep = ergE*dlnrho; else nj.e[col < RMT_N ? col : 0] = ergE*dlnrho;
+#pragma unroll
+            for (int i = 0; i < RMT_NC; ++i) {
+                double dr = 0.0;
+#pragma unroll
+                for (int j = 0; j < RMT_NR; ++j) if (RMT_NU[j][i] != 0.0) dr += RMT_NU[j][i]*dR[j];
+                double v = dr*F1Gm;
+                if (!isP && i == col) v -= h.F1*invdz;
+                if (isP) nj.g[i] = v; else nj.A[i][col < RMT_N ? col : 0] = v;
+            }
+#if !RMT_ISO
+            double dq = 0.0;
+#pragma unroll
+            for (int j = 0; j < RMT_NR; ++j) dq += dR[j]*p.dH[j];
+            double dCp = 0.0, dQm = 0.0;
+            if (isC) {
+                const int c = col < RMT_NC ? col : 0;
+                dCp = ((u[c] > RMT_EPS_CONST) ? h.Cmax : 0.0)*(p.cpm[c] - p.Cp)*invS;
+            } else if (!isP) {
+                dCp = h.Tf*pj.dCpdT;
+#pragma unroll
+                for (int j = 0; j < RMT_NR; ++j) dq += p.R[j]*(h.Tf*pj.ddHdT[j]);
+                dQm = (h.Tm == 0.0) ? 0.0 : -h.Ua*h.Tf;
+            }
+            const double dN = (-dq + dQm)*h.invGh;
+            const double dlnD = dlnrho + dCp*invCp;
+            double vT = h.invZv*(dN*invD - Nn*invD*dlnD);
+            if (!isP && col == RMT_ITN) vT -= h.invZv*invdz;
+            if (isP) nj.g[RMT_ITN] = vT; else nj.A[RMT_ITN][col < RMT_N ? col : 0] = vT;
+#endif
+        }
+        // upwind coupling (diagonal)
+#pragma unroll
+        for (int i = 0; i < RMT_NC; ++i) nj.L[i] = inlet ? 0.0 : ((ub[i] > RMT_EPS_CONST) ? h.F1*invdz : 0.0);
+#if !RMT_ISO
+        nj.L[RMT_ITN] = inlet ? 0.0 : h.invZv*invdz;
+#endif
+    }
+}
+
+// stand-alone batched RHS: y [n][zNo][B] -> f [n][zNo][B]
+extern "C" __global__ void __launch_bounds__(64)
+rmt_n2_rhs(const double* __restrict__ consts, const i64 B, const int zNo, const double* __restrict__ y, double* __restrict__ f)
+{
+    const i64 i = (i64)blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    Hot h; rmt_load_hot(consts, B, i, h);
+    const double dz = 1.0/(zNo - 1);                                               // :3439
+    const double invdz = 1.0/dz;
+    double P = h.Pf;                                                               // P_z[0] = P0, :3848
+    double ub[RMT_N] = {0}, u[RMT_N], fo[RMT_N], E;
+    NodeJac nj;
+    for (int k = 0; k < zNo; ++k) {
+#pragma unroll
+        for (int v = 0; v < RMT_N; ++v) u[v] = y[((i64)v*zNo + k)*B + i];
+        n2_node<false>(u, ub, k == 0, P, invdz, h, fo, E, nj);
+#pragma unroll
+        for (int v = 0; v < RMT_N; ++v) { f[((i64)v*zNo + k)*B + i] = fo[v]; ub[v] = u[v]; }
+        P = E*dz + P;                                                              // :3979 (dimensionless dz, kept)
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// N2 integrator: the same adaptive Rosenbrock method as N1, applied to the (nc+1)*zNo system.
+// W = I/(h*gamma) - J is block lower triangular in the node index: dense n x n diagonal
+// blocks, a diagonal sub-diagonal block from the upwind differences, and a rank-structured
+// remainder from the pressure march which is carried EXACTLY by one running scalar
+// (the linearised pressure dP_k).  Every stage is therefore one forward sweep over the nodes
+// with an n x n solve per node — no approximation of the Jacobian, as Rosenbrock methods need.
+// Per-instance work arrays live in global memory, [slot-row][node][thread] so that the lanes of
+// a warp read consecutive doubles.
+// ---------------------------------------------------------------------------------
+struct SolveArgsN2 {
+    const double* consts;
+    i64 B;
+    int zNo, tNo;
+    double period;
+    double rtol, atol;
+    int max_steps;
+    int out_mode;
+    double* out;               // [tNo][rows][zNo][B]
+    int* status;               // [B]
+    int* stats;                // [4][B]
+    double* work;
+    unsigned long long* queue;
+    double ctrl[6];
+};
+
+// rows of the per-node work record
+enum {
+    W_Y0 = 0, W_Y1 = RMT_N, W_K = 2*RMT_N, W_LU = W_K + RMT_ROS_S*RMT_N, W_L = W_LU + RMT_N*RMT_N,
+    W_G = W_L + RMT_N, W_E = W_G + RMT_N, W_EP = W_E + RMT_N, W_PERM = W_EP + 1, W_ROWS = W_PERM + 1
+};
+
+__device__ __forceinline__ int n2_out_rows(const int mode) { return mode == 2 ? 2*RMT_N + RMT_NC : RMT_N; }
+
+extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n2_solve(const SolveArgsN2 a)
+{
+    const i64 slots = (i64)gridDim.x*blockDim.x;
+    const i64 slot = (i64)blockIdx.x*blockDim.x + threadIdx.x;
+    const int zNo = a.zNo;
+    double* w = a.work + slot;
+#define WK(row, k) w[((i64)(row)*zNo + (k))*slots]
+    const double dz = 1.0/(zNo - 1), invdz = 1.0/dz;
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const double SAFE = a.ctrl[0], FAC1 = a.ctrl[1], FAC2 = 1.0/a.ctrl[2], KAPPA = a.ctrl[3], BETA = a.ctrl[4];
+
+    i64 inst = -1;
+    bool exhausted = false;
+    Hot h = {};
+    double t = 0.0, hstep = 0.0, hacc = 0.0, erracc = 1e-2, tend = 0.0;
+    int nacc = 0, nrej = 0, nanrej = 0, slab = 0, cur = 0;     // cur: which of Y0/Y1 holds y_n
+    bool last_rejected = false, fresh = false;
+
+    while (true) {
+        const bool need = (inst < 0) && !exhausted;
+        const unsigned m = __ballot_sync(FULL, need);
+        if (m) {
+            unsigned long long base = 0;
+            const int leader = __ffs(m) - 1;
+            if (lane == leader) base = atomicAdd(a.queue, (unsigned long long)__popc(m));
+            base = __shfl_sync(FULL, base, leader);
+            if (need) {
+                const i64 cand = (i64)base + __popc(m & ((1u << lane) - 1));
+                if (cand >= a.B) exhausted = true;
+                else {
+                    inst = cand;
+                    rmt_load_hot(a.consts, a.B, inst, h);
+                    for (int k = 0; k < zNo; ++k) {                      // IV: feed composition at every node, T-hat = 0 (:3483-3497)
+#pragma unroll
+                        for (int v = 0; v < RMT_NC; ++v) WK(W_Y0 + v, k) = h.iv[v];
+#if !RMT_ISO
+                        WK(W_Y0 + RMT_ITN, k) = 0.0;
+#endif
+                    }
+                    t = 0.0; nacc = nrej = nanrej = 0; slab = 0; cur = 0; last_rejected = false; fresh = true;
+                    hacc = 0.0; erracc = 1e-2;
+                    tend = a.period/a.tNo;
+                }
+            }
+        }
+        if (__all_sync(FULL, inst < 0)) break;
+        if (inst < 0) continue;
+        const int YN = cur ? W_Y1 : W_Y0, YP = cur ? W_Y0 : W_Y1;
+
+        if (fresh) {
+            // starting step from ||y0|| / ||f(y0)|| (Hairer-Wanner II.4, first guess), scaled like N1
+            double d0 = 0.0, d1 = 0.0, P = h.Pf, E;
+            double ub[RMT_N] = {0}, u[RMT_N], fo[RMT_N];
+            NodeJac nj;
+            for (int k = 0; k < zNo; ++k) {
+#pragma unroll
+                for (int v = 0; v < RMT_N; ++v) u[v] = WK(YN + v, k);
+                n2_node<false>(u, ub, k == 0, P, invdz, h, fo, E, nj);
+#pragma unroll
+                for (int v = 0; v < RMT_N; ++v) {
+                    const double sc = KAPPA*(a.atol + a.rtol*fabs(u[v]));
+                    d0 += (u[v]/sc)*(u[v]/sc); d1 += (fo[v]/sc)*(fo[v]/sc); ub[v] = u[v];
+                }
+                P = E*dz + P;
+            }
+            d0 = sqrt(d0/(RMT_N*zNo)); d1 = sqrt(d1/(RMT_N*zNo));
+            const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01*d0/d1;
+            hstep = fmin(a.ctrl[5]*100.0*h0, tend);
+            fresh = false;
+        }
+        const double hlim = tend - t;
+        const bool clipped = hstep*1.01 >= hlim;
+        const double hh = clipped ? hlim : hstep;
+        const double dg = 1.0/(hh*RMT_ROS_GAMMA), invh = 1.0/hh;
+
+        // ---- sweep 0: f(y_n), Jacobian blocks, LU of the diagonal blocks ----
+        {
+            double P = h.Pf, E;
+            double ub[RMT_N] = {0}, u[RMT_N], fo[RMT_N];
+            NodeJac nj;
+            for (int k = 0; k < zNo; ++k) {
+#pragma unroll
+                for (int v = 0; v < RMT_N; ++v) u[v] = WK(YN + v, k);
+                n2_node<true>(u, ub, k == 0, P, invdz, h, fo, E, nj);
+                // W_kk = I/(h*gamma) - A, LU with partial pivoting in registers
+                int perm[RMT_N];
+#pragma unroll
+                for (int r = 0; r < RMT_N; ++r) {
+                    perm[r] = r;
+#pragma unroll
+                    for (int c = 0; c < RMT_N; ++c) nj.A[r][c] = (r == c ? dg : 0.0) - nj.A[r][c];
+                }
+#pragma unroll
+                for (int c = 0; c < RMT_N; ++c) {
+                    double best = fabs(nj.A[c][c]);
+                    int bi = c;
+#pragma unroll
+                    for (int r = c + 1; r < RMT_N; ++r) { const double v = fabs(nj.A[r][c]); if (v > best) { best = v; bi = r; } }
+#pragma unroll
+                    for (int r = c + 1; r < RMT_N; ++r)
+                        if (r == bi) {
+#pragma unroll
+                            for (int q = 0; q < RMT_N; ++q) { const double tv = nj.A[c][q]; nj.A[c][q] = nj.A[r][q]; nj.A[r][q] = tv; }
+                            const int tp = perm[c]; perm[c] = perm[r]; perm[r] = tp;
+                        }
+                    const double piv = rmt_rcp(nj.A[c][c]);
+                    nj.A[c][c] = piv;
+#pragma unroll
+                    for (int r = c + 1; r < RMT_N; ++r) {
+                        const double l = nj.A[r][c]*piv;
+                        nj.A[r][c] = l;
+#pragma unroll
+                        for (int q = c + 1; q < RMT_N; ++q) nj.A[r][q] -= l*nj.A[c][q];
+                    }
+                }
+                long long pk = 0;
+#pragma unroll
+                for (int r = 0; r < RMT_N; ++r) pk |= (long long)perm[r] << (4*r);
+#pragma unroll
+                for (int r = 0; r < RMT_N; ++r) {
+#pragma unroll
+                    for (int c = 0; c < RMT_N; ++c) WK(W_LU + r*RMT_N + c, k) = nj.A[r][c];
+                    WK(W_L + r, k) = nj.L[r]; WK(W_G + r, k) = nj.g[r]; WK(W_E + r, k) = nj.e[r];
+                    WK(W_K + r, k) = fo[r];                    // stage-1 right-hand side
+                    ub[r] = u[r];
+                }
+                WK(W_EP, k) = nj.ep;
+                WK(W_PERM, k) = __longlong_as_double(pk);
+                P = E*dz + P;
+            }
+        }
+
+        // ---- stage sweeps ----
+        double errsum = 0.0;
+        bool bad = false;
+#pragma unroll 1
+        for (int s = 0; s < RMT_ROS_S; ++s) {
+            double P = h.Pf, dP = 0.0, E;
+            double ub[RMT_N] = {0}, kprev[RMT_N] = {0};
+            const bool lastStage = s == RMT_ROS_S - 1;
+            for (int k = 0; k < zNo; ++k) {
+                double rhs[RMT_N], u[RMT_N];
+                if (s == 0) {
+#pragma unroll
+                    for (int v = 0; v < RMT_N; ++v) rhs[v] = WK(W_K + v, k);
+                } else {
+#pragma unroll
+                    for (int v = 0; v < RMT_N; ++v) u[v] = WK(YN + v, k);
+                    for (int j = 0; j < s; ++j) {
+                        const double aj = RMT_cROS_A[s][j];
+#pragma unroll
+                        for (int v = 0; v < RMT_N; ++v) u[v] += aj*WK(W_K + j*RMT_N + v, k);
+                    }
+                    NodeJac njd;
+                    n2_node<false>(u, ub, k == 0, P, invdz, h, rhs, E, njd);
+                    P = E*dz + P;
+#pragma unroll
+                    for (int v = 0; v < RMT_N; ++v) ub[v] = u[v];
+                    for (int j = 0; j < s; ++j) {
+                        const double cj = RMT_cROS_C[s][j]*invh;
+#pragma unroll
+                        for (int v = 0; v < RMT_N; ++v) rhs[v] += cj*WK(W_K + j*RMT_N + v, k);
+                    }
+                }
+                // off-diagonal part of J*K: upwind block and the pressure column
+#pragma unroll
+                for (int v = 0; v < RMT_N; ++v) rhs[v] += WK(W_L + v, k)*kprev[v] + WK(W_G + v, k)*dP;
+                // solve with the stored LU of this node
+                const long long pk = __double_as_longlong(WK(W_PERM, k));
+                double x[RMT_N];
+#pragma unroll
+                for (int r = 0; r < RMT_N; ++r) {
+                    const int pr = (int)((pk >> (4*r)) & 15);
+                    double v = 0.0;
+#pragma unroll
+                    for (int q = 0; q < RMT_N; ++q) if (q == pr) v = rhs[q];
+#pragma unroll
+                    for (int c = 0; c < r; ++c) v -= WK(W_LU + r*RMT_N + c, k)*x[c];
+                    x[r] = v;
+                }
+#pragma unroll
+                for (int r = RMT_N - 1; r >= 0; --r) {
+                    double v = x[r];
+#pragma unroll
+                    for (int c = r + 1; c < RMT_N; ++c) v -= WK(W_LU + r*RMT_N + c, k)*x[c];
+                    x[r] = v*WK(W_LU + r*RMT_N + r, k);
+                }
+                // linearised pressure march: dP_{k+1} = dP_k + dz*(e_k . K_k + ep_k*dP_k)
+                double ek = 0.0;
+#pragma unroll
+                for (int v = 0; v < RMT_N; ++v) { ek += WK(W_E + v, k)*x[v]; kprev[v] = x[v]; }
+                dP = dP + dz*(ek + WK(W_EP, k)*dP);
+                if (!lastStage) {
+#pragma unroll
+                    for (int v = 0; v < RMT_N; ++v) WK(W_K + s*RMT_N + v, k) = x[v];
+                } else {
+                    // y_{n+1} = y_n + sum_j m_j K_j ; err = K_s (stiffly accurate pair)
+#pragma unroll
+                    for (int v = 0; v < RMT_N; ++v) {
+                        const double yo = WK(YN + v, k);
+                        double yn = yo;
+                        double ev = 0.0;
+                        for (int j = 0; j < s; ++j) {
+                            const double kj = WK(W_K + j*RMT_N + v, k);
+                            yn += RMT_cROS_M[j]*kj; ev += RMT_cROS_E[j]*kj;
+                        }
+                        yn += RMT_cROS_M[s]*x[v]; ev += RMT_cROS_E[s]*x[v];
+                        WK(YP + v, k) = yn;
+                        const double sc = KAPPA*(a.atol + a.rtol*fmax(fabs(yo), fabs(yn)));
+                        errsum += (ev/sc)*(ev/sc);
+                        bad = bad || !(fabs(yn) <= 1.7e308);
+                    }
+                }
+            }
+        }
+        double err = sqrt(errsum/(RMT_N*zNo));
+        if (bad || !(err == err)) err = 1e30;
+
+        // ---- controller (same as N1) ----
+        const double errc = fmax(err, 1e-10);
+        double fac;
+        if (BETA > 0.0 && nacc > 0) fac = pow(errc, 1.0/(RMT_ROS_ORDER) - 0.75*BETA)*pow(erracc, -BETA)/SAFE;
+        else fac = pow(errc, 1.0/(RMT_ROS_ORDER))/SAFE;
+        fac = fmax(FAC2, fmin(FAC1, fac));
+        double hnew = hh/fac;
+        int fin = -1;
+        if (err <= 1.0) {
+            if (nacc > 0 && BETA <= 0.0) {
+                double facgus = (hacc/hh)*pow(err*err/erracc, 1.0/(RMT_ROS_ORDER))/SAFE;
+                facgus = fmax(FAC2, fmin(FAC1, facgus));
+                fac = fmax(fac, facgus);
+                hnew = hh/fac;
+            }
+            hacc = hh; erracc = fmax(1e-2, err);
+            ++nacc; nanrej = 0;
+            cur ^= 1;
+            t = clipped ? tend : t + hh;
+            if (last_rejected) hnew = fmin(hnew, hh);
+            last_rejected = false;
+            hstep = clipped ? fmax(hnew, hstep) : hnew;
+            if (t >= tend) {
+                // end of a slab: un-scale and store (sortResult5, solResultAnalysis.py:252-301; :3630-3661)
+                const int YC = cur ? W_Y1 : W_Y0;
+                const int rows = n2_out_rows(a.out_mode);
+                for (int k = 0; k < zNo; ++k) {
+                    double v[RMT_N];
+#pragma unroll
+                    for (int q = 0; q < RMT_N; ++q) v[q] = WK(YC + q, k);
+                    double* o = a.out + (((i64)slab*rows)*zNo + k)*a.B + inst;
+                    const i64 rs = (i64)zNo*a.B;
+                    if (a.out_mode != 1) {
+#pragma unroll
+                        for (int q = 0; q < RMT_N; ++q) o[q*rs] = v[q];
+                        o += RMT_N*rs;
+                    }
+                    if (a.out_mode != 0) {
+                        double S = 0.0, C[RMT_NC];
+#pragma unroll
+                        for (int q = 0; q < RMT_NC; ++q) { C[q] = v[q]*h.Cmax; S += C[q]; }
+                        if (a.out_mode == 2) {
+#pragma unroll
+                            for (int q = 0; q < RMT_NC; ++q) o[q*rs] = C[q];
+                            o += RMT_NC*rs;
+                        }
+#pragma unroll
+                        for (int q = 0; q < RMT_NC; ++q) o[q*rs] = C[q]/S;
+#if !RMT_ISO
+                        o[RMT_ITN*rs] = v[RMT_ITN]*h.Tf + h.Tf;
+#endif
+                    }
+                }
+                ++slab;
+                if (slab >= a.tNo) fin = 0;
+                else tend = (slab + 1 == a.tNo) ? a.period : a.period*(slab + 1)/a.tNo;
+            }
+            if (fin < 0 && nacc + nrej >= a.max_steps) fin = 1;
+        } else {
+            ++nrej;
+            if (err >= 1e29) { ++nanrej; hnew = hh*0.1; }
+            last_rejected = true;
+            hstep = hnew;
+            if (nacc + nrej >= a.max_steps) fin = 1;
+            else if (hstep < 1e-14*fmax(a.period, 1e-300)) fin = 2;
+            else if (nanrej > 30) fin = 3;
+        }
+        if (fin >= 0) {
+            a.status[inst] = fin;
+            a.stats[inst] = nacc; a.stats[a.B + inst] = nrej;
+            a.stats[2*a.B + inst] = (nacc + nrej)*(RMT_ROS_S - 1); a.stats[3*a.B + inst] = nacc + nrej;
+            if (fin != 0) {
+                const int rows = n2_out_rows(a.out_mode);
+                const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+                for (; slab < a.tNo; ++slab)
+                    for (int r = 0; r < rows; ++r)
+                        for (int k = 0; k < zNo; ++k) a.out[(((i64)slab*rows + r)*zNo + k)*a.B + inst] = qnan;
+            }
+            inst = -1;
+        }
+    }
+#undef WK
+}
+#endif  // RMT_MODEL_N2
 
 // ---------------------------------------------------------------------------------
 // deterministic objective reduction: per-block (sum, min, argmin) partials, then one

@@ -356,3 +356,86 @@ def n1_rhs_batch(cm, modelInput, Y, sweep=None, jac=False, device=None):
             mod.n1_rhs(B, d_consts, d_y, d_f, stream=stream)
             J = None
         return d_f.cpu().numpy().T.copy(), J, d_consts.cpu().numpy()
+
+
+# ----------------------------------------------------------------------------------
+# N2 ensemble (dynamic model, method of lines)
+# ----------------------------------------------------------------------------------
+class N2Result:
+    __slots__ = ("out", "status", "stats", "zNo", "tNo", "n", "nc", "out_mode", "flops", "h2d_bytes", "d2h_bytes")
+
+
+def n2_solve_ensemble(cm, modelInput, sweep=None, B=1, zNo=None, tNo=None, period=None, rtol=None, atol=None,
+                      out_mode=1, max_steps=1000000, device=None, keep_on_device=False, workspace=None, ctrl=None):
+    """Integrate B independent dynamic reactors over [0, period]; returns the state at the end of
+    each of the tNo slabs, out[tNo][rows][zNo][B] (runN2's dataPack list, pbHomoReactor.py:3589-3696)."""
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise capi.RmtError("rmt_app_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+    spec = cm.spec
+    assert spec.model == "N2"
+    mod = cm.load(dev.index)
+    sc = modelInput.get("solver-config", {})
+    rtol = float(sc.get("rtol", DEFAULT_RTOL) if rtol is None else rtol)
+    atol = float(sc.get("atol", DEFAULT_ATOL) if atol is None else atol)
+    zNo = int(solverSetting["N2"]["zNo"] if zNo is None else zNo)
+    tNo = int(solverSetting["N2"]["tNo"] if tNo is None else tNo)
+    period = float(modelInput["operating-conditions"]["period"] if period is None else period)
+    uniform = uniform_inputs(spec, modelInput)
+    ws = workspace if workspace is not None else Workspace()
+    n, nc = spec.n, spec.nc
+    out_rows = 2*n + nc if out_mode == 2 else n
+    res = N2Result()
+    res.zNo, res.tNo, res.n, res.nc, res.out_mode, res.flops = zNo, tNo, n, nc, out_mode, cm.flops
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream().cuda_stream
+        h_rows, n_rows, row_map = sweep_rows_into(spec, sweep, B, ws)
+        d_rows = None
+        res.h2d_bytes = 0
+        if n_rows:
+            d_rows = ws.get("d_rows", (n_rows, B), torch.float64, device=dev)
+            d_rows.copy_(h_rows, non_blocking=True)
+            res.h2d_bytes = h_rows.numel()*8
+        d_consts = ws.get("d_consts", (mod.info.nconst, B), torch.float64, device=dev)
+        d_out = ws.get("d_out", (tNo, out_rows, zNo, B), torch.float64, device=dev)
+        d_status = ws.get("d_status", (B,), torch.int32, device=dev)
+        d_stats = ws.get("d_stats", (4, B), torch.int32, device=dev)
+        d_work = ws.get("d_work", (mod.n2_work_doubles(B, zNo),), torch.float64, device=dev)
+        mod.setup(B, d_rows, n_rows, row_map, uniform, d_consts, stream=stream)
+        mod.n2_solve(B, zNo, tNo, period, d_consts, rtol, atol, d_out, d_status, d_stats, d_work,
+                     max_steps=max_steps, out_mode=out_mode, ctrl=ctrl, stream=stream)
+        if keep_on_device:
+            res.out, res.status, res.stats = d_out, d_status, d_stats
+            res.d2h_bytes = 0
+        else:
+            res.out = d_out.cpu().numpy()
+            res.status = d_status.cpu().numpy()
+            res.stats = d_stats.cpu().numpy()
+            res.d2h_bytes = res.out.nbytes + res.status.nbytes + res.stats.nbytes
+    return res
+
+
+def n2_rhs_batch(cm, modelInput, Y, zNo, sweep=None, device=None):
+    """modelEquationN2 at states Y [B][n*zNo] (variable-major per instance, like the reference's
+    flattened state).  Returns F [B][n*zNo]."""
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise capi.RmtError("rmt_app_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+    spec = cm.spec
+    mod = cm.load(dev.index)
+    Y = np.ascontiguousarray(Y, dtype=np.float64)
+    B = Y.shape[0]
+    assert Y.shape[1] == spec.n*zNo
+    uniform = uniform_inputs(spec, modelInput)
+    rows, row_map = sweep_rows(spec, sweep, B)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream().cuda_stream
+        d_rows = torch.from_numpy(rows).to(dev) if rows.shape[0] else None
+        d_consts = torch.empty((mod.info.nconst, B), dtype=torch.float64, device=dev)
+        d_y = torch.from_numpy(np.ascontiguousarray(Y.T)).to(dev)            # [n*zNo][B]
+        d_f = torch.empty_like(d_y)
+        mod.setup(B, d_rows, rows.shape[0], row_map, uniform, d_consts, stream=stream)
+        mod.n2_rhs(B, zNo, d_consts, d_y, d_f, stream=stream)
+        return d_f.cpu().numpy().T.copy()

@@ -1,0 +1,43 @@
+#!/usr/bin/env python
+"""Converged N2 solutions from the ORACLE (tests/golden/n2_sol_*_oracle_tight.npz).
+
+The reference's own N2 path needs minutes per default-tolerance solve (56-446 s,
+see make_golden.py logs) and hours at rtol=1e-10, so the converged solutions used
+for the north_star 1e-6 check of the dynamic model come from the oracle port, whose
+RHS is pinned to the reference's modelEquationN2 to 1e-12 (test_oracle_golden_n2.py)
+and which calls the same scipy.integrate.solve_ivp with the same slab structure.
+
+usage: python tests/golden/make_golden_oracle.py m20 | m50 | ch4
+"""
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(HERE)), "oracle"))
+import cases  # noqa: E402
+import pyremot_oracle as O  # noqa: E402
+
+CFG = {
+    "m20": (lambda: cases.methanol_testfile_input("N2"), 20, "BDF", 1e-10, 1e-13),
+    "m50": (lambda: cases.methanol_readme_input("N2"), 50, "BDF", 1e-9, 1e-12),
+    "ch4": (lambda: cases.ch4_input("N2"), 20, "LSODA", 1e-11, 1e-13),
+}
+
+if __name__ == "__main__":
+    for which in sys.argv[1:]:
+        mk, zNo, method, rtol, atol = CFG[which]
+        O.solverSetting["N2"]["zNo"] = zNo
+        t0 = time.time()
+        o = O.N2Oracle(mk())
+        res = o.solve(method=method, rtol=rtol, atol=atol)
+        dps = res["dataPack"]
+        np.savez_compressed(os.path.join(HERE, "n2_sol_%s_oracle_tight.npz" % which),
+                            dataYs=np.array([d["dataYs"] for d in dps]), solY=np.array([d["solY"] for d in dps]),
+                            dataTime=np.array([d["dataTime"] for d in dps]), zNo=np.array(zNo),
+                            method=np.array(method), rtol=np.array(rtol), atol=np.array(atol), nfev=np.array(o.nfev),
+                            wall=np.array(time.time() - t0))
+        print(which, "done in %.0f s, nfev %d" % (time.time() - t0, o.nfev), flush=True)

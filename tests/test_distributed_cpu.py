@@ -1,0 +1,81 @@
+"""Host-side sharding / reduction / gather logic on CPU with the gloo backend, world_size 2 and 3."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from rmt_app_b200 import ensemble
+
+
+def test_partition_covers_range_without_overlap():
+    for B in (0, 1, 7, 64, 1000003):
+        for world in (1, 2, 3, 8):
+            edges = [ensemble.partition(B, world, r) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == B
+            assert all(edges[r][1] == edges[r + 1][0] for r in range(world - 1))
+            sizes = [b - a for a, b in edges]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_shard_sweep_slices_every_key():
+    B = 10
+    sw = {"temperature": np.arange(B, dtype=float), "concentration": np.arange(B*3, dtype=float).reshape(B, 3)}
+    parts = [ensemble.shard_sweep(sw, B, 3, r) for r in range(3)]
+    np.testing.assert_array_equal(np.concatenate([p[0]["temperature"] for p in parts]), sw["temperature"])
+    np.testing.assert_array_equal(np.concatenate([p[0]["concentration"] for p in parts]), sw["concentration"])
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, B, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(0)
+        obj = rng.uniform(1.0, 2.0, B)
+        obj[[3, B - 2]] = 0.25                         # tie on the minimum: smallest index wins
+        outlet = rng.normal(size=(8, B))
+        lo, hi = ensemble.partition(B, world, rank)
+        loc = obj[lo:hi]
+        s, mn, am = float(loc.sum()), float(loc.min()), int(lo + loc.argmin())
+        gs, gmn, gam = ensemble.reduce_objective(s, mn, am, group=None)
+        full = ensemble.all_gather_rows(torch.from_numpy(outlet[:, lo:hi].copy()), B)
+        fobj = ensemble.all_gather_rows(torch.from_numpy(loc.copy()), B)
+        ok = (abs(gs - obj.sum()) < 1e-9 and gmn == 0.25 and gam == 3 and
+              np.array_equal(full.numpy(), outlet) and np.array_equal(fobj.numpy(), obj))
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,B", [(2, 11), (3, 64)])
+def test_reduce_and_gather_under_gloo(world, B):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, B, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(r for r, _ in res) == list(range(world))
+    assert all(ok for _, ok in res), res
+
+
+def test_single_process_passthrough():
+    assert ensemble.world_info() == (0, 1)
+    assert ensemble.reduce_objective(3.0, 1.0, 5) == (3.0, 1.0, 5)
+    t = torch.arange(6.0).view(2, 3)
+    assert ensemble.all_gather_rows(t, 3) is t

@@ -1,0 +1,112 @@
+"""GPU parity tests for the dynamic method-of-lines model N2 (run with -m gpu)."""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+import pyremot_oracle as O
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+RHS_CASES = {
+    "methanol_testfile_z20": (lambda: cases.methanol_testfile_input("N2"), 20),
+    "methanol_readme_z50": (lambda: cases.methanol_readme_input("N2"), 50),
+    "ch4_z20": (lambda: cases.ch4_input("N2"), 20),
+}
+
+
+@pytest.fixture()
+def n2_settings():
+    from rmt_app_b200 import solverSetting
+    old = dict(solverSetting["N2"]), O.solverSetting["N2"]["zNo"]
+    yield solverSetting
+    solverSetting["N2"].update(old[0])
+    O.solverSetting["N2"]["zNo"] = old[1]
+
+
+@pytest.mark.parametrize("name", list(RHS_CASES))
+def test_n2_rhs_parity_with_reference_golden(name):
+    from rmt_app_b200 import engine
+    g = np.load(os.path.join(GOLDEN, "n2_rhs_reference.npz"))
+    mk, z = RHS_CASES[name]
+    mi = mk()
+    cm = engine.compile_model(mi)
+    Y, F = g[name + "__rhs_Y"], g[name + "__rhs_F"]
+    Fg = engine.n2_rhs_batch(cm, mi, Y, z)
+    # node-wise scale: the near-equilibrium cancellation of N1 applies per node
+    n = cm.spec.n
+    Fr, Fq = F.reshape(len(F), n, z), Fg.reshape(len(F), n, z)
+    scale = np.max(np.abs(Fr), axis=1, keepdims=True)
+    assert np.max(np.abs(Fq - Fr)/scale) < 2e-9
+    # the initial state (feed composition everywhere) is well conditioned
+    assert np.max(np.abs(Fq[0] - Fr[0])/np.maximum(np.abs(Fr[0]), 1e-9*scale[0])) < 1e-10
+
+
+def test_n2_ch4_tight_matches_reference_tight(n2_settings):
+    """Level 2 for the dynamic model: all five slab states within 1e-6 of the reference's own
+    tight-tolerance LSODA run (tests/golden/n2_sol_ch4_tight_reference.npz)."""
+    from rmt_app_b200 import rmtExe
+    g = np.load(os.path.join(GOLDEN, "n2_sol_ch4_tight_reference.npz"))
+    n2_settings["N2"]["zNo"] = int(g["zNo"])
+    mi = cases.ch4_input("N2")
+    mi["solver-config"].update(rtol=1e-9, atol=1e-12)
+    res = rmtExe(mi)["resModel"]
+    assert len(res["dataPack"]) == 5
+    for i, dp in enumerate(res["dataPack"]):
+        ref = g["dataYs"][i]
+        assert dp["dataYs"].shape == ref.shape
+        assert np.max(np.abs(dp["dataYs"] - ref)/np.abs(ref)) < 1e-6, i
+        np.testing.assert_allclose(dp["dataTime"], g["dataTime"][i])
+        np.testing.assert_allclose(dp["dataXs"], g["dataXs"])
+        assert dp["labelList"] == ["CH4", "C2H4", "H2", "Temperature"]
+        assert dp["dataYCons1"].shape == (3, 20) and dp["dataYCons2"].shape == (3, 20)
+        assert np.asarray(dp["dataYTemp1"]).shape == (20,) and dp["dataYTemp2"].shape == (1, 20)
+
+
+def test_n2_methanol_z20_against_converged_oracle_and_reference(n2_settings):
+    from rmt_app_b200 import rmtExe
+    conv = np.load(os.path.join(GOLDEN, "n2_sol_m20_oracle_tight.npz"))
+    n2_settings["N2"]["zNo"] = 20
+    mi = cases.methanol_testfile_input("N2")
+    mi["solver-config"].update(rtol=1e-8, atol=1e-11)
+    res = rmtExe(mi)["resModel"]
+    for i, dp in enumerate(res["dataPack"]):
+        ref = conv["dataYs"][i]
+        rel = np.abs(dp["dataYs"] - ref)/np.abs(ref)
+        assert rel[-1].max() < 1e-6, (i, rel[-1].max())            # temperature profile
+        assert rel[:, -1].max() < 1e-6, (i, rel[:, -1])            # outlet mole fractions
+        assert rel.max() < 1e-5
+    # the reference's own default runs sit within their tolerance of our converged answer
+    for f in ("n2_sol_m20_lsoda_reference.npz", "n2_sol_m20_bdf_reference.npz", "n2_sol_m20_tight_reference.npz"):
+        r = np.load(os.path.join(GOLDEN, f))
+        ours = res["dataPack"][-1]["dataYs"]
+        rel = np.abs(ours - r["dataYs"][-1])/np.abs(r["dataYs"][-1])
+        assert rel[:, -1].max() < (2e-5 if "tight" in f else 5e-3), (f, rel[:, -1])
+
+
+def test_n2_methanol_z50_default_vs_reference_bdf(n2_settings):
+    """BASELINE config 2 (50 nodes): default tolerance against the reference's BDF run (446 s there)."""
+    from rmt_app_b200 import rmtExe
+    r = np.load(os.path.join(GOLDEN, "n2_sol_m50_bdf_reference.npz"))
+    n2_settings["N2"]["zNo"] = 50
+    res = rmtExe(cases.methanol_readme_input("N2"))["resModel"]
+    ours = res["dataPack"][-1]["dataYs"]
+    rel = np.abs(ours - r["dataYs"][-1])/np.abs(r["dataYs"][-1])
+    assert rel[:, -1].max() < 5e-3 and rel[-1].max() < 2e-3
+
+
+def test_n2_ensemble_matches_single_and_reports_failures(n2_settings):
+    from rmt_app_b200 import engine
+    mi = cases.ch4_input("N2")
+    cm = engine.compile_model(mi)
+    B = 70
+    rng = np.random.default_rng(1)
+    sw = {"temperature": rng.uniform(900, 1000, B), "k0": 7.2e-4*rng.uniform(0.5, 2.0, B)}
+    sw["temperature"][5] = np.nan
+    r = engine.n2_solve_ensemble(cm, mi, sw, B, zNo=12, tNo=3, period=5.0)
+    assert r.status[5] != 0 and (np.delete(r.status, 5) == 0).all()
+    assert np.isnan(r.out[:, :, :, 5]).all()
+    one = engine.n2_solve_ensemble(cm, mi, {k: v[11:12] for k, v in sw.items()}, 1, zNo=12, tNo=3, period=5.0)
+    np.testing.assert_array_equal(one.out[..., 0], r.out[..., 11])

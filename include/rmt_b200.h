@@ -146,6 +146,10 @@ int rmt_n2_solve(rmt_module_t m, int64_t B, int32_t zNo, int32_t tNo, double per
 int rmt_reduce_objective(rmt_module_t m, int64_t n, const double* d_obj, int64_t index_offset,
                          double* h_sum, double* h_min, int64_t* h_argmin, void* stream);
 
+/* ---- diagnostics: accuracy probe of the branch-free device math used by the generated kinetics:
+ * d_out [5][n] = exp(x), log(x), sqrt(x), 10^x, 1/x for x = d_x[0..n). ----------------------------- */
+int rmt_math_probe(rmt_module_t m, int32_t n, const double* d_x, double* d_out, void* stream);
+
 /* ---- diagnostics: log the step sequence of one instance of the next N1 solves:
  * d_trace [cap][4] = (t, h, err, accepted) per attempt; NULL switches it off. ------ */
 int rmt_debug_trace(double* d_trace, int32_t cap, int64_t instance);

@@ -60,6 +60,7 @@ SIGNATURES = {
     "rmt_n2_solve": (C.c_int, [_u64, _i64, _i32, _i32, _dbl, _vp, _dbl, _dbl, _i32, _i32, _vp, _vp, _vp, _vp, _pdbl,
                                _vp]),
     "rmt_reduce_objective": (C.c_int, [_u64, _i64, _vp, _i64, _pdbl, _pdbl, C.POINTER(_i64), _vp]),
+    "rmt_math_probe": (C.c_int, [_u64, _i32, _vp, _vp, _vp]),
     "rmt_debug_trace": (C.c_int, [_vp, _i32, _i64]),
     "rmt_fp64_peak": (C.c_int, [_u64, _i32, _i32, _pdbl]),
 }
@@ -241,6 +242,9 @@ class Module:
         _check(lib().rmt_reduce_objective(self.handle, n, _ptr(d_obj), index_offset, C.byref(s), C.byref(mn),
                                           C.byref(am), stream))
         return s.value, mn.value, am.value
+
+    def math_probe(self, n, d_x, d_out, stream=None):
+        _check(lib().rmt_math_probe(self.handle, n, _ptr(d_x), _ptr(d_out), stream))
 
     def fp64_peak(self, iters=8192, repeats=5):
         v = _dbl(0)

@@ -20,7 +20,7 @@ from .expr import Graph
 from .tableau import TABLEAUX
 
 _CFUN = {
-    "exp": "exp", "log": "log", "log10": "log10", "log2": "log2", "sqrt": "sqrt", "exp10": "exp10",
+    "exp": "RMT_EXP", "log": "RMT_LOG", "log10": "RMT_LOG10", "log2": "log2", "sqrt": "RMT_SQRT", "exp10": "RMT_EXP10",
     "abs": "fabs", "sin": "sin", "cos": "cos", "tan": "tan", "tanh": "tanh", "sinh": "sinh", "cosh": "cosh",
     "atan": "atan", "asin": "asin", "acos": "acos", "expm1": "expm1", "log1p": "log1p", "cbrt": "cbrt",
     "pow": "pow", "min": "fmin", "max": "fmax", "atan2": "atan2",

@@ -110,7 +110,7 @@ struct Module {
     CUmodule mod = nullptr;
     rmt_module_info info{};
     CUfunction f_setup = nullptr, f_n1_rhs = nullptr, f_n1_jac = nullptr, f_n1_solve = nullptr;
-    CUfunction f_n2_rhs = nullptr, f_n2_solve = nullptr, f_reduce = nullptr, f_peak = nullptr;
+    CUfunction f_n2_rhs = nullptr, f_n2_solve = nullptr, f_reduce = nullptr, f_peak = nullptr, f_probe = nullptr;
     int solve_blocks_per_sm = 0;
     size_t solve_smem = 0;
     Scratch ring[8];
@@ -397,6 +397,7 @@ int rmt_module_load(const void* cubin, size_t size, rmt_module_t* module_out)
     M->f_n2_solve = get("rmt_n2_solve");
     M->f_reduce = get("rmt_reduce_partials");
     M->f_peak = get("rmt_dfma_peak");
+    M->f_probe = get("rmt_math_probe");
     if (!M->f_setup) { drv.p_cuModuleUnload(M->mod); delete M; return fail("module lacks rmt_setup"); }
     CUfunction fs = I.model == 1 ? M->f_n1_solve : M->f_n2_solve;
     if (fs && I.model == 1) {
@@ -654,6 +655,17 @@ int rmt_reduce_objective(rmt_module_t m, int64_t n, const double* d_obj, int64_t
     if (h_min) *h_min = mn;
     if (h_argmin) *h_argmin = am;
     return 0;
+}
+
+int rmt_math_probe(rmt_module_t m, int32_t n, const double* d_x, double* d_out, void* stream)
+{
+    Module* M = get_module(m);
+    if (!M) return fail("invalid module handle");
+    if (ensure_ctx()) return 1;
+    CUdeviceptr x = (CUdeviceptr)d_x, o = (CUdeviceptr)d_out;
+    int nn = n;
+    void* params[] = {&x, &nn, &o};
+    return launch(M->f_probe, (unsigned)((n + 127)/128), 128, 0, (CUstream)stream, params, "rmt_math_probe");
 }
 
 int rmt_debug_trace(double* d_trace, int32_t cap, int64_t instance)

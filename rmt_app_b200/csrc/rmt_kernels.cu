@@ -48,6 +48,127 @@ __device__ __forceinline__ double rmt_rcp(const double x)
 #define RMT_DIV(a, b) ((a)*rmt_rcp(b))
 #endif
 
+// Transcendentals.  libdevice's exp / log / sqrt each contain a branch to a special-case path; besides the
+// extra instructions, those branches cut the instruction stream into basic blocks, so the independent
+// Arrhenius / equilibrium exponentials of a kinetics section (all functions of T only) cannot be interleaved
+// by the scheduler.  The versions below are branch free (select instead of branch) and accurate to ~1 ulp
+// on the normal range: exp clamps its argument to [-708, 709] (finite huge/tiny instead of Inf/0), log and
+// sqrt return NaN for negative arguments.  -DRMT_EXACT_MATH=1 uses libdevice everywhere.
+#ifndef RMT_EXACT_MATH
+#define RMT_EXACT_MATH 0
+#endif
+__device__ __forceinline__ double rmt_exp_reduced(const double r, const int k)
+{
+    // exp(r) for |r| <= ln2/2 by the degree-13 Taylor polynomial (truncation 4e-18), times 2^k
+    double p = 1.6059043836821613e-10;                 // 1/13!
+    p = fma(p, r, 2.08767569878681e-09);               // 1/12!
+    p = fma(p, r, 2.505210838544172e-08);              // 1/11!
+    p = fma(p, r, 2.755731922398589e-07);              // 1/10!
+    p = fma(p, r, 2.7557319223985893e-06);             // 1/9!
+    p = fma(p, r, 2.48015873015873e-05);               // 1/8!
+    p = fma(p, r, 0.0001984126984126984);              // 1/7!
+    p = fma(p, r, 0.001388888888888889);               // 1/6!
+    p = fma(p, r, 0.008333333333333333);               // 1/5!
+    p = fma(p, r, 0.041666666666666664);               // 1/4!
+    p = fma(p, r, 0.16666666666666666);                // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+__device__ __forceinline__ double rmt_exp(double x)
+{
+#if RMT_EXACT_MATH
+    return exp(x);
+#else
+    x = fmin(fmax(x, -708.0), 709.0);
+    const double t = fma(x, 1.4426950408889634, 6755399441055744.0);     // round(x*log2(e)) in the low word
+    const double kd = t - 6755399441055744.0;
+    double r = fma(kd, -6.93147180369123816490e-01, x);
+    r = fma(kd, -1.90821492927058770002e-10, r);
+    return rmt_exp_reduced(r, __double2loint(t));
+#endif
+}
+__device__ __forceinline__ double rmt_exp10(double x)
+{
+#if RMT_EXACT_MATH
+    return exp10(x);
+#else
+    x = fmin(fmax(x, -307.0), 308.0);
+    const double t = fma(x, 3.3219280948873622, 6755399441055744.0);     // round(x*log2(10))
+    const double kd = t - 6755399441055744.0;
+    // r = x*ln10 - k*ln2, with ln10 and ln2 split hi/lo
+    double r = fma(kd, -6.93147180369123816490e-01, x*2.302585092994045901e+00);
+    r = fma(kd, -1.90821492927058770002e-10, r);
+    r = fma(x, -2.1707562233822494e-16, r);                               // ln10_lo
+    r += fma(x, 2.302585092994045901e+00, -(x*2.302585092994045901e+00)); // rounding error of the product
+    return rmt_exp_reduced(r, __double2loint(t));
+#endif
+}
+__device__ __forceinline__ double rmt_log(const double x)
+{
+#if RMT_EXACT_MATH
+    return log(x);
+#else
+    // fdlibm e_log.c without the special cases: x = 2^k * m, m in [sqrt(1/2), sqrt(2))
+    int hx = __double2hiint(x);
+    const int lx = __double2loint(x);
+    int k = (hx >> 20) - 1023;
+    hx &= 0x000fffff;
+    const int i = (hx + 0x95f64) & 0x100000;
+    const double m = __hiloint2double(hx | (i ^ 0x3ff00000), lx);
+    k += i >> 20;
+    const double f = m - 1.0;
+    double e, rr;
+    {   // s = f/(2+f) by a refined reciprocal
+        const double d = 2.0 + f;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rr) : "d"(d));
+        e = fma(-d, rr, 1.0); rr = fma(rr, e, rr);
+        e = fma(-d, rr, 1.0); rr = fma(rr, e, rr);
+    }
+    const double s = f*rr;
+    const double z = s*s, w = z*z;
+    const double t1 = w*fma(w, fma(w, 1.531383769920937332e-01, 2.222219843214978396e-01), 3.999999999940941908e-01);
+    const double t2 = z*fma(w, fma(w, fma(w, 1.479819860511658591e-01, 1.818357216161805012e-01),
+                                   2.857142874366239149e-01), 6.666666666666735130e-01);
+    const double R = t2 + t1;
+    const double hfsq = 0.5*f*f;
+    const double dk = (double)k;
+    const double res = dk*6.93147180369123816490e-01 - ((hfsq - fma(s, hfsq + R, dk*1.90821492927058770002e-10)) - f);
+    return x > 0.0 ? res : __longlong_as_double(0x7ff8000000000000LL);
+#endif
+}
+__device__ __forceinline__ double rmt_log10(const double x)
+{
+#if RMT_EXACT_MATH
+    return log10(x);
+#else
+    return rmt_log(x)*4.342944819032518167e-01;
+#endif
+}
+__device__ __forceinline__ double rmt_sqrt(const double x)
+{
+#if RMT_EXACT_MATH
+    return sqrt(x);
+#else
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double g = x*y, hh = 0.5*y;
+    double r = fma(-hh, g, 0.5);
+    g = fma(g, r, g); hh = fma(hh, r, hh);
+    r = fma(-hh, g, 0.5);
+    g = fma(g, r, g); hh = fma(hh, r, hh);
+    const double d = fma(-g, g, x);
+    g = fma(d, hh, g);
+    return x == 0.0 ? 0.0 : g;
+#endif
+}
+#define RMT_EXP(x) rmt_exp(x)
+#define RMT_EXP10(x) rmt_exp10(x)
+#define RMT_LOG(x) rmt_log(x)
+#define RMT_LOG10(x) rmt_log10(x)
+#define RMT_SQRT(x) rmt_sqrt(x)
+
 // full-mantissa literals of the generated kinetics: constant-bank operands (1) or instruction immediates (0)
 #ifndef RMT_USE_CBANK
 #define RMT_USE_CBANK 1
@@ -1443,6 +1564,16 @@ rmt_reduce_partials(const double* __restrict__ v, const i64 n, const i64 index_o
         __syncthreads();
     }
     if (threadIdx.x == 0) { psum[blockIdx.x] = ssum[0]; pmin[blockIdx.x] = smin[0]; parg[blockIdx.x] = sarg[0]; }
+}
+
+// accuracy probe of the branch-free math above: out[0..4][n] = exp, log, sqrt, exp10, 1/x
+extern "C" __global__ void rmt_math_probe(const double* __restrict__ x, const int n, double* __restrict__ out)
+{
+    const int i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double v = x[i];
+    out[i] = rmt_exp(v); out[n + i] = rmt_log(v); out[2*n + i] = rmt_sqrt(v);
+    out[3*n + i] = rmt_exp10(v); out[4*n + i] = rmt_rcp(v);
 }
 
 // ---------------------------------------------------------------------------------

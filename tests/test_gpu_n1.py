@@ -248,3 +248,38 @@ def test_full_size_ensemble_properties():
     assert y[:, 7].min() > 473.0 and y[:, 7].max() < 700.0                                # SURVEY App. B.4 extremes
     st = r["stats"]
     assert 30 < st[0].mean() < 80 and st[0].max() < 400
+
+
+def test_branch_free_device_math_accuracy():
+    """rmt_exp / rmt_log / rmt_sqrt / rmt_exp10 / rmt_rcp (csrc/rmt_kernels.cu) against NumPy: <= 2 ulp."""
+    import torch
+    from rmt_app_b200 import engine
+    cm = engine.compile_model(cases.methanol_readme_input("N1"))
+    mod = cm.load(torch.cuda.current_device())
+    rng = np.random.default_rng(2)
+    xs = np.concatenate([rng.uniform(-300, 300, 20000), np.exp(rng.uniform(-40, 40, 20000)),
+                         rng.uniform(300, 1200, 5000), [1.0, 2.0, 0.5, 10.0, 1e-300, 1e300, 709.0, -708.0]])
+    n = xs.size
+    d_x = torch.from_numpy(xs).cuda()
+    d_o = torch.empty((5, n), dtype=torch.float64, device="cuda")
+    mod.math_probe(n, d_x, d_o, stream=torch.cuda.current_stream().cuda_stream)
+    o = d_o.cpu().numpy()
+    ulp = 2.220446049250313e-16
+
+    def relerr(got, want, mask):
+        return np.max(np.abs(got[mask] - want[mask])/np.abs(want[mask]))
+    with np.errstate(all="ignore"):
+        m = (xs > -700) & (xs < 700)
+        assert relerr(o[0], np.exp(xs), m) < 2*ulp
+        pos = xs > 0
+        lg = np.log(np.where(pos, xs, 1.0))
+        big = pos & (np.abs(lg) > 1e-2)
+        assert relerr(o[1], lg, big) < 2*ulp
+        assert np.max(np.abs(o[1][pos] - lg[pos])) < 1e-15*np.maximum(1.0, np.abs(lg[pos])).max()
+        assert np.isnan(o[1][xs < 0]).all()
+        assert relerr(o[2], np.sqrt(np.where(pos, xs, 1.0)), pos) < 2*ulp
+        assert np.isnan(o[2][xs < 0]).all()
+        m10 = (xs > -300) & (xs < 300)
+        assert relerr(o[3], np.power(10.0, xs), m10) < 4*ulp
+        nz = (np.abs(xs) > 1e-290) & (np.abs(xs) < 1e290)
+        assert relerr(o[4], 1.0/xs, nz) < 2*ulp

@@ -308,12 +308,14 @@ def run_gpu_arm(args, rank, world, local_rank):
         n_ok_all = n_ok
 
     # ---- e2e through the public API: host arrays in, host arrays out -----------------------------
+    # inputs live in pinned host memory (the contract's e2e definition); results land in pinned host memory
+    psweep = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in sweep.items()}
     for _ in range(2):
-        r = rmtExeBatch(base, sweep, workspace=ws, rtol=RTOL, atol=ATOL)
+        r = rmtExeBatch(base, psweep, workspace=ws, rtol=RTOL, atol=ATOL, return_stats=False)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        r = rmtExeBatch(base, sweep, workspace=ws, rtol=RTOL, atol=ATOL)
+        r = rmtExeBatch(base, psweep, workspace=ws, rtol=RTOL, atol=ATOL, return_stats=False)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     h2d, d2h = r["h2d_bytes"], r["d2h_bytes"]
@@ -350,6 +352,29 @@ def run_gpu_arm(args, rank, world, local_rank):
     rhs_ms = e0.elapsed_time(e1)/reps
     rhs_bytes = 8.0*(info.nconst + 2*n)*B
 
+    # ---- the dynamic model (BASELINE configs[1] and configs[4]), informational ---------------------
+    n2 = None
+    if rank == 0 and not args.no_n2:
+        from rmt_app_b200 import rmtExe, solverSetting
+        mi2 = cases.methanol_readme_input("N2")
+        cm2 = engine.compile_model(mi2)
+        solverSetting["N2"]["zNo"] = 50
+        rmtExe(mi2)
+        t0 = time.perf_counter()
+        rmtExe(mi2)
+        single_s = time.perf_counter() - t0
+        solverSetting["N2"]["zNo"] = 20
+        Bn, zn = 4096, 200
+        sw2 = cases.config3_sweep(Bn, 20240613)
+        for _ in range(2):
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            r2 = engine.n2_solve_ensemble(cm2, mi2, sw2, Bn, zNo=zn, tNo=5, period=0.5, keep_on_device=True, workspace=ws)
+            torch.cuda.synchronize(); ens_s = time.perf_counter() - t0
+        n2 = {"config2_single_50_nodes_s": single_s, "reference_bdf_same_case_s": 446.3,
+              "ensemble": {"instances": Bn, "nodes": zn, "period_s": 0.5, "seconds": ens_s, "instances_per_s": Bn/ens_s,
+                           "converged": int((r2.status == 0).sum().item()),
+                           "steps_mean": float(r2.stats[0].double().mean().item())}}
+
     if rank == 0:
         steps = args.steps
         total = world*B*steps
@@ -361,7 +386,7 @@ def run_gpu_arm(args, rank, world, local_rank):
             "config": workload_config(world),
             "clocks": clocks,
             "e2e": {"value": world*B*steps/e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "api": "rmt_app_b200.rmtExeBatch(modelInput, sweep, workspace=...) with host numpy arrays",
+                    "api": "rmt_app_b200.rmtExeBatch(modelInput, sweep, workspace=...) with pinned host tensors in, pinned host arrays out",
                     "converged": e2e_ok},
             "gpu_launches": 2*steps,
             "converged": n_ok_all, "instances": world*B,
@@ -386,6 +411,8 @@ def run_gpu_arm(args, rank, world, local_rank):
             "rhs_evals_per_sec_in_solver": world*(nfev + att)/solve_s,
             "setup_kernel_ms": setup_ms,
         }
+        if n2 is not None:
+            line["n2_dynamic_model"] = n2
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line))
@@ -402,6 +429,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--instances", type=int, default=B_PER_GPU, help="reactors per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-n2", action="store_true", help="skip the informational N2 (dynamic model) timings")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

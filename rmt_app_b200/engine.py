@@ -203,9 +203,8 @@ class Workspace:
         return buf[:need].view(*shape)
 
 
-def sweep_rows_into(spec, sweep, B, ws):
-    """Like sweep_rows but writes straight into a pinned staging buffer."""
-    torch = _torch()
+def _sweep_plan(spec, sweep, B):
+    """Map sweep keys to device input rows: [(value, column or None)], row_map."""
     nin = spec.nin
     row_map = -np.ones(nin, dtype=np.int32)
     scalar_index = {name: 2 + spec.nc + k for k, name in enumerate(SCALAR_INPUTS[2:])}
@@ -214,8 +213,7 @@ def sweep_rows_into(spec, sweep, B, ws):
     plan = []
     for key, val in (sweep or {}).items():
         if key == "concentration":
-            shp = tuple(val.shape)
-            if shp != (B, spec.nc):
+            if tuple(val.shape) != (B, spec.nc):
                 raise ValueError("sweep['concentration'] must have shape (B, nc) = (%d, %d)" % (B, spec.nc))
             for i in range(spec.nc):
                 row_map[2 + i] = len(plan)
@@ -233,6 +231,13 @@ def sweep_rows_into(spec, sweep, B, ws):
                               spec.kin.param_names))
         row_map[q] = len(plan)
         plan.append((val, None))
+    return plan, row_map
+
+
+def sweep_rows_into(spec, sweep, B, ws):
+    """Like sweep_rows but writes straight into a pinned staging buffer."""
+    torch = _torch()
+    plan, row_map = _sweep_plan(spec, sweep, B)
     n_rows = len(plan)
     if n_rows == 0:
         return None, 0, row_map
@@ -245,6 +250,48 @@ def sweep_rows_into(spec, sweep, B, ws):
             a = np.asarray(val)
             np.copyto(view[r], a if col is None else a[:, col], casting="same_kind")
     return stage, n_rows, row_map
+
+
+def sweep_rows_to_device(spec, sweep, B, ws, dev):
+    """Inputs -> device rows [n_rows][B].  NumPy arrays are staged through one pinned buffer; torch
+    tensors (pinned host memory or already on the device) are copied directly, a [B, nc] concentration
+    block in one transfer followed by a device-side transpose.  Returns (d_rows, n_rows, row_map, h2d_bytes)."""
+    torch = _torch()
+    plan, row_map = _sweep_plan(spec, sweep, B)
+    n_rows = len(plan)
+    if n_rows == 0:
+        return None, 0, row_map, 0
+    d_rows = ws.get("d_rows", (n_rows, B), torch.float64, device=dev)
+    h2d = 0
+    np_rows = [r for r, (val, _) in enumerate(plan) if not torch.is_tensor(val)]
+    if np_rows:
+        stage = ws.get("h_rows", (len(np_rows), B), torch.float64, pinned=True)
+        view = stage.numpy()
+        for k, r in enumerate(np_rows):
+            val, col = plan[r]
+            a = np.asarray(val)
+            np.copyto(view[k], a if col is None else a[:, col], casting="same_kind")
+        if np_rows == list(range(np_rows[0], np_rows[0] + len(np_rows))):
+            d_rows[np_rows[0]:np_rows[0] + len(np_rows)].copy_(stage, non_blocking=True)
+        else:
+            for k, r in enumerate(np_rows):
+                d_rows[r].copy_(stage[k], non_blocking=True)
+        h2d += stage.numel()*8
+    done = set()
+    for r, (val, col) in enumerate(plan):
+        if not torch.is_tensor(val) or id(val) in done:
+            continue
+        if col is None:
+            d_rows[r].copy_(val.to(torch.float64) if val.dtype != torch.float64 else val, non_blocking=True)
+            h2d += 0 if val.is_cuda else B*8
+        else:
+            done.add(id(val))
+            blk = val if val.is_cuda else ws.get("d_conc", (B, spec.nc), torch.float64, device=dev)
+            if not val.is_cuda:
+                blk.copy_(val, non_blocking=True)
+                h2d += val.numel()*8
+            d_rows[r - col:r - col + spec.nc].copy_(blk.t())
+    return d_rows, n_rows, row_map, h2d
 
 
 # ----------------------------------------------------------------------------------
@@ -285,13 +332,7 @@ def n1_solve_ensemble(cm, modelInput, sweep=None, B=1, z_eval=None, rtol=None, a
     res.z_eval, res.n, res.nc, res.out_mode, res.flops = z_eval, n, nc, out_mode, cm.flops
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream().cuda_stream
-        h_rows, n_rows, row_map = sweep_rows_into(spec, sweep, B, ws)
-        d_rows = None
-        res.h2d_bytes = 0
-        if n_rows:
-            d_rows = ws.get("d_rows", (n_rows, B), torch.float64, device=dev)
-            d_rows.copy_(h_rows, non_blocking=True)
-            res.h2d_bytes = h_rows.numel()*8
+        d_rows, n_rows, row_map, res.h2d_bytes = sweep_rows_to_device(spec, sweep, B, ws, dev)
         d_consts = ws.get("d_consts", (mod.info.nconst, B), torch.float64, device=dev)
         d_out = ws.get("d_out", (z_eval.size, out_rows, B), torch.float64, device=dev)
         d_status = ws.get("d_status", (B,), torch.int32, device=dev)
@@ -390,13 +431,7 @@ def n2_solve_ensemble(cm, modelInput, sweep=None, B=1, zNo=None, tNo=None, perio
     res.zNo, res.tNo, res.n, res.nc, res.out_mode, res.flops = zNo, tNo, n, nc, out_mode, cm.flops
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream().cuda_stream
-        h_rows, n_rows, row_map = sweep_rows_into(spec, sweep, B, ws)
-        d_rows = None
-        res.h2d_bytes = 0
-        if n_rows:
-            d_rows = ws.get("d_rows", (n_rows, B), torch.float64, device=dev)
-            d_rows.copy_(h_rows, non_blocking=True)
-            res.h2d_bytes = h_rows.numel()*8
+        d_rows, n_rows, row_map, res.h2d_bytes = sweep_rows_to_device(spec, sweep, B, ws, dev)
         d_consts = ws.get("d_consts", (mod.info.nconst, B), torch.float64, device=dev)
         d_out = ws.get("d_out", (tNo, out_rows, zNo, B), torch.float64, device=dev)
         d_status = ws.get("d_status", (B,), torch.int32, device=dev)

@@ -91,7 +91,8 @@ def rmtExeBatchSharded(modelInput, sweep, B=None, *, rtol=None, atol=None, objec
     from .rmt import _check_components
     _check_components(modelInput)
     if B is None:
-        B = int(np.asarray(next(iter(sweep.values()))).shape[0])
+        first = next(iter(sweep.values()))
+        B = int(first.shape[0]) if hasattr(first, "shape") else len(first)
     rank, world = world_info(group)
     local, lo, hi = shard_sweep(sweep, B, world, rank)
     cm = engine.compile_model(modelInput)

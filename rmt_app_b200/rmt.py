@@ -147,7 +147,8 @@ def _runN2(modelInput):
 
 
 def rmtExeBatch(modelInput, sweep=None, B=None, *, rtol=None, atol=None, profile=False, z_eval=None,
-                objective_ref=None, dense=True, max_steps=100000, keep_on_device=False, workspace=None):
+                objective_ref=None, dense=True, max_steps=100000, keep_on_device=False, workspace=None,
+                return_stats=True):
     """Ensemble form of rmtExe for model "N1": B independent reactors that share
     `modelInput` except for the per-instance arrays in `sweep` (keys:
     "temperature", "pressure", "concentration" [B, nc], "volumetric-flowrate",
@@ -158,7 +159,9 @@ def rmtExeBatch(modelInput, sweep=None, B=None, *, rtol=None, atol=None, profile
              "objective": [B] or None, "comTime": ms}.
     Failed instances are flagged in `status` and never abort the ensemble.
     `workspace` (engine.Workspace) reuses pinned/device buffers across calls; the
-    returned arrays are then views valid until the next call with that workspace."""
+    returned arrays are then views valid until the next call with that workspace.
+    Sweep values may be NumPy arrays (staged through pinned memory), pinned torch CPU
+    tensors (copied directly) or torch CUDA tensors (no host transfer at all)."""
     tic = timer()
     _check_components(modelInput)
     if modelInput['model'] != "N1":
@@ -167,13 +170,13 @@ def rmtExeBatch(modelInput, sweep=None, B=None, *, rtol=None, atol=None, profile
         if not sweep:
             raise ValueError("give B or a non-empty sweep")
         first = next(iter(sweep.values()))
-        B = int(np.asarray(first).shape[0])
+        B = int(first.shape[0]) if hasattr(first, "shape") else len(first)
     cm = engine.compile_model(modelInput)
     if z_eval is None:
         z_eval = np.linspace(0, 1, solverSetting['N1']['zNo'] + 1) if profile else np.array([1.0])
     res = engine.n1_solve_ensemble(cm, modelInput, sweep, B, z_eval=z_eval, rtol=rtol, atol=atol, out_mode=1,
                                    dense=dense, max_steps=max_steps, objective_ref=objective_ref,
-                                   keep_on_device=keep_on_device, workspace=workspace)
+                                   keep_on_device=keep_on_device, workspace=workspace, want_stats=return_stats)
     if keep_on_device:
         out = res.out.permute(2, 1, 0)
         data = out[:, :, 0] if out.shape[2] == 1 else out

@@ -112,7 +112,7 @@ def workload_config(world, sample=None):
                     "T0~U[473,573]K, P0~U[2,8]MPa, H2/COx~U[1,3], CO2/COx~U[0.2,0.8]; seed %d+rank" % SEED,
         "instances_per_gpu": B_PER_GPU, "rtol": RTOL, "atol": ATOL, "output": "outlet (y_i, P, T)",
         "integrator": "Rodas4(3), PI step control, analytic Jacobian", "parallelism": "ensemble-sharded x%d, no data-path collective" % world,
-        "cache": "inputs+constants+outputs 330 MB per step > 126 MB L2 (no flush needed)",
+        "cache": "inputs+constants+outputs 410 MB per step > 126 MB L2 (no flush needed)",
     }
     if sample is not None:
         cfg["instances_per_step"] = sample
@@ -350,7 +350,18 @@ def run_gpu_arm(args, rank, world, local_rank):
     e1.record()
     torch.cuda.synchronize()
     rhs_ms = e0.elapsed_time(e1)/reps
-    rhs_bytes = 8.0*(info.nconst + 2*n)*B
+    # algorithmic bytes per evaluation: the 14 hot constants + kinetic parameters + state in, derivative out
+    rhs_bytes = 8.0*(14 + info.nkp + 2*n)*B
+    d_J = torch.empty((n*n, B), dtype=torch.float64, device=dev)
+    for _ in range(3):
+        mod.n1_jac(B, d_consts, d_y, d_f, d_J, stream=stream)
+    e0.record()
+    for _ in range(reps):
+        mod.n1_jac(B, d_consts, d_y, d_f, d_J, stream=stream)
+    e1.record()
+    torch.cuda.synchronize()
+    jac_ms = e0.elapsed_time(e1)/reps
+    jac_bytes = 8.0*(14 + info.nkp + 2*n + n*n)*B
 
     # ---- the dynamic model (BASELINE configs[1] and configs[4]), informational ---------------------
     n2 = None
@@ -407,6 +418,12 @@ def run_gpu_arm(args, rank, world, local_rank):
                 "unit": "GB/s", "frac": rhs_bytes/(rhs_ms*1e-3)/1e9/hbm_peak, "traffic": None, "peak_source": hbm_src,
                 "kernel_ms": rhs_ms, "rhs_evals_per_s": B/(rhs_ms*1e-3),
                 "fp64_tflops_weighted": B*info.flops_rhs_wt/(rhs_ms*1e-3)/1e12,
+            },
+            "roofline_jac_kernel": {
+                "kernel": "rmt_n1_jac", "bound": "hbm", "achieved": jac_bytes/(jac_ms*1e-3)/1e9, "peak": hbm_peak,
+                "unit": "GB/s", "frac": jac_bytes/(jac_ms*1e-3)/1e9/hbm_peak, "traffic": None, "peak_source": hbm_src,
+                "kernel_ms": jac_ms, "jac_evals_per_s": B/(jac_ms*1e-3),
+                "fp64_tflops_weighted": B*info.flops_jac_wt/(jac_ms*1e-3)/1e12,
             },
             "rhs_evals_per_sec_in_solver": world*(nfev + att)/solve_s,
             "setup_kernel_ms": setup_ms,

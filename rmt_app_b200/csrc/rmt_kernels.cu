@@ -189,7 +189,7 @@ __device__ __forceinline__ double rmt_sqrt(const double x)
 #else
 #define RMT_N (RMT_NC + (RMT_ISO ? 0 : 1))      // Ci..., (T) per node
 #endif
-#define RMT_NCONST_VALUE (19 + RMT_NC + RMT_NKP)
+#define RMT_NCONST_VALUE (29 + RMT_NC + RMT_NKP)
 #define RMT_IP RMT_NC                            // N1: index of P-hat
 #define RMT_IT (RMT_NC + 1)                      // N1: index of T-hat
 
@@ -204,6 +204,22 @@ __device__ __forceinline__ double rmt_sqrt(const double x)
 // 1 = the Rosenbrock stage loop is a real loop (one copy of the RHS code), 0 = fully unrolled
 #ifndef RMT_ROLL
 #define RMT_ROLL 1
+#endif
+// with RMT_SYNC == 1: a block barrier every RMT_SYNC_EVERY-th step attempt
+#ifndef RMT_SYNC_EVERY
+#define RMT_SYNC_EVERY 1
+#endif
+// a warp fetches new reactors when at least RMT_REFILL_MIN of its lanes are idle, or one has idled for
+// more than RMT_REFILL_WAIT step attempts
+#ifndef RMT_REFILL_MIN
+#define RMT_REFILL_MIN 1
+#endif
+#ifndef RMT_REFILL_WAIT
+#define RMT_REFILL_WAIT 2
+#endif
+// alternative: block-uniform refill every RMT_REFILL_EVERY-th attempt (0/1 = off)
+#ifndef RMT_REFILL_EVERY
+#define RMT_REFILL_EVERY 3
 #endif
 
 typedef long long i64;
@@ -251,7 +267,10 @@ __device__ __forceinline__ double rmt_in(const RmtInputs& p, const int q, const 
 // ---------------------------------------------------------------------------------
 enum {
     K_CMAX = 0, K_TF, K_PF, K_C0, K_UI0, K_US0, K_RHO0, K_CPF, K_GM, K_GH, K_MU,
-    K_EPS, K_DP, K_ZF, K_U, K_A, K_TM, K_VF, K_MWF, K_IV0,
+    K_EPS, K_DP, K_ZF, K_U, K_A, K_TM, K_VF, K_MWF,
+    // derived once per reactor for the hot loops (so that picking up a reactor is loads only)
+    H_ERGA, H_ERGC, H_UA, H_INVC0, H_INVRHO0, H_INVGM, H_INVGH, H_EPSCPF, H_X0, H_X1,
+    K_IV0,
     K_KP0 = K_IV0 + RMT_NC,
     RMT_NCONST = K_KP0 + RMT_NKP
 };
@@ -340,6 +359,20 @@ extern "C" __global__ void __launch_bounds__(128) rmt_setup(const RmtInputs in, 
     c[(i64)K_GM*B] = Gm;     c[(i64)K_GH*B] = Gh;   c[(i64)K_MU*B] = mumix;  c[(i64)K_EPS*B] = eps;
     c[(i64)K_DP*B] = dp;     c[(i64)K_ZF*B] = L;    c[(i64)K_U*B] = U;       c[(i64)K_A*B] = a;
     c[(i64)K_TM*B] = Tm;     c[(i64)K_VF*B] = vf;   c[(i64)K_MWF*B] = MWf;
+    // Ergun coefficients (pbHomoReactor.py:3214-3217): ergA*ergB = H_ERGA*us, ergC*ergD = H_ERGC*rho*us^2
+    c[(i64)H_ERGA*B] = 150*mumix/(dp*dp)*(((1 - eps)*(1 - eps))/(eps*eps*eps));
+    c[(i64)H_ERGC*B] = 1.75/dp*((1 - eps)/(eps*eps*eps));
+    c[(i64)H_UA*B] = U*a;
+    c[(i64)H_INVC0*B] = 1.0/C0;   c[(i64)H_INVRHO0*B] = 1.0/rho0;
+    c[(i64)H_INVGM*B] = 1.0/Gm;   c[(i64)H_INVGH*B] = 1.0/Gh;
+    c[(i64)H_EPSCPF*B] = eps/Cpf;
+#if defined(RMT_MODEL_N1)
+    c[(i64)H_X0*B] = L/P;                  // 1/(Pf/zf), the Ergun scale
+    c[(i64)H_X1*B] = 0.0;
+#else
+    c[(i64)H_X0*B] = 1/(eps*(L/vf));       // const_F1, :4075
+    c[(i64)H_X1*B] = 1/(L/vf);
+#endif
 #pragma unroll
     for (int k = 0; k < RMT_NC; ++k) c[(i64)(K_IV0 + k)*B] = C0i[k]/Cmax;     // :2833 / :3489
 #pragma unroll
@@ -361,29 +394,25 @@ struct Hot {
 
 __device__ __forceinline__ void rmt_load_hot(const double* __restrict__ consts, const i64 B, const i64 i, Hot& h)
 {
+    // loads only (independent, issued back to back): a lane picks up a new reactor while the other
+    // lanes of its warp — and, through the block barrier, the other warps — wait for it
     const double* c = consts + i;
-    h.Cmax = c[(i64)K_CMAX*B]; h.Tf = c[(i64)K_TF*B]; h.Pf = c[(i64)K_PF*B];
-    h.us0 = c[(i64)K_US0*B];
-    h.invC0 = 1.0/c[(i64)K_C0*B]; h.invRho0 = 1.0/c[(i64)K_RHO0*B];
-    h.invGm = 1.0/c[(i64)K_GM*B]; h.invGh = 1.0/c[(i64)K_GH*B];
-    const double mu = c[(i64)K_MU*B], eps = c[(i64)K_EPS*B], dp = c[(i64)K_DP*B], zf = c[(i64)K_ZF*B];
-    h.epsCpf = eps/c[(i64)K_CPF*B];
-    // Ergun coefficients (pbHomoReactor.py:3214-3217): ergA*ergB = cA*us, ergC*ergD = cC*rho*us^2
-    h.ergA = 150*mu/(dp*dp)*(((1 - eps)*(1 - eps))/(eps*eps*eps));
-    h.ergC = 1.75/dp*((1 - eps)/(eps*eps*eps));
-    h.Ua = c[(i64)K_U*B]*c[(i64)K_A*B];
-    h.Tm = c[(i64)K_TM*B];
+    h.Cmax = __ldg(c + (i64)K_CMAX*B); h.Tf = __ldg(c + (i64)K_TF*B); h.Pf = __ldg(c + (i64)K_PF*B);
+    h.us0 = __ldg(c + (i64)K_US0*B); h.Tm = __ldg(c + (i64)K_TM*B);
+    h.ergA = __ldg(c + (i64)H_ERGA*B); h.ergC = __ldg(c + (i64)H_ERGC*B); h.Ua = __ldg(c + (i64)H_UA*B);
+    h.invC0 = __ldg(c + (i64)H_INVC0*B); h.invRho0 = __ldg(c + (i64)H_INVRHO0*B);
+    h.invGm = __ldg(c + (i64)H_INVGM*B); h.invGh = __ldg(c + (i64)H_INVGH*B);
+    h.epsCpf = __ldg(c + (i64)H_EPSCPF*B);
 #if defined(RMT_MODEL_N1)
-    h.invBeta = zf/h.Pf;
+    h.invBeta = __ldg(c + (i64)H_X0*B);
 #else
-    const double vf = c[(i64)K_VF*B];
-    h.F1 = 1/(eps*(zf/vf));
-    h.invZv = 1/(zf/vf);
+    h.F1 = __ldg(c + (i64)H_X0*B);
+    h.invZv = __ldg(c + (i64)H_X1*B);
 #pragma unroll
-    for (int k = 0; k < RMT_NC; ++k) h.iv[k] = c[(i64)(K_IV0 + k)*B];
+    for (int k = 0; k < RMT_NC; ++k) h.iv[k] = __ldg(c + (i64)(K_IV0 + k)*B);
 #endif
 #pragma unroll
-    for (int k = 0; k < RMT_NKP; ++k) h.kp[k] = c[(i64)(K_KP0 + k)*B];
+    for (int k = 0; k < RMT_NKP; ++k) h.kp[k] = __ldg(c + (i64)(K_KP0 + k)*B);
 }
 
 // ---------------------------------------------------------------------------------
@@ -703,18 +732,43 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
     double t = 0.0, hstep = 0.0, hacc = 0.0, erracc = 0.0, tend = 0.0;
     int nacc = 0, nrej = 0, next_e = 0, nanrej = 0;
     bool last_rejected = false, fresh = false;
+#if RMT_SYNC && RMT_SYNC_EVERY > 1
+    int iter = 0;
+#endif
+#if RMT_REFILL_MIN > 1
+    int idle = 0;
+#endif
+#if RMT_REFILL_EVERY > 1
+    int rslot = 0;
+#endif
 
     while (true) {
         // ---- refill idle lanes from the queue (warp-aggregated atomic) ----
         const bool need = (inst < 0) && !exhausted;
         const unsigned m = __ballot_sync(FULL, need);
+#if RMT_REFILL_EVERY > 1
+        // block-uniform refill slots: every warp of the block picks up reactors in the same attempt, so the
+        // load latency is paid once per slot by everybody at the same time
+        const bool go = (rslot++ % RMT_REFILL_EVERY) == 0;
+        if (m && go) {
+#elif RMT_REFILL_MIN > 1
+        // picking up a reactor makes the rest of the warp (and, through the barrier, of the block) wait for
+        // the loads: do it for several lanes at once — a lane idles at most RMT_REFILL_WAIT attempts
+        if (need) ++idle;
+        const bool go = __popc(m) >= RMT_REFILL_MIN || __any_sync(FULL, need && idle > RMT_REFILL_WAIT);
+        if (m && go) {
+#else
         if (m) {
+#endif
             unsigned long long base = 0;
             const int leader = __ffs(m) - 1;
             if (lane == leader) base = atomicAdd(a.queue, (unsigned long long)__popc(m));
             base = __shfl_sync(FULL, base, leader);
             if (need) {
                 const i64 cand = (i64)base + __popc(m & ((1u << lane) - 1));
+#if RMT_REFILL_MIN > 1
+                idle = 0;
+#endif
                 if (cand >= a.B) exhausted = true;
                 else {
                     inst = cand;
@@ -733,6 +787,9 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
             }
         }
 #if RMT_SYNC
+#if RMT_SYNC_EVERY > 1
+        if ((++iter % RMT_SYNC_EVERY) == 0)
+#endif
         if (__syncthreads_and(inst < 0)) break;      // block-uniform exit; also re-aligns the warps
 #else
         if (__all_sync(FULL, inst < 0)) break;
@@ -770,7 +827,8 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
         }
         // clip to the end of the domain / next output point
         double hlim = tend - t;
-        if (!a.dense && next_e < a.n_eval) hlim = a.z_eval[next_e] - t;
+        const bool dense = RMT_ROS_DENSE && a.dense;
+        if (!dense && next_e < a.n_eval) hlim = a.z_eval[next_e] - t;
         const bool clipped = hstep*1.01 >= hlim;
         const double hh = clipped ? hlim : hstep;
 
@@ -830,9 +888,30 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
             __syncthreads();
 #endif
             double rhs[RMT_N];
-            if (s == 0) {
+#if RMT_ROLL
+            if (s == 0 || !RMT_cROS_NEWF[s]) {
+#else
+            if (s == 0 || !RMT_ROS_NEWF[s]) {
+#endif
+                // first stage, or a stage whose argument is y_n again: f(y_n) from the Jacobian evaluation
 #pragma unroll
                 for (int i = 0; i < RMT_N; ++i) rhs[i] = f0[i];
+#if RMT_ROLL
+                for (int j = 0; j < s; ++j) {
+                    const double cj = RMT_cROS_C[s][j]*invh;
+                    const double* kj = &KS(j, 0);
+#pragma unroll
+                    for (int i = 0; i < RMT_N; ++i) rhs[i] += cj*kj[i*RMT_BLOCK];
+                }
+#else
+#pragma unroll
+                for (int j = 0; j < s; ++j)
+                    if (RMT_ROS_C[s][j] != 0.0) {
+                        const double cj = RMT_cROS_C[s][j]*invh;
+#pragma unroll
+                        for (int i = 0; i < RMT_N; ++i) rhs[i] += cj*KS(j, i);
+                    }
+#endif
             } else {
                 double u[RMT_N];
 #pragma unroll
@@ -955,9 +1034,9 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
             }
             hacc = hh; erracc = fmax(1e-2, err);
             ++nacc; nanrej = 0;
-            const double tnew = clipped ? (a.dense || next_e >= a.n_eval ? tend : a.z_eval[next_e]) : t + hh;
+            const double tnew = clipped ? (dense || next_e >= a.n_eval ? tend : a.z_eval[next_e]) : t + hh;
             // output points inside (t, tnew]
-            if (a.dense) {
+            if (dense) {
                 while (next_e < a.n_eval && a.z_eval[next_e] <= tnew) {
                     const double ze = a.z_eval[next_e];
                     double v[RMT_N];
@@ -1005,7 +1084,10 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
         if (fin >= 0 && live) {
             a.status[inst] = fin;
             a.stats[inst] = nacc; a.stats[a.B + inst] = nrej;
-            a.stats[2*a.B + inst] = (nacc + nrej)*(RMT_ROS_S - 1); a.stats[3*a.B + inst] = nacc + nrej;
+            int nnew = 0;
+#pragma unroll
+            for (int q = 1; q < RMT_ROS_S; ++q) nnew += RMT_ROS_NEWF[q];
+            a.stats[2*a.B + inst] = (nacc + nrej)*nnew; a.stats[3*a.B + inst] = nacc + nrej;
             if (fin != 0) {
                 // make failures loud in the data as well: NaN for every point not yet written
                 double v[RMT_N];

@@ -36,10 +36,11 @@ def _torch():
 
 
 class CompiledModel:
-    def __init__(self, spec, block):
+    def __init__(self, spec, block, method="rodas4"):
         self.spec = spec
         self.block = block
-        self.header = generate_model_header(spec)
+        self.method = method
+        self.header = generate_model_header(spec, tableau=method)
         self.flops = model_flops(spec)
         self.module = None
 
@@ -51,14 +52,14 @@ class CompiledModel:
         return self.module
 
 
-def default_block(spec):
+def default_block(spec, stages=6):
     """Integrator block size.  Per-thread shared memory is (n^2 + s*n) doubles (LU + stage vectors).
     One block per SM, as many warps as fit (<= 256 threads: the kernel needs ~250 registers per
     thread): the warps of a block run in lockstep (one barrier per step attempt) so that they share
     instruction-cache lines — measured 2x faster than two independent 128-thread blocks per SM."""
     if spec.model != "N1":
         return 64
-    per_thread = 8*(spec.n*spec.n + 6*spec.n)
+    per_thread = 8*(spec.n*spec.n + stages*spec.n)
     fit = (227*1024 - 1024)//per_thread
     return int(max(32, min(256, (fit//32)*32)))
 
@@ -77,6 +78,15 @@ def _fn_sig(f):
     return (f.__code__, cells, repr(f.__defaults__), id(f.__globals__))
 
 
+def _method_of(modelInput, method=None):
+    """Integrator tableau: solver-config.method (extension key) or the default Rodas4(3)."""
+    from .tableau import TABLEAUX
+    m = method or modelInput.get("solver-config", {}).get("method", "rodas4")
+    if m not in TABLEAUX:
+        raise ValueError("solver-config.method must be one of %s (got %r)" % (sorted(TABLEAUX), m))
+    return m
+
+
 def _fast_key(modelInput, block):
     """Cheap identity of the model *structure* (no tracing): same components,
     reactions, process type and the same code objects in VARS/RATES."""
@@ -89,7 +99,7 @@ def _fast_key(modelInput, block):
         sig.append((k, _fn_sig(v)) if isinstance(v, types.FunctionType) else (k, type(v).__name__))
     return (modelInput["model"], tuple(modelInput["feed"]["components"]["shell"]),
             modelInput["operating-conditions"]["process-type"], tuple(modelInput["reactions"].values()),
-            tuple(sig), block)
+            tuple(sig), block, modelInput.get("solver-config", {}).get("method", "rodas4"))
 
 
 _fast = {}
@@ -113,13 +123,15 @@ def compile_model(modelInput, block=None):
 
 
 def _compile_model(modelInput, block=None):
+    from .tableau import TABLEAUX
     spec = ModelSpec(modelInput)
-    blk = block or default_block(spec)
-    key = spec.key("b%d" % blk)
+    method = _method_of(modelInput)
+    blk = block or default_block(spec, TABLEAUX[method]["stages"])
+    key = spec.key("b%d%s" % (blk, method))
     with _lock:
         cm = _compiled.get(key)
         if cm is None:
-            cm = CompiledModel(spec, blk)
+            cm = CompiledModel(spec, blk, method)
             _compiled[key] = cm
     return cm
 

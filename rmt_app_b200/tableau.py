@@ -54,7 +54,23 @@ RODAS4 = {
     ],
 }
 
-TABLEAUX = {"rodas4": RODAS4}
+# Rodas3 (Sandu, Verwer et al. 1997, the KPP "Rodas3" integrator): 4 stages, order 3(2), L-stable,
+# stiffly accurate; stage 2 is evaluated at y_n (a21 = 0) so it re-uses f(y_n): 3 RHS evaluations
+# (one of them together with the Jacobian) per step.  No dense output: output points are hit by
+# stepping onto them.
+RODAS3 = {
+    "name": "rodas3",
+    "stages": 4,
+    "order": 3,
+    "gamma": 0.5,
+    "a": [[], [0.0], [2.0, 0.0], [2.0, 0.0, 1.0]],
+    "c": [[], [4.0], [1.0, -1.0], [1.0, -1.0, -8.0/3.0]],
+    "m": [2.0, 0.0, 1.0, 1.0],
+    "e": [0.0, 0.0, 0.0, 1.0],
+    "dense": None,
+}
+
+TABLEAUX = {"rodas4": RODAS4, "rodas3": RODAS3}
 
 
 def reference_step(tab, f, jac, y, h):

@@ -1,0 +1,78 @@
+"""Host-side front-end logic (no GPU): input row mapping, block-size choice, structural cache, API errors."""
+import numpy as np
+import pytest
+
+import cases
+from rmt_app_b200 import engine, rmtCom
+from rmt_app_b200.componentdb import COMPONENTS, componentSymbolList
+from rmt_app_b200.model import ModelSpec
+
+
+def test_rmtcom_matches_reference_order():
+    assert rmtCom() == "CO2,H2,CH3OH,H2O,CO,DME,N2,CH4,C2H4,C3H6,C3H8,C4H10"
+    assert tuple(COMPONENTS) == componentSymbolList
+
+
+def test_uniform_inputs_follow_header_order():
+    mi = cases.methanol_testfile_input("N1")
+    spec = ModelSpec(mi)
+    u = engine.uniform_inputs(spec, mi)
+    assert spec.input_names() == ["temperature", "pressure"] + ["concentration[%d]" % i for i in range(6)] + [
+        "volumetric-flowrate", "ReInDi", "ReLe", "PaDi", "BeVoFr", "OvHeTrCo", "MeTe", "VARS:CaBeDe"]
+    assert u.size == spec.nin == 16
+    assert u[0] == 523 and u[1] == 5e6 and u[-1] == pytest.approx(1982*0.61)
+    np.testing.assert_array_equal(u[2:8], mi["feed"]["concentration"])
+    assert u[13] == 100 and u[14] == 522
+    # the scalar VARS value comes from THIS modelInput even though the compiled model is shared
+    mi2 = cases.methanol_readme_input("N1")
+    cm1, cm2 = engine.compile_model(mi), engine.compile_model(mi2)
+    assert cm1 is cm2
+    assert engine.uniform_inputs(cm2.spec, mi2)[-1] == 1171.2
+
+
+def test_sweep_rows_mapping_and_errors():
+    mi = cases.methanol_readme_input("N1")
+    mi["reaction-rates"] = cases.methanol_kinetics_param(1171.2)
+    spec = ModelSpec(mi)
+    B = 5
+    sw = {"pressure": np.arange(B) + 1.0, "concentration": np.arange(B*6, dtype=float).reshape(B, 6),
+          "E1": -np.ones(B), "MeTe": np.full(B, 500.0)}
+    rows, row_map = engine.sweep_rows(spec, sw, B)
+    assert rows.shape == (9, B)
+    assert row_map[1] == 0 and list(row_map[2:8]) == [1, 2, 3, 4, 5, 6]
+    names = spec.input_names()
+    assert row_map[names.index("VARS:E1")] == 7 and row_map[names.index("MeTe")] == 8
+    assert (row_map == -1).sum() == spec.nin - 9
+    np.testing.assert_array_equal(rows[3], sw["concentration"][:, 2])
+    with pytest.raises(KeyError, match="neither"):
+        engine.sweep_rows(spec, {"bogus": np.ones(B)}, B)
+    with pytest.raises(ValueError, match="shape"):
+        engine.sweep_rows(spec, {"pressure": np.ones(B + 1)}, B)
+    with pytest.raises(ValueError, match="concentration"):
+        engine.sweep_rows(spec, {"concentration": np.ones((B, 5))}, B)
+
+
+def test_block_size_keeps_one_block_per_sm_within_shared_memory():
+    for mk, n in ((lambda: cases.methanol_readme_input("N1"), 8), (lambda: cases.ch4_input("N1"), 5),
+                  (lambda: cases.ch4_input("N1", "iso-thermal"), 4)):
+        spec = ModelSpec(mk())
+        assert spec.n == n
+        b = engine.default_block(spec)
+        assert b % 32 == 0 and 32 <= b <= 256
+        assert b*8*(n*n + 6*n) + 1024 <= 227*1024
+
+
+def test_model_key_depends_on_structure_only():
+    a = ModelSpec(cases.methanol_readme_input("N1")).key()
+    b = ModelSpec(cases.methanol_testfile_input("N1")).key()
+    c = ModelSpec(cases.methanol_readme_input("N2")).key()
+    mi = cases.methanol_readme_input("N1")
+    mi["reaction-rates"] = cases.methanol_kinetics_param(1171.2)
+    d = ModelSpec(mi).key()
+    assert a == b and a != c and a != d
+
+
+def test_n_unknowns():
+    assert ModelSpec(cases.methanol_readme_input("N2")).n == 7
+    assert ModelSpec(cases.ch4_input("N2", "iso-thermal")).n == 3
+    assert ModelSpec(cases.ch4_input("N1", "iso-thermal")).n == 4

@@ -41,11 +41,25 @@ for v in variants:
         mod.n1_solve(B, d_consts, z, 1e-3, 1e-6, d_out, d_status, d_stats, stream=stream)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)/3
+    # stand-alone RHS / Jacobian kernels
+    n = info.n
+    d_y = torch.rand((n, B), dtype=torch.float64, device="cuda")*0.5 + 0.25
+    d_y[n - 2] = 1.0; d_y[n - 1] = 0.1
+    d_f = torch.empty((n, B), dtype=torch.float64, device="cuda"); d_J = torch.empty((n*n, B), dtype=torch.float64, device="cuda")
+    tk = {}
+    for nm, fn in (("rhs", lambda: mod.n1_rhs(B, d_consts, d_y, d_f, stream=stream)), ("jac", lambda: mod.n1_jac(B, d_consts, d_y, d_f, d_J, stream=stream))):
+        for _ in range(3): fn()
+        a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(20): fn()
+        a1.record(); torch.cuda.synchronize()
+        tk[nm] = a0.elapsed_time(a1)/20
     out = d_out.cpu().numpy(); ok = int((d_status == 0).sum())
     if ref is None:
         ref = out
     same = np.array_equal(out, ref)
     dev = np.nanmax(np.abs(out - ref)/np.abs(ref))
-    print("%-40s %8.2f ms  %.2f Msolves/s  ok %d  identical %s maxdev %.1e  (compile %.0fs, att/solve %.1f)" % (
-        ",".join(v), ms, B/ms/1e3, ok, same, dev, tc, d_stats[3].double().mean().item()))
+    print("%-40s %8.2f ms  %.2f Msolves/s  ok %d  identical %s maxdev %.1e  (compile %.0fs, att/solve %.1f) rhs %.4f ms (%.0f GB/s) jac %.4f ms (%.0f GB/s)" % (
+        ",".join(v), ms, B/ms/1e3, ok, same, dev, tc, d_stats[3].double().mean().item(),
+        tk["rhs"], 8e-6*(info.nconst + 2*n)*B/tk["rhs"], tk["jac"], 8e-6*(info.nconst + 2*n + n*n)*B/tk["jac"]))
     mod.close()

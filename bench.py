@@ -368,14 +368,14 @@ def run_gpu_arm(args, rank, world, local_rank):
     if rank == 0 and not args.no_n2:
         from rmt_app_b200 import rmtExe, solverSetting
         mi2 = cases.methanol_readme_input("N2")
-        cm2 = engine.compile_model(mi2)
         solverSetting["N2"]["zNo"] = 50
         rmtExe(mi2)
         t0 = time.perf_counter()
         rmtExe(mi2)
         single_s = time.perf_counter() - t0
         solverSetting["N2"]["zNo"] = 20
-        Bn, zn = 4096, 200
+        Bn, zn = 12500, 200                     # BASELINE configs[4]: 100k instances x 200 nodes over 8 GPUs
+        cm2 = engine.compile_model(mi2, block=engine.n2_block(Bn))
         sw2 = cases.config3_sweep(Bn, 20240613)
         for _ in range(2):
             torch.cuda.synchronize(); t0 = time.perf_counter()

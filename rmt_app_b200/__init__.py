@@ -4,9 +4,13 @@ pseudo-homogeneous packed-bed reactor models N1 (steady state) and N2
 
     from rmt_app_b200 import rmtExe, rmtCom, rmtExeBatch
 """
-from .rmt import rmtExe, rmtCom, rmtExeBatch      # noqa: F401
+from .rmt import rmtExe, rmtCom, rmtExeBatch, rmtExeBatchN2      # noqa: F401
 from .engine import solverSetting, Workspace       # noqa: F401
 
 from .ensemble import rmtExeBatchSharded            # noqa: F401
 
-__all__ = ["rmtExe", "rmtCom", "rmtExeBatch", "rmtExeBatchSharded", "solverSetting", "Workspace"]
+from .textkin import parse_reaction_rates           # noqa: F401
+from .estimate import differential_evolution        # noqa: F401
+
+__all__ = ["rmtExe", "rmtCom", "rmtExeBatch", "rmtExeBatchN2", "rmtExeBatchSharded", "solverSetting", "Workspace",
+           "parse_reaction_rates", "differential_evolution"]

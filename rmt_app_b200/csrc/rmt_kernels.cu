@@ -1360,8 +1360,12 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n2_solve(const Solve
                 }
             }
         }
-        if (__all_sync(FULL, inst < 0)) break;
-        if (inst < 0) continue;
+        // Lockstep: all warps of the block walk the same node loops (same zNo, same stage count), so a block
+        // barrier per node keeps them on the same instructions and lets them share instruction-cache lines
+        // (the sweep body is far larger than the I-cache).  Lanes without a reactor run as ghosts on their own
+        // work slot; every write to out / status / stats is predicated on `live`.
+        if (__syncthreads_and(inst < 0)) break;
+        const bool live = inst >= 0;
         const int YN = cur ? W_Y1 : W_Y0, YP = cur ? W_Y0 : W_Y1;
 
         if (fresh) {
@@ -1396,6 +1400,7 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n2_solve(const Solve
             double ub[RMT_N] = {0}, u[RMT_N], fo[RMT_N];
             NodeJac nj;
             for (int k = 0; k < zNo; ++k) {
+                __syncthreads();
 #pragma unroll
                 for (int v = 0; v < RMT_N; ++v) u[v] = WK(YN + v, k);
                 n2_node<true>(u, ub, k == 0, P, invdz, h, fo, E, nj);
@@ -1456,6 +1461,7 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n2_solve(const Solve
             double ub[RMT_N] = {0}, kprev[RMT_N] = {0};
             const bool lastStage = s == RMT_ROS_S - 1;
             for (int k = 0; k < zNo; ++k) {
+                __syncthreads();
                 double rhs[RMT_N], u[RMT_N];
                 if (s == 0) {
 #pragma unroll
@@ -1555,7 +1561,7 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n2_solve(const Solve
             if (last_rejected) hnew = fmin(hnew, hh);
             last_rejected = false;
             hstep = clipped ? fmax(hnew, hstep) : hnew;
-            if (t >= tend) {
+            if (t >= tend && live) {
                 // end of a slab: un-scale and store (sortResult5, solResultAnalysis.py:252-301; :3630-3661)
                 const int YC = cur ? W_Y1 : W_Y0;
                 const int rows = n2_out_rows(a.out_mode);
@@ -1600,7 +1606,7 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n2_solve(const Solve
             else if (hstep < 1e-14*fmax(a.period, 1e-300)) fin = 2;
             else if (nanrej > 30) fin = 3;
         }
-        if (fin >= 0) {
+        if (fin >= 0 && live) {
             a.status[inst] = fin;
             a.stats[inst] = nacc; a.stats[a.B + inst] = nrej;
             a.stats[2*a.B + inst] = (nacc + nrej)*(RMT_ROS_S - 1); a.stats[3*a.B + inst] = nacc + nrej;

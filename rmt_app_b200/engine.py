@@ -78,6 +78,15 @@ def _fn_sig(f):
     return (f.__code__, cells, repr(f.__defaults__), id(f.__globals__))
 
 
+def n2_block(B, sm_count=148):
+    """Threads per block of the N2 integrator (one reactor per thread, one lockstep block per SM):
+    spread a small ensemble over all SMs rather than filling a few of them."""
+    for b in (256, 128, 64):
+        if B >= sm_count*b*3//4:
+            return b
+    return 32
+
+
 def _method_of(modelInput, method=None):
     """Integrator tableau: solver-config.method (extension key) or the default Rodas4(3)."""
     from .tableau import TABLEAUX

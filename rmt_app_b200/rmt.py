@@ -108,7 +108,7 @@ def _runN1(modelInput):
 def _runN2(modelInput):
     from .engine import n2_solve_ensemble
     start = timer()
-    cm = engine.compile_model(modelInput)
+    cm = engine.compile_model(modelInput, block=engine.n2_block(1))
     spec = cm.spec
     nc, n = spec.nc, spec.n
     zNo, tNo = solverSetting['N2']['zNo'], solverSetting['N2']['tNo']
@@ -188,3 +188,32 @@ def rmtExeBatch(modelInput, sweep=None, B=None, *, rtol=None, atol=None, profile
     return {"dataYs": data, "status": res.status, "success": success, "stats": res.stats, "dataXs": res.z_eval,
             "objective": res.objective, "h2d_bytes": res.h2d_bytes, "d2h_bytes": res.d2h_bytes, "labelList": list(cm.spec.compList) + ["Pressure"] + (
                 [] if cm.spec.iso else ["Temperature"]), "comTime": (timer() - tic)*1000}
+
+
+def rmtExeBatchN2(modelInput, sweep=None, B=None, *, zNo=None, tNo=None, rtol=None, atol=None,
+                  keep_on_device=False, workspace=None):
+    """Ensemble form of rmtExe for the dynamic model "N2": B independent reactors integrated over
+    [0, period]; returns the profiles at the end of each of the tNo slabs.
+
+    Returns {"dataYs": [B, tNo, nc+1, zNo] (rows y_i..., T [K] — each [b, i] is one dataPack
+    entry's dataYs, pbHomoReactor.py:3660-3677), "dataTime": [tNo], "dataXs": [zNo], "status": [B], ...}."""
+    tic = timer()
+    _check_components(modelInput)
+    if modelInput['model'] != "N2":
+        raise NotImplementedError("rmtExeBatchN2 covers model N2")
+    if B is None:
+        if not sweep:
+            raise ValueError("give B or a non-empty sweep")
+        first = next(iter(sweep.values()))
+        B = int(first.shape[0]) if hasattr(first, "shape") else len(first)
+    zNo = int(solverSetting['N2']['zNo'] if zNo is None else zNo)
+    tNo = int(solverSetting['N2']['tNo'] if tNo is None else tNo)
+    cm = engine.compile_model(modelInput, block=engine.n2_block(B))
+    res = engine.n2_solve_ensemble(cm, modelInput, sweep, B, zNo=zNo, tNo=tNo, rtol=rtol, atol=atol, out_mode=1,
+                                   keep_on_device=keep_on_device, workspace=workspace)
+    out = res.out.permute(3, 0, 1, 2) if keep_on_device else np.transpose(res.out, (3, 0, 1, 2))
+    period = float(modelInput['operating-conditions']['period'])
+    return {"dataYs": out, "dataTime": np.linspace(0, period, tNo + 1)[1:], "dataXs": np.linspace(0, 1, zNo),
+            "status": res.status, "success": res.status == 0, "stats": res.stats,
+            "labelList": list(cm.spec.compList) + ([] if cm.spec.iso else ["Temperature"]),
+            "comTime": (timer() - tic)*1000}

@@ -23,7 +23,7 @@ for nm, mk, z, ref, tols in [("ch4", lambda: cases.ch4_input("N2"), 20, "n2_sol_
     solverSetting["N2"]["zNo"] = z
     for rtol, atol in tols:
         mi = mk(); mi["solver-config"].update(rtol=rtol, atol=atol)
-        cm = engine.compile_model(mi)
+        cm = engine.compile_model(mi, block=engine.n2_block(1))
         t0 = time.time()
         res = engine.n2_solve_ensemble(cm, mi, None, 1, out_mode=1)
         dt = time.time() - t0
@@ -31,11 +31,12 @@ for nm, mk, z, ref, tols in [("ch4", lambda: cases.ch4_input("N2"), 20, "n2_sol_
         print("%s rtol %g: status %d stats %s  %.2fs | vs %s: max rel all slabs %.2e, last slab outlet %.2e, T prof %.2e" % (
             nm, rtol, res.status[0], res.stats[:, 0], dt, ref, rel.max(), rel[-1][:, -1].max(), rel[-1][-1].max()))
 # small ensemble timing
-mi = cases.methanol_readme_input("N2"); cm = engine.compile_model(mi)
-for B, z in [(1024, 50), (4096, 50), (4096, 200)]:
+mi = cases.methanol_readme_input("N2")
+for B, z, blk in [(1024, 50, None), (4096, 50, None), (4096, 200, None), (4096, 200, 64), (12500, 200, None), (12500, 200, 128), (12500, 200, 256), (50000, 50, None)]:
+    cm = engine.compile_model(mi, block=blk or engine.n2_block(B))
     sw = cases.config3_sweep(B, 20240613)
     torch.cuda.synchronize(); t0 = time.time()
     res = engine.n2_solve_ensemble(cm, mi, sw, B, zNo=z, tNo=5, period=0.5, keep_on_device=True)
     torch.cuda.synchronize(); dt = time.time() - t0
     st = res.stats.cpu().numpy(); ok = int((res.status == 0).sum())
-    print("N2 ensemble B=%d zNo=%d: %.2fs -> %.0f inst/s, ok %d, steps mean %.0f rej %.1f" % (B, z, dt, B/dt, ok, st[0].mean(), st[1].mean()))
+    print("N2 ensemble B=%d zNo=%d block %d: %.2fs -> %.0f inst/s, ok %d, steps mean %.0f rej %.1f" % (B, z, cm.block, dt, B/dt, ok, st[0].mean(), st[1].mean()))

@@ -403,7 +403,10 @@ def run_gpu_arm(args, rank, world, local_rank):
             "converged": n_ok_all, "instances": world*B,
             "roofline": {
                 "kernel": "rmt_n1_solve", "bound": "fp64", "achieved": alg/solve_s/1e12, "peak": fp64_peak,
-                "unit": "TFLOP/s", "frac": alg/solve_s/1e12/fp64_peak, "traffic": None,
+                "unit": "TFLOP/s", "frac": alg/solve_s/1e12/fp64_peak,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the ncu --set full capture of this
+                # command at 2^20 reactors (profiles/r01_ncu_n1_solve_v3_final.csv: 179.7 MB + 63.0 MB), scaled per reactor
+                "traffic": 231.5*B, "traffic_algorithmic": 8.0*(22 + n)*B + 20.0*B,
                 "achieved_weighted": wt/solve_s/1e12, "frac_weighted": wt/solve_s/1e12/fp64_peak,
                 "peak_source": "rmt_dfma_peak measured in this run (MEASURED_PEAKS.json has no FP64 figure; "
                                "nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2)",

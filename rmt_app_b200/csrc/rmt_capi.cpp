@@ -165,7 +165,7 @@ int scratch_get(Module* M, size_t bytes, CUdeviceptr* out)
 
 // default step-size controller: safety, max shrink, max growth, tolerance scale kappa, PI beta,
 // initial-step factor (applied to the Hairer-Wanner starting step)
-const double RMT_DEFAULT_CTRL[6] = {0.8, 5.0, 6.0, 1.0, 0.08, 0.1};
+const double RMT_DEFAULT_CTRL[6] = {0.8, 5.0, 6.0, 1.0, 0.08, 0.03};
 
 // diagnostics: step log of one instance (rmt_debug_trace)
 double* g_trace_buf = nullptr;

@@ -206,6 +206,10 @@ __device__ __forceinline__ double rmt_sqrt(const double x)
 #define RMT_ROLL 1
 #endif
 // with RMT_SYNC == 1: a block barrier every RMT_SYNC_EVERY-th step attempt
+// read each stage vector once per stage (argument and c-sum together) at the cost of 2n live registers
+#ifndef RMT_MERGE_KLOADS
+#define RMT_MERGE_KLOADS 1
+#endif
 #ifndef RMT_SYNC_EVERY
 #define RMT_SYNC_EVERY 1
 #endif
@@ -680,9 +684,9 @@ struct SolveArgs {
 #define KS(s, i) SM(RMT_N*RMT_N + (s)*RMT_N + (i))
 #define RMT_SMEM_DOUBLES_PER_THREAD (RMT_N*RMT_N + RMT_ROS_S*RMT_N)
 
-struct SmemJac {
+struct SmemJac {            // stores -J: the iteration matrix is W = I/(h*gamma) - J
     double* sm;
-    __device__ __forceinline__ void operator()(int r, int c, double v) const { LU(r, c) = v; }
+    __device__ __forceinline__ void operator()(int r, int c, double v) const { LU(r, c) = -v; }
 };
 
 // rows written per output point: mode 0 raw scaled state (sol.y); mode 1 dataYs rows
@@ -805,7 +809,7 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
         // ---- one step attempt ----
         double f0[RMT_N];
         SmemJac sj{sm};
-        n1_eval<true>(y, h, f0, sj);                          // f(y_n) and J into LU(.,.)
+        n1_eval<true>(y, h, f0, sj);                          // f(y_n), and -J into LU(.,.)
 
         if (fresh) {
             // initial step (Hairer-Wanner II.4 with the exact y'' = J f)
@@ -815,7 +819,7 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
                 const double sc = a.ctrl[3]*(a.atol + a.rtol*fabs(y[i]));
                 double jf = 0.0;
 #pragma unroll
-                for (int j = 0; j < RMT_N; ++j) jf += LU(i, j)*f0[j];
+                for (int j = 0; j < RMT_N; ++j) jf -= LU(i, j)*f0[j];
                 d0 += (y[i]/sc)*(y[i]/sc); d1 += (f0[i]/sc)*(f0[i]/sc); d2 += (jf/sc)*(jf/sc);
             }
             d0 = sqrt(d0/RMT_N); d1 = sqrt(d1/RMT_N); d2 = sqrt(d2/RMT_N);
@@ -836,9 +840,7 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
         // shared-memory address of each (pivoted) row, so every access is [row + immediate].
         const double dg = 1.0/(hh*RMT_ROS_GAMMA);
 #pragma unroll
-        for (int i = 0; i < RMT_N; ++i)
-#pragma unroll
-            for (int j = 0; j < RMT_N; ++j) LU(i, j) = (i == j ? dg : 0.0) - LU(i, j);
+        for (int i = 0; i < RMT_N; ++i) LU(i, i) += dg;
         double* row[RMT_N];
         int perm[RMT_N];
 #pragma unroll
@@ -918,12 +920,24 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
                 for (int i = 0; i < RMT_N; ++i) u[i] = y[i];
 #if RMT_ROLL
                 // rolled form: one copy of the RHS / triangular-solve code for all stages (instruction-cache
-                // footprint); tableau rows are read from the constant bank with a runtime stage index
+                // footprint); tableau rows are read from the constant bank with a runtime stage index.
+                // Each K_j is read once for both the stage argument and the (c_sj/h) K_j sum.
+#if RMT_MERGE_KLOADS
+                double vc[RMT_N];
+#pragma unroll
+                for (int i = 0; i < RMT_N; ++i) vc[i] = 0.0;
+#endif
                 for (int j = 0; j < s; ++j) {
                     const double aj = RMT_cROS_A[s][j];
                     const double* kj = &KS(j, 0);
+#if RMT_MERGE_KLOADS
+                    const double cj = RMT_cROS_C[s][j]*invh;
+#pragma unroll
+                    for (int i = 0; i < RMT_N; ++i) { const double kv = kj[i*RMT_BLOCK]; u[i] += aj*kv; vc[i] += cj*kv; }
+#else
 #pragma unroll
                     for (int i = 0; i < RMT_N; ++i) u[i] += aj*kj[i*RMT_BLOCK];
+#endif
                 }
 #else
 #pragma unroll
@@ -935,12 +949,17 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
 #endif
                 n1_eval<false>(u, h, rhs, NoJac());
 #if RMT_ROLL
+#if RMT_MERGE_KLOADS
+#pragma unroll
+                for (int i = 0; i < RMT_N; ++i) rhs[i] += vc[i];
+#else
                 for (int j = 0; j < s; ++j) {
                     const double cj = RMT_cROS_C[s][j]*invh;
                     const double* kj = &KS(j, 0);
 #pragma unroll
                     for (int i = 0; i < RMT_N; ++i) rhs[i] += cj*kj[i*RMT_BLOCK];
                 }
+#endif
 #else
 #pragma unroll
                 for (int j = 0; j < s; ++j)

@@ -44,7 +44,8 @@ typedef uint64_t rmt_module_t;   /* module loaded on the current device       */
 
 /* model description read back from a loaded module */
 typedef struct rmt_module_info {
-    int32_t model;        /* 1 = N1, 2 = N2                                    */
+    int32_t model;        /* 1 = N1, 2 = N2, 7 = M7 (dimensional twin of N1;    */
+                          /* served by the rmt_n1_* entry points)               */
     int32_t n;            /* unknowns per axial point                          */
     int32_t nc;           /* species                                           */
     int32_t nr;           /* reactions                                         */
@@ -87,7 +88,8 @@ int rmt_module_free(rmt_module_t m);
  * d_rows [n_rows][B] holds the inputs that vary per instance; row_map[q] (q <
  * nin) is the row of input q in d_rows or -1, in which case uniform[q] is used
  * for every instance.  Input order: temperature, pressure, concentration[nc],
- * volumetric-flowrate, ReInDi, ReLe, PaDi, BeVoFr, OvHeTrCo, MeTe, then the
+ * volumetric-flowrate, ReInDi, ReLe, PaDi, BeVoFr, OvHeTrCo, MeTe,
+ * mixture-viscosity, EfHeTrAr (the last two are read by model M7 only), then the
  * scalar VARS entries in VARS order.  d_consts [nconst][B]. */
 int rmt_setup(rmt_module_t m, int64_t B, const double* d_rows, int32_t n_rows, const int32_t* row_map,
               const double* uniform, double* d_consts, void* stream);

@@ -37,7 +37,7 @@ Tref = 273.15 + 25.00       # core/constants.py:17-23
 
 # N1/N2 grid sizes, solvers/solSetting.py:30-39 (module-level mutable dict in
 # the reference; same here so tests can override zNo exactly as callers do).
-solverSetting = {"N1": {"zNo": 100}, "N2": {"zNo": 20, "rNo": 5, "tNo": 5, "timesNo": 5}}
+solverSetting = {"N1": {"zNo": 100}, "N2": {"zNo": 20, "rNo": 5, "tNo": 5, "timesNo": 5}, "M9": {"zNo": 30}}
 
 # ----------------------------------------------------------------------------
 # component data — data/componentData.py:11-22 (MW), :72-86 (dHf25),
@@ -457,6 +457,84 @@ class N2Oracle(HomoReactorSetup):
         return {"computation-time": 0.0, "dataPack": dataPack}
 
 
+class M7Oracle:
+    """Model M7 = PackedBedReactorClass.runM3 + modelEquationM3 (docs/pbReactor.py:1170-1575): the
+    DIMENSIONAL steady-state twin of N1, unknowns [C_i [mol/m^3]..., T [K], P [Pa]] over z in [0, ReLe]."""
+
+    def __init__(self, modelInput):
+        mi = self.modelInput = modelInput
+        self.P, self.T = mi['operating-conditions']['pressure'], mi['operating-conditions']['temperature']
+        self.reactionList = list(mi['reactions'].values())
+        self.reactionListSorted, self.reactionStochCoeff = parse_reactions(mi['reactions'])
+        self.varis, self.rates = mi['reaction-rates']['VARS'], mi['reaction-rates']['RATES']
+        self.compList = list(mi['feed']['components']['shell'])
+        for c in self.compList:
+            if c not in componentSymbolList:
+                raise Exception("Component database is not up to date!")
+        self.compNo = nc = len(self.compList)
+        rs = mi['reactor']
+        self.ReLe, self.PaDi, self.BeVoFr = rs['ReLe'], rs['PaDi'], rs['BeVoFr']
+        self.CrSeAr = PI_CONST*(rs['ReInDi'] ** 2)/4                      # :1218
+        self.VoFlRa0 = mi['feed']['volumetric-flowrate']
+        self.SpCoi0 = 1*np.array(mi['feed']['concentration'], dtype=float)
+        self.SpCo0 = np.sum(self.SpCoi0)
+        self.MoWei = [_DB[s][0] for s in self.compList]
+        self.ExHe = mi['external-heat']                                   # EfHeTrAr used as given (:1508)
+        self.GaMiVi = mi['feed']['mixture-viscosity']                     # :1235 (input, not Wilke)
+        self.StHeRe25 = np.array([standard_enthalpy_of_reaction(r) for r in self.reactionList])
+        self.IV = np.concatenate([self.SpCoi0, [self.T, self.P]])         # :1240-1246
+        self.times = np.linspace(0, self.ReLe, solverSetting['M9']['zNo'])   # :1283-1287
+
+    def rhs(self, t, y):
+        """modelEquationM3, :1371-1575."""
+        nc, BeVoFr, PaDi = self.compNo, self.BeVoFr, self.PaDi
+        InGaVe0 = self.VoFlRa0/(self.CrSeAr*BeVoFr)
+        y = np.asarray(y, dtype=float)
+        CoSpi, T, P = y[0:nc], y[nc], y[nc+1]
+        CoSp = np.sum(CoSpi)
+        MoFri = CoSpi/np.sum(CoSpi)
+        InGaVe = InGaVe0*(CoSp/self.SpCo0)*(self.P/P)
+        SuGaVe = InGaVe*BeVoFr
+        MoFl = (CoSp*SuGaVe*self.CrSeAr)/self.CrSeAr
+        MiMoWe = np.dot(MoFri, np.array(self.MoWei))*1e-3
+        GaDe = MiMoWe*CoSp                                              # calDensityIG, not the EOS one (:1471)
+        ergA = 150*self.GaMiVi*SuGaVe/(PaDi**2)
+        ergB = ((1-BeVoFr)**2)/(BeVoFr**3)
+        ergC = 1.75*GaDe*(SuGaVe**2)/PaDi
+        ergD = (1-BeVoFr)/(BeVoFr**3)
+        RHS_ergun = -1*(ergA*ergB + ergC*ergD)
+        Ri = np.array(reaction_rate_exe((T, P, MoFri, CoSpi), self.varis, self.rates))
+        ri = component_formation_rate(nc, self.compList, self.reactionStochCoeff, Ri)
+        CpMeanMixture = np.dot(MoFri, cp_mean_list(self.compList, T))
+        HeReT = np.array(np.array(enthalpy_change_of_reaction(self.reactionListSorted, T)) + self.StHeRe25)
+        OvHeReT = np.dot(Ri, HeReT)
+        Qm = (self.ExHe['OvHeTrCo']*self.ExHe['EfHeTrAr'])*(self.ExHe['MeTe'] - T)     # no adiabatic switch here
+        const_C1 = 1/SuGaVe
+        const_T1 = 1/(MoFl*CpMeanMixture)
+        return [const_C1*ri[i] for i in range(nc)] + [const_T1*(-OvHeReT + Qm), RHS_ergun]
+
+    def solve(self, method=None, rtol=None, atol=None):
+        ivp = self.modelInput['solver-config']['ivp']
+        method = method or ("LSODA" if ivp == 'default' else ivp)
+        kw = {}
+        if rtol is not None:
+            kw["rtol"] = rtol
+        if atol is not None:
+            kw["atol"] = atol
+        return solve_ivp(lambda t, y: self.rhs(t, y), np.array([0, self.ReLe]), self.IV, method=method,
+                         t_eval=self.times, **kw)
+
+    def pack(self, sol):
+        """:1301-1368 — mole fractions + temperature rows, plot-helper lists (library/plot.py:85-115)."""
+        nc = self.compNo
+        C = sol.y[0:nc, :]
+        dataYs = np.concatenate((C/np.sum(C, axis=0), [sol.y[nc, :]]), axis=0)
+        labelList = self.compList.copy() + ["Temperature", "Pressure"]
+        XYList = [[sol.t, item] for item in dataYs]
+        dataList = [{"x": XYList[i][0], "y": XYList[i][1], "leg": labelList[i]} for i in range(len(XYList))]
+        return {"dataYs": dataYs, "XYList": XYList, "dataList": dataList, "nfev": sol.nfev, "solY": sol.y}
+
+
 def rmtExe(modelInput, method=None, rtol=None, atol=None):
     """rmt.py:21-80 restricted to the N1/N2 branch of rmtCore.py:63-127."""
     if modelInput['model'] == "N1":
@@ -469,6 +547,12 @@ def rmtExe(modelInput, method=None, rtol=None, atol=None):
     elif modelInput['model'] == "N2":
         o = N2Oracle(modelInput)
         res = o.solve(method=method, rtol=rtol, atol=atol)
+    elif modelInput['model'] == "M7":
+        o = M7Oracle(modelInput)
+        sol = o.solve(method=method, rtol=rtol, atol=atol)
+        if sol.success is False:
+            raise RuntimeError("ODE Error")
+        res = o.pack(sol)
     else:
         raise NotImplementedError(modelInput['model'])
     return {"resModel": res, "comTime": 0.0}

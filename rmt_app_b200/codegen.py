@@ -139,7 +139,7 @@ def balance_flops(spec):
     div = nc + 2
     # formation rates, Cp polynomials + means + mixture, heats of reaction
     mul_add += 2*nnz + 2 + 8*nc + 2*nc + energy*(8*nr + 2*nr + 1 + 3)
-    if spec.model == "N1":
+    if spec.model in ("N1", "M7"):
         mul_add += 3 + 7 + nc + energy*6      # velocities, Ergun, balances
         div += 5 + 1 + 1 + nc + energy*3
     else:

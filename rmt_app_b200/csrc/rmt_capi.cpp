@@ -399,8 +399,8 @@ int rmt_module_load(const void* cubin, size_t size, rmt_module_t* module_out)
     M->f_peak = get("rmt_dfma_peak");
     M->f_probe = get("rmt_math_probe");
     if (!M->f_setup) { drv.p_cuModuleUnload(M->mod); delete M; return fail("module lacks rmt_setup"); }
-    CUfunction fs = I.model == 1 ? M->f_n1_solve : M->f_n2_solve;
-    if (fs && I.model == 1) {
+    CUfunction fs = I.model != 2 ? M->f_n1_solve : M->f_n2_solve;
+    if (fs && I.model != 2) {
         M->solve_smem = (size_t)I.block*8*((size_t)I.n*I.n + (size_t)I.stages*I.n);
         CU(cuFuncSetAttribute(fs, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)M->solve_smem));
         CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&M->solve_blocks_per_sm, fs, I.block, M->solve_smem));
@@ -490,7 +490,7 @@ int rmt_n1_solve(rmt_module_t m, int64_t B, const double* d_consts, int32_t n_ev
     Module* M = get_module(m);
     if (!M) return fail("invalid module handle");
     if (ensure_ctx()) return 1;
-    if (M->info.model != 1) return fail("rmt_n1_solve: module was generated for model N2");
+    if (M->info.model == 2) return fail("rmt_n1_solve: module was generated for model N2");
     if (B <= 0 || n_eval < 1 || !z_eval) return fail("rmt_n1_solve: need B > 0 and at least one output position");
     for (int e = 1; e < n_eval; ++e)
         if (!(z_eval[e] > z_eval[e - 1])) return fail("rmt_n1_solve: z_eval must be strictly increasing");

@@ -184,14 +184,23 @@ __device__ __forceinline__ double rmt_sqrt(const double x)
 #define RMT_PI 3.141592653589793        // core/constants.py:14
 #define RMT_EPS_CONST 1e-30             // core/constants.py:11
 
-#if defined(RMT_MODEL_N1)
+// steady-state axial models share the integrator: N1 (dimensionless, [Ci..., P, (T)]) and its dimensional
+// twin M7 = pbReactor.runM3 ([Ci..., T, P], docs/pbReactor.py:1170-1575)
+#if defined(RMT_MODEL_N1) || defined(RMT_MODEL_M7)
+#define RMT_STEADY 1
+#endif
+#if defined(RMT_MODEL_M7)
+#define RMT_N (RMT_NC + 2)                       // Ci [mol/m^3]..., T [K], P [Pa]
+#define RMT_IT RMT_NC
+#define RMT_IP (RMT_NC + 1)
+#elif defined(RMT_MODEL_N1)
 #define RMT_N (RMT_NC + (RMT_ISO ? 1 : 2))      // Ci..., P, (T)
+#define RMT_IP RMT_NC                            // N1: index of P-hat
+#define RMT_IT (RMT_NC + 1)                      // N1: index of T-hat
 #else
 #define RMT_N (RMT_NC + (RMT_ISO ? 0 : 1))      // Ci..., (T) per node
 #endif
 #define RMT_NCONST_VALUE (29 + RMT_NC + RMT_NKP)
-#define RMT_IP RMT_NC                            // N1: index of P-hat
-#define RMT_IT (RMT_NC + 1)                      // N1: index of T-hat
 
 #ifndef RMT_BLOCK
 #define RMT_BLOCK 256
@@ -234,6 +243,8 @@ extern "C" __global__ void rmt_meta(int* out)
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
 #if defined(RMT_MODEL_N1)
     out[0] = 1;
+#elif defined(RMT_MODEL_M7)
+    out[0] = 7;
 #else
     out[0] = 2;
 #endif
@@ -249,6 +260,7 @@ extern "C" __global__ void rmt_meta(int* out)
 enum {
     IN_T = 0, IN_P = 1, IN_C0 = 2,
     IN_Q = 2 + RMT_NC, IN_D, IN_L, IN_DP, IN_EPS, IN_U, IN_TM,
+    IN_MUG, IN_AEX,            // feed.mixture-viscosity and external-heat.EfHeTrAr: read by M7 only
     IN_KP0
 };
 static_assert(IN_KP0 + RMT_NKP == RMT_NIN, "input row count");
@@ -311,12 +323,16 @@ extern "C" __global__ void __launch_bounds__(128) rmt_setup(const RmtInputs in, 
     const double A = RMT_PI*(D*D)/4;                         // :2751
     const double ui0 = Q0/(A*eps);                           // :3137 / :3391
     const double us0 = ui0*eps;
-#if defined(RMT_MODEL_N1)
+#if defined(RMT_MODEL_N1) || defined(RMT_MODEL_M7)
     const double vf = Q0/A;                                  // :2763
 #else
     const double vf = us0;                                   // :3452
 #endif
+#if defined(RMT_MODEL_M7)
+    const double a = rmt_in(in, IN_AEX, i);                  // M7 uses EfHeTrAr as given (pbReactor.py:1508)
+#else
     const double a = 4/D;                                    // :2778 (EfHeTrAr input ignored)
+#endif
     // pure-gas viscosities at feed T (gasTransPor.py:137-154, dataGasViscosity.py:133)
     double mu[RMT_NC];
 #pragma unroll
@@ -345,6 +361,9 @@ extern "C" __global__ void __launch_bounds__(128) rmt_setup(const RmtInputs in, 
         }
         mumix += (mu[p]*y0[p])/den;
     }
+#if defined(RMT_MODEL_M7)
+    mumix = rmt_in(in, IN_MUG, i);                           // feed.mixture-viscosity (pbReactor.py:1235)
+#endif
     const double T2 = T*T, T3 = T*T*T;
     double Cpf = 0.0, MWf = 0.0;
 #pragma unroll
@@ -370,15 +389,20 @@ extern "C" __global__ void __launch_bounds__(128) rmt_setup(const RmtInputs in, 
     c[(i64)H_INVC0*B] = 1.0/C0;   c[(i64)H_INVRHO0*B] = 1.0/rho0;
     c[(i64)H_INVGM*B] = 1.0/Gm;   c[(i64)H_INVGH*B] = 1.0/Gh;
     c[(i64)H_EPSCPF*B] = eps/Cpf;
-#if defined(RMT_MODEL_N1)
-    c[(i64)H_X0*B] = L/P;                  // 1/(Pf/zf), the Ergun scale
+#if defined(RMT_STEADY)
+    c[(i64)H_X0*B] = L/P;                  // 1/(Pf/zf), the Ergun scale (N1)
     c[(i64)H_X1*B] = 0.0;
 #else
     c[(i64)H_X0*B] = 1/(eps*(L/vf));       // const_F1, :4075
     c[(i64)H_X1*B] = 1/(L/vf);
 #endif
 #pragma unroll
-    for (int k = 0; k < RMT_NC; ++k) c[(i64)(K_IV0 + k)*B] = C0i[k]/Cmax;     // :2833 / :3489
+    for (int k = 0; k < RMT_NC; ++k)
+#if defined(RMT_MODEL_M7)
+        c[(i64)(K_IV0 + k)*B] = C0i[k];            // dimensional initial state (pbReactor.py:1240-1246)
+#else
+        c[(i64)(K_IV0 + k)*B] = C0i[k]/Cmax;       // :2833 / :3489
+#endif
 #pragma unroll
     for (int k = 0; k < RMT_NKP; ++k) c[(i64)(K_KP0 + k)*B] = rmt_in(in, IN_KP0 + k, i);
 }
@@ -387,7 +411,7 @@ extern "C" __global__ void __launch_bounds__(128) rmt_setup(const RmtInputs in, 
 struct Hot {
     double Cmax, Tf, Pf, us0, ergA, ergC, Ua, Tm;
     double invC0, invRho0, invGm, invGh, epsCpf;     // 1/C0, 1/rho0, 1/Gm, 1/Gh, eps/Cpf
-#if defined(RMT_MODEL_N1)
+#if defined(RMT_STEADY)
     double invBeta;              // zf/Pf
 #else
     double F1, invZv;            // 1/(eps*(zf/vf)), vf/zf
@@ -407,7 +431,7 @@ __device__ __forceinline__ void rmt_load_hot(const double* __restrict__ consts, 
     h.invC0 = __ldg(c + (i64)H_INVC0*B); h.invRho0 = __ldg(c + (i64)H_INVRHO0*B);
     h.invGm = __ldg(c + (i64)H_INVGM*B); h.invGh = __ldg(c + (i64)H_INVGH*B);
     h.epsCpf = __ldg(c + (i64)H_EPSCPF*B);
-#if defined(RMT_MODEL_N1)
+#if defined(RMT_STEADY)
     h.invBeta = __ldg(c + (i64)H_X0*B);
 #else
     h.F1 = __ldg(c + (i64)H_X0*B);
@@ -493,12 +517,104 @@ __device__ __forceinline__ void rmt_point(const double (&C)[RMT_NC], const doubl
     p.Qm = (h.Tm == 0.0) ? 0.0 : h.Ua*(h.Tm - T);             // rmtUtility.py:424-452
 }
 
-#if defined(RMT_MODEL_N1)
+#if defined(RMT_STEADY)
+struct NoJac { __device__ __forceinline__ void operator()(int, int, double) const {} };
+
+#if defined(RMT_MODEL_M7)
+// ---------------------------------------------------------------------------------
+// M7 right-hand side (modelEquationM3, docs/pbReactor.py:1371-1575): the dimensional twin of N1.
+// y = [C_i [mol/m^3]..., T [K], P [Pa]] along z [m].  Differences from N1 besides the scaling: the Ergun
+// term uses rho = MW*C (not the EOS density), the mixture viscosity and the exchange area are inputs, and
+// there is no adiabatic switch on MeTe.
+// ---------------------------------------------------------------------------------
+template <bool JAC, class JS>
+__device__ __forceinline__ void n1_eval(const double (&yv)[RMT_N], const Hot& h, double (&f)[RMT_N], JS&& J)
+{
+    double C[RMT_NC];
+#pragma unroll
+    for (int i = 0; i < RMT_NC; ++i) C[i] = yv[i];
+    const double T = yv[RMT_IT], P = yv[RMT_IP];
+    Point p; PointJac pj;
+    rmt_point<JAC>(C, T, P, h, p, pj);
+    const double invP = rmt_rcp(P);
+    const double w = (p.S*h.invC0)*(h.Pf*invP);               // rmtUtility.calGaVeFromEOS (:405-421)
+    const double us = h.us0*w;                                // SuGaVe
+    const double gade = p.MWm*p.S;                            // calDensityIG(MiMoWe, CoSp)
+    f[RMT_IP] = -1*(h.ergA*us + h.ergC*gade*(us*us));
+    const double c1 = rmt_rcp(us);
+#pragma unroll
+    for (int i = 0; i < RMT_NC; ++i) f[i] = p.r[i]*c1;
+    const double Qm = h.Ua*(h.Tm - T);
+    const double invDn = rmt_rcp((p.S*us)*p.Cp);              // 1/(MoFl*CpMeanMixture)
+    f[RMT_IT] = (-p.q + Qm)*invDn;
+    if (JAC) {
+        const double invS = p.invS, invCp = rmt_rcp(p.Cp);
+        double sy[RMT_NR];
+#pragma unroll
+        for (int j = 0; j < RMT_NR; ++j) {
+            double a = 0.0;
+#if RMT_RATES_DEP_Y
+#pragma unroll
+            for (int i = 0; i < RMT_NC; ++i) a += pj.dRdy[j][i]*p.y[i];
+#endif
+            sy[j] = a;
+        }
+#pragma unroll
+        for (int col = 0; col < RMT_N; ++col) {
+            const bool isC = col < RMT_NC, isP = col == RMT_IP;
+            const int cc = col < RMT_NC ? col : 0;
+            double dlnw, dgade = 0.0, dlnS = 0.0, dR[RMT_NR];
+            if (isC) {
+                dlnw = invS; dlnS = invS; dgade = 1e-3*RMT_cMW[cc];
+#pragma unroll
+                for (int j = 0; j < RMT_NR; ++j) {
+                    double a = 0.0;
+#if RMT_RATES_DEP_Y
+                    a = (pj.dRdy[j][cc] - sy[j])*invS;
+#endif
+#if RMT_RATES_DEP_C
+                    a += pj.dRdC[j][cc];
+#endif
+                    dR[j] = a;
+                }
+            } else if (isP) {
+                dlnw = -invP;
+#pragma unroll
+                for (int j = 0; j < RMT_NR; ++j) dR[j] = pj.dRdP[j];
+            } else {
+                dlnw = 0.0;
+#pragma unroll
+                for (int j = 0; j < RMT_NR; ++j) dR[j] = pj.dRdT[j];
+            }
+            const double dus = us*dlnw;
+            J(RMT_IP, col, -1*(h.ergA*dus + h.ergC*(dgade*(us*us) + 2.0*gade*us*dus)));
+#pragma unroll
+            for (int i = 0; i < RMT_NC; ++i) {
+                double dr = 0.0;
+#pragma unroll
+                for (int j = 0; j < RMT_NR; ++j) if (RMT_NU[j][i] != 0.0) dr += RMT_NU[j][i]*dR[j];
+                J(i, col, dr*c1 - f[i]*dlnw);
+            }
+            double dq = 0.0;
+#pragma unroll
+            for (int j = 0; j < RMT_NR; ++j) dq += dR[j]*p.dH[j];
+            double dCp = 0.0, dQm = 0.0;
+            if (isC) dCp = (p.cpm[cc] - p.Cp)*invS;
+            else if (!isP) {
+                dCp = pj.dCpdT;
+#pragma unroll
+                for (int j = 0; j < RMT_NR; ++j) dq += p.R[j]*pj.ddHdT[j];
+                dQm = -h.Ua;
+            }
+            J(RMT_IT, col, (-dq + dQm)*invDn - f[RMT_IT]*(dlnS + dlnw + dCp*invCp));
+        }
+    }
+}
+#else
 // ---------------------------------------------------------------------------------
 // N1 right-hand side (modelEquationN1, pbHomoReactor.py:3017-3314) and its analytic
 // Jacobian.  `JS` receives J(i, j, value) = d f_i / d yhat_j.
 // ---------------------------------------------------------------------------------
-struct NoJac { __device__ __forceinline__ void operator()(int, int, double) const {} };
 
 template <bool JAC, class JS>
 __device__ __forceinline__ void n1_eval(const double (&yh)[RMT_N], const Hot& h, double (&f)[RMT_N], JS&& J)
@@ -608,6 +724,8 @@ __device__ __forceinline__ void n1_eval(const double (&yh)[RMT_N], const Hot& h,
     }
 }
 
+#endif  // N1 vs M7 right-hand side
+
 // stand-alone batched RHS: y [N][B] -> f [N][B]   (parity + "RHS evals/s" kernel)
 extern "C" __global__ void __launch_bounds__(128)
 rmt_n1_rhs(const double* __restrict__ consts, const i64 B, const double* __restrict__ y, double* __restrict__ f)
@@ -704,10 +822,16 @@ __device__ __forceinline__ void n1_write_point(const SolveArgs& a, const Hot& h,
         o += (i64)RMT_N*a.B;
     }
     if (a.out_mode != 0) {
-        // sortResult4 (solResultAnalysis.py:191-249) + mole fractions (pbHomoReactor.py:2973-2983)
+        // sortResult4 (solResultAnalysis.py:191-249) + mole fractions (pbHomoReactor.py:2973-2983);
+        // M7: mole fractions from the dimensional concentrations (pbReactor.py:1301-1312)
         double S = 0.0, C[RMT_NC];
+#if defined(RMT_MODEL_M7)
+#pragma unroll
+        for (int k = 0; k < RMT_NC; ++k) { C[k] = v[k]; S += C[k]; }
+#else
 #pragma unroll
         for (int k = 0; k < RMT_NC; ++k) { C[k] = v[k]*h.Cmax; S += C[k]; }
+#endif
         if (a.out_mode == 2) {
 #pragma unroll
             for (int k = 0; k < RMT_NC; ++k) o[(i64)k*a.B] = C[k];
@@ -715,9 +839,14 @@ __device__ __forceinline__ void n1_write_point(const SolveArgs& a, const Hot& h,
         }
 #pragma unroll
         for (int k = 0; k < RMT_NC; ++k) o[(i64)k*a.B] = C[k]/S;
+#if defined(RMT_MODEL_M7)
+        o[(i64)RMT_IT*a.B] = v[RMT_IT];
+        o[(i64)RMT_IP*a.B] = v[RMT_IP];
+#else
         o[(i64)RMT_IP*a.B] = v[RMT_IP]*h.Pf;
 #if !RMT_ISO
         o[(i64)RMT_IT*a.B] = v[RMT_IT]*h.Tf + h.Tf;
+#endif
 #endif
     }
 }
@@ -779,9 +908,13 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
                     rmt_load_hot(a.consts, a.B, inst, h);
 #pragma unroll
                     for (int k = 0; k < RMT_NC; ++k) y[k] = a.consts[(i64)(K_IV0 + k)*a.B + inst];
+#if defined(RMT_MODEL_M7)
+                    y[RMT_IT] = h.Tf; y[RMT_IP] = h.Pf;       // pbReactor.py:1244-1246
+#else
                     y[RMT_IP] = 1.0;                          // P/Pf, :2834
 #if !RMT_ISO
                     y[RMT_IT] = 0.0;                          // (T-Tf)/Tf, :2838
+#endif
 #endif
                     t = 0.0; nacc = 0; nrej = 0; nanrej = 0; next_e = 0; last_rejected = false; fresh = true;
                     hacc = 0.0; erracc = 1e-2;
@@ -1123,10 +1256,12 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
                 if (fin == 0) {
                     double S = 0.0, C[RMT_NC];
 #pragma unroll
-                    for (int k = 0; k < RMT_NC; ++k) { C[k] = y[k]*h.Cmax; S += C[k]; }
+                    for (int k = 0; k < RMT_NC; ++k) { C[k] = y[k]; S += C[k]; }      // the common scale cancels in C/S
 #pragma unroll
                     for (int k = 0; k < RMT_NC; ++k) { const double d = (C[k]/S - a.obj_ref[k])/a.obj_ref[k]; ob += d*d; }
-#if !RMT_ISO
+#if defined(RMT_MODEL_M7)
+                    { const double d = (y[RMT_IT] - a.obj_ref[RMT_IT])/a.obj_ref[RMT_IT]; ob += d*d; }
+#elif !RMT_ISO
                     { const double d = ((y[RMT_IT]*h.Tf + h.Tf) - a.obj_ref[RMT_IT])/a.obj_ref[RMT_IT]; ob += d*d; }
 #endif
                 } else ob = __longlong_as_double(0x7ff0000000000000LL);
@@ -1136,7 +1271,7 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
         }
     }
 }
-#endif  // RMT_MODEL_N1
+#endif  // RMT_STEADY
 
 #if defined(RMT_MODEL_N2)
 // ---------------------------------------------------------------------------------

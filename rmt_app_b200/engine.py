@@ -20,6 +20,7 @@ from .model import SCALAR_INPUTS, ModelSpec
 solverSetting = {
     "N1": {"zNo": 100},
     "N2": {"zNo": 20, "rNo": 5, "tNo": 5, "timesNo": 5},
+    "M9": {"zNo": 30},          # runM3 (model M7) takes its number of output points from here (pbReactor.py:1283)
 }
 
 # SciPy defaults the reference inherits by never passing tolerances
@@ -57,7 +58,7 @@ def default_block(spec, stages=6):
     One block per SM, as many warps as fit (<= 256 threads: the kernel needs ~250 registers per
     thread): the warps of a block run in lockstep (one barrier per step attempt) so that they share
     instruction-cache lines — measured 2x faster than two independent 128-thread blocks per SM."""
-    if spec.model != "N1":
+    if spec.model == "N2":
         return 64
     per_thread = 8*(spec.n*spec.n + stages*spec.n)
     fit = (227*1024 - 1024)//per_thread
@@ -107,7 +108,7 @@ def _fast_key(modelInput, block):
     for k, v in rr["RATES"].items():
         sig.append((k, _fn_sig(v)) if isinstance(v, types.FunctionType) else (k, type(v).__name__))
     return (modelInput["model"], tuple(modelInput["feed"]["components"]["shell"]),
-            modelInput["operating-conditions"]["process-type"], tuple(modelInput["reactions"].values()),
+            modelInput["operating-conditions"].get("process-type"), tuple(modelInput["reactions"].values()),
             tuple(sig), block, modelInput.get("solver-config", {}).get("method", "rodas4"))
 
 
@@ -157,7 +158,9 @@ def uniform_inputs(spec, modelInput):
         raise ValueError("feed.concentration has %d entries for %d components" % (conc.size, spec.nc))
     vals = [float(oc["temperature"]), float(oc["pressure"])] + [float(c) for c in conc]
     vals += [float(feed["volumetric-flowrate"]), float(rs["ReInDi"]), float(rs["ReLe"]), float(rs["PaDi"]),
-             float(rs["BeVoFr"]), float(eh["OvHeTrCo"]), float(eh["MeTe"])]
+             float(rs["BeVoFr"]), float(eh["OvHeTrCo"]), float(eh["MeTe"]),
+             float(feed.get("mixture-viscosity", 0.0) or 0.0),      # read by M7 only (pbReactor.py:1235)
+             float(eh.get("EfHeTrAr", 0.0) or 0.0)]                 # used by M7 only; N1/N2 overwrite it with 4/ReInDi
     # scalar VARS entries of THIS modelInput (the compiled model is shared by every input with the same structure)
     varis = modelInput["reaction-rates"]["VARS"]
     vals += [float(varis[name]) for name in spec.kin.param_names]

@@ -21,7 +21,7 @@ _TERM = re.compile(r"([0-9.]*)([a-zA-Z0-9.]+)")
 # per-instance primary inputs of the device setup kernel, in row order.
 # "concentration" expands to nc rows; kinetic parameter slots follow.
 SCALAR_INPUTS = ("temperature", "pressure", "volumetric-flowrate", "ReInDi", "ReLe", "PaDi", "BeVoFr",
-                 "OvHeTrCo", "MeTe")
+                 "OvHeTrCo", "MeTe", "mixture-viscosity", "EfHeTrAr")
 
 
 def parse_reaction(expr):
@@ -41,16 +41,17 @@ class ModelSpec:
     def __init__(self, modelInput):
         mi = modelInput
         self.model = mi["model"]
-        if self.model not in ("N1", "N2"):
+        if self.model not in ("N1", "N2", "M7"):
             raise NotImplementedError(
-                "rmt_app_b200 implements the pseudo-homogeneous packed-bed models N1 and N2 only "
+                "rmt_app_b200 implements the pseudo-homogeneous packed-bed models N1, N2 and M7 only "
                 "(got model=%r)" % (self.model,))
         self.compList = list(mi["feed"]["components"]["shell"])
         for c in self.compList:
             if c not in componentSymbolList:                          # rmt.py:55-57
                 raise Exception("Component database is not up to date!")
         self.nc = len(self.compList)
-        self.iso = mi["operating-conditions"]["process-type"] == "iso-thermal"   # modelSetting.py:21-23
+        # modelSetting.py:21-23; M7 (pbReactor.runM3) has no process-type switch: always with the energy balance
+        self.iso = self.model != "M7" and mi["operating-conditions"]["process-type"] == "iso-thermal"
         self.reactions = list(mi["reactions"].values())
         self.nr = len(self.reactions)
         self.components = [COMPONENTS[c] for c in self.compList]
@@ -90,7 +91,9 @@ class ModelSpec:
     # -- input row bookkeeping --------------------------------------------------
     @property
     def n(self):
-        """unknowns per axial point: N1 = nc + P (+ T); N2 = nc (+ T)."""
+        """unknowns per axial point: N1 = nc + P (+ T); M7 = nc + T + P; N2 = nc (+ T)."""
+        if self.model == "M7":
+            return self.nc + 2
         if self.model == "N1":
             return self.nc + (1 if self.iso else 2)
         return self.nc + (0 if self.iso else 1)

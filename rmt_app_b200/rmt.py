@@ -45,9 +45,12 @@ def rmtExe(modelInput):
             resModel = _runN1(modelInput)
         elif modelType == "N2":
             resModel = _runN2(modelInput)
+        elif modelType == "M7":
+            resModel = _runM7(modelInput)
         else:
             raise NotImplementedError(
-                "model %r: this build accelerates the pseudo-homogeneous packed-bed models N1/N2 only" % (modelType,))
+                "model %r: this build accelerates the pseudo-homogeneous packed-bed models N1, N2 and M7 only"
+                % (modelType,))
         return {"resModel": resModel, "comTime": (timer() - tic)*1000}
     except Exception as e:
         print(e)
@@ -103,6 +106,31 @@ def _runN1(modelInput):
         from .plotting import plotResultsSteadyState
         plotResultsSteadyState(dataPack)
     return dataPack
+
+
+def _runM7(modelInput):
+    """runM3 (PyREMOT/docs/pbReactor.py:1170-1368), model id "M7": the dimensional twin of N1.
+    Result: {"dataYs": (nc+1) x zNo [mole fractions..., T], "XYList", "dataList"} (:1301-1368); the
+    number of output points comes from solverSetting['M9']['zNo'] (:1283).  The reference always draws
+    a figure here; that only happens with solver-config.display-result == "True"."""
+    cm = engine.compile_model(modelInput)
+    spec = cm.spec
+    nc = spec.nc
+    times = np.linspace(0, modelInput['reactor']['ReLe'], solverSetting['M9']['zNo'])
+    res = engine.n1_solve_ensemble(cm, modelInput, None, 1, z_eval=times, out_mode=1)
+    if int(res.status[0]) != 0:
+        raise RuntimeError("ODE Error: integrator status %d (%s)" % (res.status[0], STATUS_TEXT.get(int(res.status[0]))))
+    rows = res.out[:, :, 0].T                         # y_i..., T, P
+    dataYs = np.ascontiguousarray(rows[:nc + 1])
+    labelList = list(spec.compList) + ["Temperature", "Pressure"]
+    XYList = [[times, item] for item in dataYs]       # library/plot.py:85-115
+    dataList = [{"x": XYList[i][0], "y": XYList[i][1], "leg": labelList[i]} for i in range(len(XYList))]
+    out = {"dataYs": dataYs, "XYList": XYList, "dataList": dataList, "dataPressure": rows[nc + 1].copy()}
+    if _display(modelInput):
+        from .plotting import plotResultsSteadyState
+        plotResultsSteadyState([{"dataXs": times, "dataYs": rows, "labelList": labelList[:nc] + ["Pressure", "Temperature"],
+                                 "indexList": [nc, nc + 1, nc], "modelId": "M7", "computation-time": 0.0}])
+    return out
 
 
 def _runN2(modelInput):
@@ -164,8 +192,8 @@ def rmtExeBatch(modelInput, sweep=None, B=None, *, rtol=None, atol=None, profile
     tensors (copied directly) or torch CUDA tensors (no host transfer at all)."""
     tic = timer()
     _check_components(modelInput)
-    if modelInput['model'] != "N1":
-        raise NotImplementedError("rmtExeBatch covers model N1; use rmtExeBatchN2 for the dynamic model")
+    if modelInput['model'] not in ("N1", "M7"):
+        raise NotImplementedError("rmtExeBatch covers the steady-state models N1 and M7; use rmtExeBatchN2 for N2")
     if B is None:
         if not sweep:
             raise ValueError("give B or a non-empty sweep")
@@ -173,7 +201,13 @@ def rmtExeBatch(modelInput, sweep=None, B=None, *, rtol=None, atol=None, profile
         B = int(first.shape[0]) if hasattr(first, "shape") else len(first)
     cm = engine.compile_model(modelInput)
     if z_eval is None:
-        z_eval = np.linspace(0, 1, solverSetting['N1']['zNo'] + 1) if profile else np.array([1.0])
+        if modelInput['model'] == "M7":       # dimensional axial coordinate; ReLe must be the same for the whole batch
+            L = float(modelInput['reactor']['ReLe'])
+            if sweep and "ReLe" in sweep:
+                raise ValueError("model M7 integrates over [0, ReLe]: ReLe cannot be swept")
+            z_eval = np.linspace(0, L, solverSetting['M9']['zNo']) if profile else np.array([L])
+        else:
+            z_eval = np.linspace(0, 1, solverSetting['N1']['zNo'] + 1) if profile else np.array([1.0])
     res = engine.n1_solve_ensemble(cm, modelInput, sweep, B, z_eval=z_eval, rtol=rtol, atol=atol, out_mode=1,
                                    dense=dense, max_steps=max_steps, objective_ref=objective_ref,
                                    keep_on_device=keep_on_device, workspace=workspace, want_stats=return_stats)
@@ -186,8 +220,10 @@ def rmtExeBatch(modelInput, sweep=None, B=None, *, rtol=None, atol=None, profile
         data = out[:, :, 0] if out.shape[2] == 1 else out
         success = res.status == 0
     return {"dataYs": data, "status": res.status, "success": success, "stats": res.stats, "dataXs": res.z_eval,
-            "objective": res.objective, "h2d_bytes": res.h2d_bytes, "d2h_bytes": res.d2h_bytes, "labelList": list(cm.spec.compList) + ["Pressure"] + (
-                [] if cm.spec.iso else ["Temperature"]), "comTime": (timer() - tic)*1000}
+            "objective": res.objective, "h2d_bytes": res.h2d_bytes, "d2h_bytes": res.d2h_bytes,
+            "labelList": list(cm.spec.compList) + (["Temperature", "Pressure"] if cm.spec.model == "M7" else
+                                                   ["Pressure"] + ([] if cm.spec.iso else ["Temperature"])),
+            "comTime": (timer() - tic)*1000}
 
 
 def rmtExeBatchN2(modelInput, sweep=None, B=None, *, zNo=None, tNo=None, rtol=None, atol=None,

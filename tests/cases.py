@@ -199,6 +199,38 @@ def methanol_testfile_input(model="N1", ivp="default"):
     return mi
 
 
+def methanol_m7_input(ivp="default"):
+    """`PyREMOT/tests/test_rmt_DME3.py:20-262` instance: model M7, the dimensional steady-state twin of N1
+    (pbReactor.py runM3 :1170-1575).  Needs `feed.mixture-viscosity` and uses `external-heat.EfHeTrAr` as given."""
+    P, T = 5*1e6, 523
+    bed_por, rea_D, rea_L, cat_d, cat_rho, cat_Cp, cat_por = 0.39, 0.0381, 1, 0.002, 1982, 960, 0.45
+    bulk_rho = cat_rho*(1 - bed_por)
+    y32 = feed_mole_fraction(1, 0.5, dtype=np.float32)
+    ct0 = np.round(np.array([(P/(R_CONST*T))*float(v)/1000 for v in y32]), 7)
+    InGaVe = 0.2/bed_por
+    rea_CSA = bed_por*(math.pi*(rea_D**2)/4)
+    VoFlRa = InGaVe*rea_CSA
+    kin = methanol_kinetics(bulk_rho)
+    varis = {"CaDe": cat_rho, "CaBeDe": bulk_rho, "CaPo": cat_por}
+    for k, v in kin["VARS"].items():
+        if k not in varis:
+            varis[k] = v
+    return {
+        "model": "M7",
+        "operating-conditions": {"pressure": P, "temperature": T, "period": 50},
+        "feed": {
+            "volumetric-flowrate": VoFlRa, "concentration": ct0*1000, "mixture-viscosity": 1e-5,
+            "components": {"shell": list(METHANOL_COMPONENTS), "tube": [], "medium": []},
+        },
+        "reactions": dict(METHANOL_REACTIONS),
+        "reaction-rates": {"VARS": varis, "RATES": kin["RATES"]},
+        "external-heat": {"OvHeTrCo": 50, "EfHeTrAr": 4/rea_D, "MeTe": 523},
+        "reactor": {"ReInDi": rea_D, "ReLe": rea_L, "PaDi": cat_d, "BeVoFr": bed_por, "CaBeDe": bulk_rho,
+                    "CaDe": cat_rho, "CaSpHeCa": cat_Cp/1000},
+        "solver-config": {"ivp": ivp},
+    }
+
+
 def ch4_input(model="N1", process_type="non-iso-thermal", ivp="default"):
     """Methane-coupling instance of `PyREMOT/tests/test_rmt_N2_CH4.py:23-250`
     (SURVEY.md App. B.5)."""

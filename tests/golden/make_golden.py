@@ -266,6 +266,49 @@ def part_n2sol(which):
     np.savez_compressed(os.path.join(HERE, fname), **out)
 
 
+def part_m7():
+    """Model M7 (pbReactor.runM3, the dimensional twin of N1): RHS known answers and solutions."""
+    PyREMOT, H, _ = load_reference()
+    import PyREMOT.docs.pbReactor as PB
+    PB.pltc.plots2DSub = staticmethod(lambda *a, **k: None)      # runM3 always plots (pbReactor.py:1350-1356)
+    rng = np.random.default_rng(13)
+    out = {}
+    orig = PB.solve_ivp
+
+    def run(inject):
+        calls = []
+
+        def patched(fun, t_span, y0, **kw):
+            kw = dict(kw); kw.update(inject)
+            sol = orig(fun, t_span, y0, **kw)
+            calls.append(dict(fun=fun, y0=np.array(y0, float), args=kw.get("args"), nfev=sol.nfev, y=sol.y, t=sol.t))
+            return sol
+        PB.solve_ivp = patched
+        try:
+            res, wall = run_ref(PyREMOT, cases.methanol_m7_input())
+        finally:
+            PB.solve_ivp = orig
+        return res, calls[0], wall
+    res, c, wall = run({})
+    out["default__dataYs"] = np.array(res["resModel"]["dataYs"])
+    out["default__soly"] = c["y"]; out["default__t"] = c["t"]
+    out["default__nfev_wall"] = np.array([c["nfev"], wall])
+    res_t, ct, wall_t = run(dict(rtol=1e-10, atol=1e-12, method="LSODA"))
+    out["tight__dataYs"] = np.array(res_t["resModel"]["dataYs"])
+    out["tight__soly"] = ct["y"]
+    out["tight__nfev_wall"] = np.array([ct["nfev"], wall_t])
+    fun, args, traj = c["fun"], c["args"], c["y"]
+    Y = [c["y0"]] + [traj[:, i] for i in (1, 2, 3, 5, 10, 20, 29)]
+    for i in (0, 1, 3, 10, 29):
+        for _ in range(3):
+            Y.append(traj[:, i]*(1 + 0.05*rng.uniform(-1, 1, traj.shape[0])))
+    Y = np.array(Y)
+    out["rhs_Y"] = Y
+    out["rhs_F"] = np.array([fun(0.0, y, *args) for y in Y])
+    np.savez_compressed(os.path.join(HERE, "m7_reference.npz"), **out)
+    print("m7 done: default nfev %d wall %.2f, tight nfev %d" % (c["nfev"], wall, ct["nfev"]))
+
+
 def part_props():
     """Component-table known answers: Cp_i(T), viscosity_i(T), dHf25, MW for all 12 species,
     Wilke mixture viscosity and reaction parsing, straight from the reference's helpers."""
@@ -299,6 +342,8 @@ if __name__ == "__main__":
             part_n1()
         elif part == "corners":
             part_corners()
+        elif part == "m7":
+            part_m7()
         elif part == "props":
             part_props()
         elif part == "n2rhs":

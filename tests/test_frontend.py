@@ -18,8 +18,9 @@ def test_uniform_inputs_follow_header_order():
     spec = ModelSpec(mi)
     u = engine.uniform_inputs(spec, mi)
     assert spec.input_names() == ["temperature", "pressure"] + ["concentration[%d]" % i for i in range(6)] + [
-        "volumetric-flowrate", "ReInDi", "ReLe", "PaDi", "BeVoFr", "OvHeTrCo", "MeTe", "VARS:CaBeDe"]
-    assert u.size == spec.nin == 16
+        "volumetric-flowrate", "ReInDi", "ReLe", "PaDi", "BeVoFr", "OvHeTrCo", "MeTe", "mixture-viscosity", "EfHeTrAr",
+        "VARS:CaBeDe"]
+    assert u.size == spec.nin == 18
     assert u[0] == 523 and u[1] == 5e6 and u[-1] == pytest.approx(1982*0.61)
     np.testing.assert_array_equal(u[2:8], mi["feed"]["concentration"])
     assert u[13] == 100 and u[14] == 522
@@ -39,6 +40,7 @@ def test_sweep_rows_mapping_and_errors():
           "E1": -np.ones(B), "MeTe": np.full(B, 500.0)}
     rows, row_map = engine.sweep_rows(spec, sw, B)
     assert rows.shape == (9, B)
+    assert spec.nin == 2 + 6 + 9 + 13
     assert row_map[1] == 0 and list(row_map[2:8]) == [1, 2, 3, 4, 5, 6]
     names = spec.input_names()
     assert row_map[names.index("VARS:E1")] == 7 and row_map[names.index("MeTe")] == 8
@@ -70,6 +72,16 @@ def test_model_key_depends_on_structure_only():
     mi["reaction-rates"] = cases.methanol_kinetics_param(1171.2)
     d = ModelSpec(mi).key()
     assert a == b and a != c and a != d
+
+
+def test_m7_inputs():
+    mi = cases.methanol_m7_input()
+    spec = ModelSpec(mi)
+    assert spec.model == "M7" and spec.n == 8 and not spec.iso
+    u = engine.uniform_inputs(spec, mi)
+    names = spec.input_names()
+    assert u[names.index("mixture-viscosity")] == 1e-5 and u[names.index("EfHeTrAr")] == pytest.approx(4/0.0381)
+    assert spec.kin.param_names == ["CaDe", "CaBeDe", "CaPo"]
 
 
 def test_n_unknowns():

@@ -45,3 +45,54 @@ def test_rmtexebatch_n2_matches_single_runs():
             np.testing.assert_allclose(r["dataYs"][j, i], packs[i]["dataYs"], rtol=1e-12)
     finally:
         solverSetting["N2"].update(old)
+
+
+def test_m7_dimensional_twin_parity():
+    """Model M7 (pbReactor.runM3): RHS against the reference's modelEquationM3, Jacobian against differences,
+    solution against the reference at tight tolerance (1e-6) and at default tolerance (its own scatter)."""
+    import os
+    import pyremot_oracle as O
+    from conftest import GOLDEN
+    from rmt_app_b200 import engine, rmtExe, rmtExeBatch
+    g = np.load(os.path.join(GOLDEN, "m7_reference.npz"))
+    mi = cases.methanol_m7_input()
+    cm = engine.compile_model(mi)
+    assert cm.spec.n == 8 and cm.spec.model == "M7"
+    Y, F = g["rhs_Y"], g["rhs_F"]
+    Fg, J, _ = engine.n1_rhs_batch(cm, mi, Y, jac=True)
+    o = O.M7Oracle(mi)
+    rng = np.random.default_rng(3)
+    for y, f, fg in zip(Y, F, Fg):
+        dev = 0.0
+        for _ in range(6):
+            dev = max(dev, np.max(np.abs(np.array(o.rhs(0, y*(1 + 2.2e-16*rng.choice([-1, 0, 1], size=8)))) - f)))
+        assert np.max(np.abs(fg - f)) <= 1e-13*np.max(np.abs(f)) + 50*dev
+    for y, Jg in zip(Y[[0, 8, 12]], J[[0, 8, 12]]):
+        Jfd = np.zeros((8, 8))
+        for j in range(8):
+            h = 1e-6*max(abs(y[j]), 1e-3)
+            yp, ym = y.copy(), y.copy()
+            yp[j] += h; ym[j] -= h
+            Jfd[:, j] = (np.array(o.rhs(0, yp)) - np.array(o.rhs(0, ym)))/(2*h)
+        rowscale = np.max(np.abs(Jfd), axis=1, keepdims=True)
+        assert np.max(np.abs(Jg - Jfd)/rowscale) < 5e-6
+    tight = dict(mi); tight["solver-config"] = dict(mi["solver-config"], rtol=1e-9, atol=1e-12)
+    res = rmtExe(tight)["resModel"]
+    assert res["dataYs"].shape == g["tight__dataYs"].shape == (7, 30)
+    assert np.max(np.abs(res["dataYs"] - g["tight__dataYs"])/np.abs(g["tight__dataYs"])) < 1e-6
+    assert len(res["XYList"]) == 7 and res["dataList"][-1]["leg"] == "Temperature"
+    np.testing.assert_allclose(res["dataPressure"], g["tight__soly"][7], rtol=1e-8)
+    dflt = rmtExe(mi)["resModel"]["dataYs"][:, -1]
+    conv = g["tight__dataYs"][:, -1]
+    theirs = np.max(np.abs(g["default__dataYs"][:, -1] - conv)/np.abs(conv))
+    assert np.max(np.abs(dflt - conv)/np.abs(conv)) < max(3*theirs, 2e-3)
+    # ensemble form
+    B = 300
+    sw = cases.config3_sweep(B, seed=6)
+    r = rmtExeBatch(mi, sw, rtol=1e-8, atol=1e-11)
+    assert r["success"].all() and r["labelList"][-2:] == ["Temperature", "Pressure"]
+    i = 123
+    want = O.rmtExe(cases.instance_input(mi, sw, i), method="LSODA", rtol=1e-10, atol=1e-12)["resModel"]["solY"][:, -1]
+    got = r["dataYs"][i]
+    np.testing.assert_allclose(got[6:], want[6:], rtol=1e-6)
+    np.testing.assert_allclose(got[:6], want[:6]/want[:6].sum(), rtol=1e-6)

@@ -1256,7 +1256,11 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
                 if (fin == 0) {
                     double S = 0.0, C[RMT_NC];
 #pragma unroll
-                    for (int k = 0; k < RMT_NC; ++k) { C[k] = y[k]; S += C[k]; }      // the common scale cancels in C/S
+#if defined(RMT_MODEL_M7)
+                    for (int k = 0; k < RMT_NC; ++k) { C[k] = y[k]; S += C[k]; }
+#else
+                    for (int k = 0; k < RMT_NC; ++k) { C[k] = y[k]*h.Cmax; S += C[k]; }     // same arithmetic as the output rows
+#endif
 #pragma unroll
                     for (int k = 0; k < RMT_NC; ++k) { const double d = (C[k]/S - a.obj_ref[k])/a.obj_ref[k]; ob += d*d; }
 #if defined(RMT_MODEL_M7)

@@ -301,10 +301,12 @@ def generate_model_header(spec, tableau="rodas4"):
     A("__device__ constexpr double RMT_ROS_M[RMT_ROS_S] = %s;" % _arr(tab["m"]))
     A("__device__ constexpr double RMT_ROS_E[RMT_ROS_S] = %s;" % _arr(tab["e"]))
     dense = tab["dense"] if tab.get("dense") else [[0.0]*s, [0.0]*s]
-    newf = [1 if (i == 0 or any(v != 0.0 for v in tab["a"][i])) else 0 for i in range(s)]
+    from .tableau import new_function_flags
+    newf = new_function_flags(tab)
     A("#define RMT_ROS_DENSE %d" % (1 if tab.get("dense") else 0))
     A("__device__ constexpr double RMT_ROS_D[2][RMT_ROS_S] = %s;" % _arr2(dense))
-    A("// stage i evaluates f at a new argument (0: its argument is y_n again, f(y_n) is re-used)")
+    A("// stage i evaluates f at a new argument (0: same argument as the previous stage, whose f is re-used)")
+    A("#define RMT_ROS_REUSE %d" % (0 if all(newf) else 1))
     A("__device__ constexpr int RMT_ROS_NEWF[RMT_ROS_S] = %s;" % _arr(newf, fmt=lambda v: str(int(v))))
     A("__constant__ int RMT_cROS_NEWF[RMT_ROS_S] = %s;" % _arr(newf, fmt=lambda v: str(int(v))))
     A("__constant__ double RMT_cROS_A[RMT_ROS_S][RMT_ROS_S] = %s;" % _arr2(full(tab["a"])))

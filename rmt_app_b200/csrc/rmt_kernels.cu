@@ -1009,6 +1009,13 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
         }
 
         // stages
+#if RMT_ROS_REUSE
+        double flast[RMT_N];                   // latest evaluated f (a re-using stage takes the previous stage's)
+#pragma unroll
+        for (int i = 0; i < RMT_N; ++i) flast[i] = f0[i];
+#else
+        const double (&flast)[RMT_N] = f0;
+#endif
         double ynew[RMT_N], errv[RMT_N];
 #pragma unroll
         for (int i = 0; i < RMT_N; ++i) { ynew[i] = y[i]; errv[i] = 0.0; }
@@ -1028,9 +1035,10 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
 #else
             if (s == 0 || !RMT_ROS_NEWF[s]) {
 #endif
-                // first stage, or a stage whose argument is y_n again: f(y_n) from the Jacobian evaluation
+                // first stage, or a stage with the same argument as the previous one: re-use its function value
+                // (flast == f(y_n) until a later stage has evaluated a new one)
 #pragma unroll
-                for (int i = 0; i < RMT_N; ++i) rhs[i] = f0[i];
+                for (int i = 0; i < RMT_N; ++i) rhs[i] = flast[i];
 #if RMT_ROLL
                 for (int j = 0; j < s; ++j) {
                     const double cj = RMT_cROS_C[s][j]*invh;
@@ -1081,6 +1089,10 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
                     }
 #endif
                 n1_eval<false>(u, h, rhs, NoJac());
+#if RMT_ROS_REUSE
+#pragma unroll
+                for (int i = 0; i < RMT_N; ++i) flast[i] = rhs[i];
+#endif
 #if RMT_ROLL
 #if RMT_MERGE_KLOADS
 #pragma unroll

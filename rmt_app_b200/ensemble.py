@@ -95,7 +95,8 @@ def rmtExeBatchSharded(modelInput, sweep, B=None, *, rtol=None, atol=None, objec
         B = int(first.shape[0]) if hasattr(first, "shape") else len(first)
     rank, world = world_info(group)
     local, lo, hi = shard_sweep(sweep, B, world, rank)
-    cm = engine.compile_model(modelInput)
+    rt = modelInput.get('solver-config', {}).get('rtol', engine.DEFAULT_RTOL) if rtol is None else rtol
+    cm = engine.compile_model(modelInput, method=engine.choose_method(modelInput, rt, 1))
     res = engine.n1_solve_ensemble(cm, modelInput, local, hi - lo, rtol=rtol, atol=atol, out_mode=1,
                                    objective_ref=objective_ref, keep_on_device=True, workspace=workspace)
     out = {"range": (lo, hi), "local_dataYs": res.out[0], "local_status": res.status, "local_stats": res.stats}

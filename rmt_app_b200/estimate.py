@@ -29,7 +29,8 @@ def differential_evolution(modelInput, bounds, outlet_ref, popsize=4096, generat
     ws = workspace if workspace is not None else engine.Workspace()
     ref = np.asarray(outlet_ref, float)
     multi = world_info()[1] > 1
-    cm = engine.compile_model(modelInput)
+    rt = modelInput.get('solver-config', {}).get('rtol', engine.DEFAULT_RTOL) if rtol is None else rtol
+    cm = engine.compile_model(modelInput, method=engine.choose_method(modelInput, rt, 1))
 
     def score(P):
         sweep = {k: np.ascontiguousarray(P[:, j]) for j, k in enumerate(names)}

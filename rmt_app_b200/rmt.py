@@ -199,7 +199,6 @@ def rmtExeBatch(modelInput, sweep=None, B=None, *, rtol=None, atol=None, profile
             raise ValueError("give B or a non-empty sweep")
         first = next(iter(sweep.values()))
         B = int(first.shape[0]) if hasattr(first, "shape") else len(first)
-    cm = engine.compile_model(modelInput)
     if z_eval is None:
         if modelInput['model'] == "M7":       # dimensional axial coordinate; ReLe must be the same for the whole batch
             L = float(modelInput['reactor']['ReLe'])
@@ -208,6 +207,8 @@ def rmtExeBatch(modelInput, sweep=None, B=None, *, rtol=None, atol=None, profile
             z_eval = np.linspace(0, L, solverSetting['M9']['zNo']) if profile else np.array([L])
         else:
             z_eval = np.linspace(0, 1, solverSetting['N1']['zNo'] + 1) if profile else np.array([1.0])
+    rt = modelInput.get('solver-config', {}).get('rtol', engine.DEFAULT_RTOL) if rtol is None else rtol
+    cm = engine.compile_model(modelInput, method=engine.choose_method(modelInput, rt, len(z_eval), dense))
     res = engine.n1_solve_ensemble(cm, modelInput, sweep, B, z_eval=z_eval, rtol=rtol, atol=atol, out_mode=1,
                                    dense=dense, max_steps=max_steps, objective_ref=objective_ref,
                                    keep_on_device=keep_on_device, workspace=workspace, want_stats=return_stats)

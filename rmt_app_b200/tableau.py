@@ -70,7 +70,34 @@ RODAS3 = {
     "dense": None,
 }
 
-TABLEAUX = {"rodas4": RODAS4, "rodas3": RODAS3}
+# Ros4 (Hairer & Wanner IV.7, the "L-stable method of order 4"; KPP's Ros4): 4 stages, order 4(3), L-stable
+# but not stiffly accurate; stage 4 has the same argument as stage 3 and re-uses its function value:
+# 3 RHS evaluations (one with the Jacobian) per step.
+ROS4 = {
+    "name": "ros4",
+    "stages": 4,
+    "order": 4,
+    "gamma": 0.5728200000000000,
+    "a": [[], [2.0], [1.867943637803922, 0.2344449711399156], [1.867943637803922, 0.2344449711399156, 0.0]],
+    "c": [[], [-7.137615036412310], [2.580708087951457, 0.6515950076447975],
+          [-2.137148994382534, -0.3214669691237626, -0.6949742501781779]],
+    "m": [2.255570073418735, 0.2870493262186792, 0.4353179431840180, 1.093502252409163],
+    "e": [-0.2815431932141155, -0.07276199124938920, -0.1082196201495311, -1.093502252409163],
+    "dense": None,
+}
+
+TABLEAUX = {"rodas4": RODAS4, "rodas3": RODAS3, "ros4": ROS4}
+
+
+def new_function_flags(tab):
+    """flag[i] = stage i evaluates f at a new argument; 0 = its argument equals the previous stage's
+    (or y_n for the second stage), whose function value is re-used."""
+    flags = [1]
+    for i in range(1, tab["stages"]):
+        row = list(tab["a"][i]) + [0.0]*(tab["stages"] - len(tab["a"][i]))
+        prev = (list(tab["a"][i - 1]) + [0.0]*(tab["stages"] - len(tab["a"][i - 1]))) if i > 1 else [0.0]*tab["stages"]
+        flags.append(0 if row == prev else 1)
+    return flags
 
 
 def reference_step(tab, f, jac, y, h):

@@ -84,6 +84,19 @@ def test_m7_inputs():
     assert spec.kin.param_names == ["CaDe", "CaBeDe", "CaPo"]
 
 
+def test_automatic_method_choice():
+    mi = cases.methanol_readme_input("N1")
+    assert engine.choose_method(mi, 1e-3, 1) == "ros4"              # outlet only, loose tolerance
+    assert engine.choose_method(mi, 1e-3, 101) == "rodas4"          # profile: needs dense output
+    assert engine.choose_method(mi, 1e-3, 101, dense=False) == "ros4"
+    assert engine.choose_method(mi, 1e-6, 1) == "rodas4"            # tight tolerance
+    mi["solver-config"]["method"] = "rodas3"
+    assert engine.choose_method(mi, 1e-3, 1) == "rodas3"
+    mi["solver-config"]["method"] = "euler"
+    with pytest.raises(ValueError, match="solver-config.method"):
+        engine.choose_method(mi, 1e-3, 1)
+
+
 def test_n_unknowns():
     assert ModelSpec(cases.methanol_readme_input("N2")).n == 7
     assert ModelSpec(cases.ch4_input("N2", "iso-thermal")).n == 3

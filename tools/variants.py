@@ -8,6 +8,8 @@ from rmt_app_b200 import engine, capi
 
 B = int(os.environ.get("B", 1 << 20))
 base = cases.methanol_readme_input(); sw = cases.config3_sweep(B)
+base["solver-config"]["method"] = os.environ.get("METHOD", "rodas4")
+CTRL = [float(v) for v in os.environ["CTRL"].split(",")] if os.environ.get("CTRL") else None
 cm = engine.compile_model(base)
 capi.init(0)
 ws = engine.Workspace()
@@ -34,11 +36,11 @@ for v in variants:
     mod.setup(B, d_rows, n_rows, row_map, uniform, d_consts, stream=stream)
     z = np.array([1.0])
     for _ in range(2):
-        mod.n1_solve(B, d_consts, z, 1e-3, 1e-6, d_out, d_status, d_stats, stream=stream)
+        mod.n1_solve(B, d_consts, z, 1e-3, 1e-6, d_out, d_status, d_stats, ctrl=CTRL, stream=stream)
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(3):
-        mod.n1_solve(B, d_consts, z, 1e-3, 1e-6, d_out, d_status, d_stats, stream=stream)
+        mod.n1_solve(B, d_consts, z, 1e-3, 1e-6, d_out, d_status, d_stats, ctrl=CTRL, stream=stream)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)/3
     # stand-alone RHS / Jacobian kernels

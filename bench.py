@@ -192,21 +192,25 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------
-def solver_flops(info, stats, n):
+def solver_flops(info, stats, cm):
     """Algorithmic flops of one integrator launch from its per-instance counters.
-    Per attempt: 1 f+Jacobian, (s-1) RHS, one n x n LU, s triangular solves,
-    stage combinations and the error norm.  (alg: 1 flop per op; wt: FP64-
-    instruction weighted, rmt_app_b200/expr.py FLOP_WEIGHT.)"""
+    Per attempt: 1 evaluation of g and A = dg/dx, the other RHS evaluations, one m x m LU,
+    s triangular solves, stage combinations and the error norm; m = nr + 2 unknowns when the
+    integrator works in reaction extents, else n.  (alg: 1 flop per op; wt: FP64-instruction
+    weighted, rmt_app_b200/expr.py FLOP_WEIGHT.)"""
     att = float(stats[3].sum())
     nfev = float(stats[2].sum())
     s = info.stages
+    n = cm.m
     lu = (2.0*n**3)/3.0 + n*n            # factorisation incl. forming W
     tri = s*2.0*n*n
-    comb = 2.0*n*(s*(s - 1)) + 8.0*n      # a_ij / c_ij combinations, update, error norm (upper bound: all coefficients)
+    comb = 2.0*n*(s*(s - 1)) + 8.0*info.n  # a_ij / c_ij combinations, update, error norm (upper bound: all coefficients)
+    if cm.reduced:
+        comb += (s + 1)*2.0*float((cm.spec.nu != 0).sum())      # E x: stage arguments, y_new and the error vector
     lin_alg = att*(lu + tri + comb)
     lin_wt = lin_alg + att*9.0*n          # n reciprocal pivots
-    alg = nfev*info.flops_rhs_alg + att*info.flops_jac_alg + lin_alg
-    wt = nfev*info.flops_rhs_wt + att*info.flops_jac_wt + lin_wt
+    alg = nfev*info.flops_rhs_alg + att*cm.flops["sys_alg"] + lin_alg
+    wt = nfev*info.flops_rhs_wt + att*cm.flops["sys_weighted"] + lin_wt
     return alg, wt, att, nfev
 
 
@@ -304,7 +308,7 @@ def run_gpu_arm(args, rank, world, local_rank):
     status = d_status.cpu().numpy()
     stats = d_stats.cpu().numpy()
     n_ok = int((status == 0).sum())
-    alg, wt, att, nfev = solver_flops(info, stats, n)
+    alg, wt, att, nfev = solver_flops(info, stats, cm)
     if world > 1:
         t = torch.tensor([n_ok, att, nfev], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)

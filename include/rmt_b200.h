@@ -57,6 +57,8 @@ typedef struct rmt_module_info {
     int32_t iso;          /* 1 = iso-thermal                                   */
     int32_t flops_rhs_alg, flops_rhs_wt;     /* per RHS evaluation (per node)  */
     int32_t flops_jac_alg, flops_jac_wt;     /* per RHS+Jacobian evaluation    */
+    int32_t m;            /* unknowns of the integrator's linear systems: n, or */
+                          /* nr + (n - nc) when it works in reaction extents    */
 } rmt_module_info;
 
 const char* rmt_last_error(void);
@@ -98,6 +100,15 @@ int rmt_setup(rmt_module_t m, int64_t B, const double* d_rows, int32_t n_rows, c
  * d_y, d_f [n][B];  d_J [n*n][B] with d f_r / d y_c at row r*n + c. */
 int rmt_n1_rhs(rmt_module_t m, int64_t B, const double* d_consts, const double* d_y, double* d_f, void* stream);
 int rmt_n1_jac(rmt_module_t m, int64_t B, const double* d_consts, const double* d_y, double* d_f, double* d_J,
+               void* stream);
+
+/* The integrator's own form of the same equations (no reference counterpart; parity
+ * hook for the reduced Jacobian).  When nr < nc the species balances f_C = c(y) nu^T R
+ * are integrated in reaction extents: unknowns (xi_1..xi_nr, P, T), y_C = y_C(0) +
+ * nu^T xi.  d_g [m][B] = (c R_j, f_P, f_T), d_A [m*m][B] = dg/d(unknowns), so that
+ * E d_A == d_J E and E d_g == d_f with E = [[nu^T, 0], [0, I]].  m == n: d_g == d_f,
+ * d_A == d_J. */
+int rmt_n1_sys(rmt_module_t m, int64_t B, const double* d_consts, const double* d_y, double* d_g, double* d_A,
                void* stream);
 
 /* ---- N1: solve_ivp call of runN1 (:2931) + post-processing (:2949-2983) ---------

@@ -25,7 +25,7 @@ class RmtError(RuntimeError):
 class ModuleInfo(C.Structure):
     _fields_ = [(k, C.c_int32) for k in (
         "model", "n", "nc", "nr", "nin", "nconst", "nkp", "stages", "block", "iso",
-        "flops_rhs_alg", "flops_rhs_wt", "flops_jac_alg", "flops_jac_wt")]
+        "flops_rhs_alg", "flops_rhs_wt", "flops_jac_alg", "flops_jac_wt", "m")]
 
 
 _lib = None
@@ -51,6 +51,7 @@ SIGNATURES = {
     "rmt_setup": (C.c_int, [_u64, _i64, _vp, _i32, _pi32, _pdbl, _vp, _vp]),
     "rmt_n1_rhs": (C.c_int, [_u64, _i64, _vp, _vp, _vp, _vp]),
     "rmt_n1_jac": (C.c_int, [_u64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "rmt_n1_sys": (C.c_int, [_u64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "rmt_n1_solve": (C.c_int, [_u64, _i64, _vp, _i32, _pdbl, _dbl, _dbl, _i32, _i32, _i32, _vp, _vp, _vp, _pdbl,
                                _vp, _pdbl, _vp]),
     "rmt_n1_solve_host": (C.c_int, [_u64, _i64, _vp, _i32, _pi32, _pdbl, _i32, _pdbl, _dbl, _dbl, _i32, _i32, _i32,
@@ -196,6 +197,9 @@ class Module:
 
     def n1_jac(self, B, d_consts, d_y, d_f, d_J, stream=None):
         _check(lib().rmt_n1_jac(self.handle, B, _ptr(d_consts), _ptr(d_y), _ptr(d_f), _ptr(d_J), stream))
+
+    def n1_sys(self, B, d_consts, d_y, d_g, d_A, stream=None):
+        _check(lib().rmt_n1_sys(self.handle, B, _ptr(d_consts), _ptr(d_y), _ptr(d_g), _ptr(d_A), stream))
 
     def n1_solve(self, B, d_consts, z_eval, rtol, atol, d_out, d_status, d_stats, max_steps=100000, dense=True,
                  out_mode=1, obj_ref=None, d_obj=None, ctrl=None, stream=None):

@@ -151,14 +151,28 @@ def balance_flops(spec):
     percol_div = 2 + energy*3
     jma = mul_add + 2*nr*nc + 6*nc + 6*nr + n*percol_ma
     jdiv = div + 1 + n*percol_div
-    return {"rhs": rhs, "jac": (jma + jdiv, jma + 10*jdiv)}
+    out = {"rhs": rhs, "jac": (jma + jdiv, jma + 10*jdiv)}
+    if spec.model in ("N1", "M7"):
+        # system form in reaction extents (`n1_eval_sys`): nr directions nu_k (contractions over the non-zeros of
+        # nu_k) + P and T directions; rows = nr reaction rows, the Ergun row and the energy row
+        sma = mul_add + 2*nr*nc + 6*nc + 6*nr
+        for k in range(nr):
+            nzk = int((spec.nu[k] != 0).sum())
+            sma += 2*nzk + 8 + nr*(4*nzk + 4) + 10 + 3*nr + energy*(2*nr + 10)
+        sma += (spec.n - nc)*(10 + nr + 3*nr + energy*(4*nr + 10))
+        sdiv = div + 1 + (nr + spec.n - nc)*percol_div
+        out["sys"] = (sma + sdiv, sma + 10*sdiv)
+    return out
 
 
-def model_flops(spec):
-    """Per-axial-point flop counts: traced rates + balance."""
+def model_flops(spec, reduced=False):
+    """Per-axial-point flop counts: traced rates + balance.  sys_*: one evaluation of the
+    integrator's g and A = dg/dx (the full f and J unless it works in reaction extents)."""
     k = spec.kin.flops()
     b = balance_flops(spec)
+    sys_ = b["sys"] if (reduced and "sys" in b) else b["jac"]
     return {
+        "sys_alg": k["rates_jac_alg"] + sys_[0], "sys_weighted": k["rates_jac_weighted"] + sys_[1],
         "rates_alg": k["rates_alg"], "rates_weighted": k["rates_weighted"],
         "rates_jac_alg": k["rates_jac_alg"], "rates_jac_weighted": k["rates_jac_weighted"],
         "rhs_alg": k["rates_alg"] + b["rhs"][0], "rhs_weighted": k["rates_weighted"] + b["rhs"][1],
@@ -166,9 +180,28 @@ def model_flops(spec):
     }
 
 
-def generate_model_header(spec, tableau="rodas4"):
+def use_extents(spec):
+    """Integrate the steady-state models in reaction extents (nr + 2 unknowns instead of nc + 2)?  The
+    species balances of N1 (pbHomoReactor.py:3283-3289) and M7 (pbReactor.py:1545-1551) are c(y)*nu^T R(y),
+    so the Rosenbrock stage increments lie in the range of nu^T and the iterates are the same either way;
+    it pays when there are fewer reactions than species."""
+    return spec.model in ("N1", "M7") and spec.nr < spec.nc
+
+
+def system_size(spec, reduced=None):
+    """Dimension of the integrator's linear systems."""
+    if reduced is None:
+        reduced = use_extents(spec)
+    return spec.nr + (spec.n - spec.nc) if reduced else spec.n
+
+
+def generate_model_header(spec, tableau="rodas4", reduced=None):
     kin, g = spec.kin, spec.kin.g
     nc, nr, nkp = spec.nc, spec.nr, spec.nkp
+    if reduced is None:
+        reduced = use_extents(spec)
+    if reduced and spec.model not in ("N1", "M7"):
+        raise ValueError("reaction-extent form exists for the steady-state models only")
 
     def in_name(nm):
         if nm in ("T", "P"):
@@ -194,6 +227,10 @@ def generate_model_header(spec, tableau="rodas4"):
     A("#define RMT_NKP %d" % nkp)
     A("#define RMT_ISO %d" % (1 if spec.iso else 0))
     A("#define RMT_NIN %d" % spec.nin)
+    A("// integrator unknowns: 1 = reaction extents (nr + non-species unknowns), 0 = the full state")
+    A("#ifndef RMT_REDUCED")
+    A("#define RMT_REDUCED %d" % (1 if reduced else 0))
+    A("#endif")
     for k, nm in enumerate(kin.param_names):
         A("// kinetic parameter slot %d = VARS[%r] (default %r)" % (k, nm, kin.param_defaults[k]))
 

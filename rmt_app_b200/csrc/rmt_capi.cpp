@@ -109,7 +109,7 @@ struct Scratch {           // per-launch device scratch: queue counter + z_eval 
 struct Module {
     CUmodule mod = nullptr;
     rmt_module_info info{};
-    CUfunction f_setup = nullptr, f_n1_rhs = nullptr, f_n1_jac = nullptr, f_n1_solve = nullptr;
+    CUfunction f_setup = nullptr, f_n1_rhs = nullptr, f_n1_jac = nullptr, f_n1_sys = nullptr, f_n1_solve = nullptr;
     CUfunction f_n2_rhs = nullptr, f_n2_solve = nullptr, f_reduce = nullptr, f_peak = nullptr, f_probe = nullptr;
     int solve_blocks_per_sm = 0;
     size_t solve_smem = 0;
@@ -388,10 +388,12 @@ int rmt_module_load(const void* cubin, size_t size, rmt_module_t* module_out)
     I.model = mv[0]; I.n = mv[1]; I.nc = mv[2]; I.nr = mv[3]; I.nin = mv[4]; I.nconst = mv[5]; I.nkp = mv[6];
     I.stages = mv[7]; I.block = mv[8]; I.iso = mv[9];
     I.flops_rhs_alg = mv[10]; I.flops_rhs_wt = mv[11]; I.flops_jac_alg = mv[12]; I.flops_jac_wt = mv[13];
+    I.m = mv[14] > 0 ? mv[14] : mv[1];
     auto get = [&](const char* name) { CUfunction f = nullptr; drv.p_cuModuleGetFunction(&f, M->mod, name); return f; };
     M->f_setup = get("rmt_setup");
     M->f_n1_rhs = get("rmt_n1_rhs");
     M->f_n1_jac = get("rmt_n1_jac");
+    M->f_n1_sys = get("rmt_n1_sys");
     M->f_n1_solve = get("rmt_n1_solve");
     M->f_n2_rhs = get("rmt_n2_rhs");
     M->f_n2_solve = get("rmt_n2_solve");
@@ -401,7 +403,7 @@ int rmt_module_load(const void* cubin, size_t size, rmt_module_t* module_out)
     if (!M->f_setup) { drv.p_cuModuleUnload(M->mod); delete M; return fail("module lacks rmt_setup"); }
     CUfunction fs = I.model != 2 ? M->f_n1_solve : M->f_n2_solve;
     if (fs && I.model != 2) {
-        M->solve_smem = (size_t)I.block*8*((size_t)I.n*I.n + (size_t)I.stages*I.n);
+        M->solve_smem = (size_t)I.block*8*((size_t)I.m*I.m + (size_t)I.stages*I.m);
         CU(cuFuncSetAttribute(fs, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)M->solve_smem));
         CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&M->solve_blocks_per_sm, fs, I.block, M->solve_smem));
         if (M->solve_blocks_per_sm < 1) { drv.p_cuModuleUnload(M->mod); delete M; return fail("integrator kernel does not fit on an SM (smem %zu B)", M->solve_smem); }
@@ -480,6 +482,19 @@ int rmt_n1_jac(rmt_module_t m, int64_t B, const double* d_consts, const double* 
     long long b = B;
     void* params[] = {&c, &b, &y, &f, &J};
     return launch(M->f_n1_jac, (unsigned)((B + 127)/128), 128, 0, (CUstream)stream, params, "rmt_n1_jac");
+}
+
+int rmt_n1_sys(rmt_module_t m, int64_t B, const double* d_consts, const double* d_y, double* d_g, double* d_A,
+               void* stream)
+{
+    Module* M = get_module(m);
+    if (!M) return fail("invalid module handle");
+    if (!M->f_n1_sys) return fail("module has no steady-state integrator");
+    if (ensure_ctx()) return 1;
+    CUdeviceptr c = (CUdeviceptr)d_consts, y = (CUdeviceptr)d_y, g = (CUdeviceptr)d_g, A = (CUdeviceptr)d_A;
+    long long b = B;
+    void* params[] = {&c, &b, &y, &g, &A};
+    return launch(M->f_n1_sys, (unsigned)((B + 127)/128), 128, 0, (CUstream)stream, params, "rmt_n1_sys");
 }
 
 int rmt_n1_solve(rmt_module_t m, int64_t B, const double* d_consts, int32_t n_eval, const double* z_eval,

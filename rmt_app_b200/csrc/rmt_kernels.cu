@@ -202,6 +202,21 @@ __device__ __forceinline__ double rmt_sqrt(const double x)
 #endif
 #define RMT_NCONST_VALUE (29 + RMT_NC + RMT_NKP)
 
+// Linear-system dimension of the steady-state integrator.  The species balances of N1 and M7 are
+// f_C = c(y) * nu^T R(y): every stage increment of a Rosenbrock method therefore lies in the range of
+// E = [[nu^T, 0], [0, I]] and K_i = E k_i with (I/(h*gamma) - G E) k_i = g(Y_i) + sum_j (c_ij/h) k_j, where
+// g = (c R_1..c R_nr, f_P, f_T) and G = dg/dy.  Solving for the k_i (dimension nr + 2) instead of the K_i
+// (dimension nc + 2) gives the same iterates — error norm, guards and outputs are evaluated on the expanded
+// state — with a smaller Jacobian, LU and triangular solves.  Used when nr < nc.
+#ifndef RMT_REDUCED
+#define RMT_REDUCED 0
+#endif
+#if defined(RMT_STEADY) && RMT_REDUCED
+#define RMT_M (RMT_NR + RMT_N - RMT_NC)
+#elif defined(RMT_STEADY)
+#define RMT_M RMT_N
+#endif
+
 #ifndef RMT_BLOCK
 #define RMT_BLOCK 256
 #endif
@@ -251,7 +266,12 @@ extern "C" __global__ void rmt_meta(int* out)
     out[1] = RMT_N; out[2] = RMT_NC; out[3] = RMT_NR; out[4] = RMT_NIN; out[5] = RMT_NCONST_VALUE;
     out[6] = RMT_NKP; out[7] = RMT_ROS_S; out[8] = RMT_BLOCK; out[9] = RMT_ISO;
     out[10] = RMT_FLOPS_RHS_ALG; out[11] = RMT_FLOPS_RHS_WT; out[12] = RMT_FLOPS_JAC_ALG; out[13] = RMT_FLOPS_JAC_WT;
-    out[14] = 0; out[15] = 0;
+#if defined(RMT_STEADY)
+    out[14] = RMT_M;
+#else
+    out[14] = 0;
+#endif
+    out[15] = 0;
 }
 
 // ---------------------------------------------------------------------------------
@@ -726,6 +746,200 @@ __device__ __forceinline__ void n1_eval(const double (&yh)[RMT_N], const Hot& h,
 
 #endif  // N1 vs M7 right-hand side
 
+// ---------------------------------------------------------------------------------
+// System form seen by the integrator: g (dimension RMT_M) and A = dg/dx for its unknowns x.
+// Full form: x = y, g = f, A = J.  Reduced form (RMT_REDUCED): x = (xi_1..xi_nr, non-species unknowns) with
+// y_C = y_C(0) + nu^T xi, g = (c R_j, f_P, f_T), A = G E — derivatives along the reaction directions.
+// ---------------------------------------------------------------------------------
+#define RMT_NX (RMT_N - RMT_NC)               // non-species unknowns (P, T)
+
+// d = E x: increments of the integrator's unknowns -> increments of the full state
+__device__ __forceinline__ void rmt_expand(const double (&x)[RMT_M], double (&d)[RMT_N])
+{
+#if RMT_REDUCED
+#pragma unroll
+    for (int i = 0; i < RMT_NC; ++i) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < RMT_NR; ++j) if (RMT_NU[j][i] != 0.0) acc += RMT_NU[j][i]*x[j];
+        d[i] = acc;
+    }
+#pragma unroll
+    for (int q = 0; q < RMT_NX; ++q) d[RMT_NC + q] = x[RMT_NR + q];
+#else
+#pragma unroll
+    for (int i = 0; i < RMT_N; ++i) d[i] = x[i];
+#endif
+}
+
+#if !RMT_REDUCED
+template <bool JAC, class JS>
+__device__ __forceinline__ void n1_eval_sys(const double (&y)[RMT_N], const Hot& h, double (&g)[RMT_M], JS&& A)
+{
+    n1_eval<JAC>(y, h, g, A);
+}
+#else
+#define RMT_RP (RMT_NR + RMT_IP - RMT_NC)     // position of P / T among the reduced unknowns
+#define RMT_RT (RMT_NR + RMT_IT - RMT_NC)
+
+// compile-time sums over the stoichiometry of reaction k: net mole change and net molar mass [kg/mol]
+__device__ constexpr double rmt_nu_sum(const int k)
+{
+    double a = 0.0;
+    for (int i = 0; i < RMT_NC; ++i) a += RMT_NU[k][i];
+    return a;
+}
+__device__ constexpr double rmt_nu_mw(const int k)
+{
+    double a = 0.0;
+    for (int i = 0; i < RMT_NC; ++i) a += RMT_NU[k][i]*(1e-3*RMT_MW[i]);
+    return a;
+}
+
+template <bool JAC, class JS>
+__device__ __forceinline__ void n1_eval_sys(const double (&yv)[RMT_N], const Hot& h, double (&g)[RMT_M], JS&& A)
+{
+    double C[RMT_NC];
+#if defined(RMT_MODEL_M7)
+#pragma unroll
+    for (int i = 0; i < RMT_NC; ++i) C[i] = yv[i];
+    const double T = yv[RMT_IT], P = yv[RMT_IP];
+    const double sC = 1.0, sP = 1.0, sT = 1.0;               // column scales d(C,P,T)/d(unknown)
+#else
+#pragma unroll
+    for (int i = 0; i < RMT_NC; ++i) C[i] = yv[i]*h.Cmax;
+    const double P = yv[RMT_IP]*h.Pf;
+#if RMT_ISO
+    const double T = 0.0*h.Tf + h.Tf;
+#else
+    const double T = yv[RMT_IT]*h.Tf + h.Tf;
+#endif
+    const double sC = h.Cmax, sP = h.Pf, sT = h.Tf;
+#endif
+    Point p; PointJac pj;
+    rmt_point<JAC>(C, T, P, h, p, pj);
+    const double invP = rmt_rcp(P);
+    const double w = (p.S*h.invC0)*(h.Pf*invP);
+    const double us = h.us0*w;
+#if defined(RMT_MODEL_M7)
+    const double gade = p.MWm*p.S;
+    g[RMT_RP] = -1*(h.ergA*us + h.ergC*gade*(us*us));
+    const double cR = rmt_rcp(us);                            // species balances: f_i = r_i/us
+    const double Qm = h.Ua*(h.Tm - T);
+    const double invDn = rmt_rcp((p.S*us)*p.Cp);
+    g[RMT_RT] = (-p.q + Qm)*invDn;
+#else
+    const double rhoh = p.rho*h.invRho0;
+    g[RMT_RP] = -1*(h.ergA*us + h.ergC*p.rho*(us*us))*h.invBeta;
+    const double cR = rmt_rcp(w)*h.invGm;                     // species balances: f_i = r_i/(w*Gm)
+#if !RMT_ISO
+    const double cpeffh = p.Cp*h.epsCpf;
+    const double invDn = rmt_rcp(rhoh*cpeffh*w);
+    g[RMT_RT] = ((-p.q + p.Qm)*h.invGh)*invDn;
+#endif
+#endif
+#pragma unroll
+    for (int j = 0; j < RMT_NR; ++j) g[j] = p.R[j]*cR;
+    if (JAC) {
+        const double invS = p.invS;
+#if !defined(RMT_MODEL_M7)
+        const double invT = rmt_rcp(T), invMW = rmt_rcp(p.MWm);
+#endif
+#if !RMT_ISO
+        const double invCp = rmt_rcp(p.Cp);
+#endif
+        double sy[RMT_NR];
+#pragma unroll
+        for (int j = 0; j < RMT_NR; ++j) {
+            double a = 0.0;
+#if RMT_RATES_DEP_Y
+#pragma unroll
+            for (int i = 0; i < RMT_NC; ++i) a += pj.dRdy[j][i]*p.y[i];
+#endif
+            sy[j] = a;
+        }
+#pragma unroll
+        for (int d = 0; d < RMT_M; ++d) {
+            const bool isX = d < RMT_NR, isP = d == RMT_RP;
+            const int k = d < RMT_NR ? d : 0;
+            // derivatives along direction d: d ln w, d ln rho (N1) or d(MW*C) and d ln S (M7), dR_j, dCp
+            double dlnw, dlnrho = 0.0, dgade = 0.0, dlnS = 0.0, dCp = 0.0, dR[RMT_NR];
+            if (isX) {
+                const double sn = rmt_nu_sum(k);
+                dlnw = (sC*sn)*invS;
+                dlnS = dlnw;
+                dgade = sC*rmt_nu_mw(k);
+#if !defined(RMT_MODEL_M7)
+                dlnrho = sC*(rmt_nu_mw(k) - p.MWm*sn)*invS*invMW;
+#endif
+                double scp = 0.0;
+#pragma unroll
+                for (int i = 0; i < RMT_NC; ++i) if (RMT_NU[k][i] != 0.0) scp += RMT_NU[k][i]*p.cpm[i];
+                dCp = sC*(scp - p.Cp*sn)*invS;
+#pragma unroll
+                for (int j = 0; j < RMT_NR; ++j) {
+                    double a = 0.0;
+#if RMT_RATES_DEP_Y
+                    double ty = 0.0;
+#pragma unroll
+                    for (int i = 0; i < RMT_NC; ++i) if (RMT_NU[k][i] != 0.0) ty += RMT_NU[k][i]*pj.dRdy[j][i];
+                    a = (ty - sy[j]*sn)*invS;
+#endif
+#if RMT_RATES_DEP_C
+#pragma unroll
+                    for (int i = 0; i < RMT_NC; ++i) if (RMT_NU[k][i] != 0.0) a += RMT_NU[k][i]*pj.dRdC[j][i];
+#endif
+                    dR[j] = sC*a;
+                }
+            } else if (isP) {
+                dlnw = -sP*invP;
+#if !defined(RMT_MODEL_M7)
+                dlnrho = sP*invP;
+#endif
+#pragma unroll
+                for (int j = 0; j < RMT_NR; ++j) dR[j] = sP*pj.dRdP[j];
+            } else {
+                dlnw = 0.0;
+#if !defined(RMT_MODEL_M7)
+                dlnrho = -sT*invT;
+#endif
+#pragma unroll
+                for (int j = 0; j < RMT_NR; ++j) dR[j] = sT*pj.dRdT[j];
+            }
+            const double dus = us*dlnw;
+#if defined(RMT_MODEL_M7)
+            A(RMT_RP, d, -1*(h.ergA*dus + h.ergC*(dgade*(us*us) + 2.0*gade*us*dus)));
+#else
+            A(RMT_RP, d, -1*(h.ergA*dus + h.ergC*(p.rho*dlnrho*(us*us) + 2.0*p.rho*us*dus))*h.invBeta);
+#endif
+#pragma unroll
+            for (int j = 0; j < RMT_NR; ++j) A(j, d, dR[j]*cR - g[j]*dlnw);
+#if !RMT_ISO
+            double dq = 0.0, dQm = 0.0;
+#pragma unroll
+            for (int j = 0; j < RMT_NR; ++j) dq += dR[j]*p.dH[j];
+            if (!isX && !isP) {
+                dCp = sT*pj.dCpdT;
+#pragma unroll
+                for (int j = 0; j < RMT_NR; ++j) dq += p.R[j]*(sT*pj.ddHdT[j]);
+#if defined(RMT_MODEL_M7)
+                dQm = -h.Ua;
+#else
+                dQm = (h.Tm == 0.0) ? 0.0 : -h.Ua*sT;
+#endif
+            }
+#if defined(RMT_MODEL_M7)
+            A(RMT_RT, d, (-dq + dQm)*invDn - g[RMT_RT]*(dlnS + dlnw + dCp*invCp));
+#else
+            A(RMT_RT, d, ((-dq + dQm)*h.invGh)*invDn - g[RMT_RT]*(dlnrho + dCp*invCp + dlnw));
+#endif
+#endif
+            (void)dgade; (void)dlnS; (void)dlnrho;
+        }
+    }
+}
+#endif  // system form
+
 // stand-alone batched RHS: y [N][B] -> f [N][B]   (parity + "RHS evals/s" kernel)
 extern "C" __global__ void __launch_bounds__(128)
 rmt_n1_rhs(const double* __restrict__ consts, const i64 B, const double* __restrict__ y, double* __restrict__ f)
@@ -763,6 +977,29 @@ rmt_n1_jac(const double* __restrict__ consts, const i64 B, const double* __restr
     for (int k = 0; k < RMT_N; ++k) f[(i64)k*B + i] = fo[k];
 }
 
+struct GlobalSys {
+    double* A; i64 B, i;
+    __device__ __forceinline__ void operator()(int r, int c, double v) const { A[(i64)(r*RMT_M + c)*B + i] = v; }
+};
+
+// the integrator's system form at given states: y [N][B] -> g [M][B], A [M*M][B] (parity of the
+// reduced-coordinate Jacobian: E A == J E and E g == f)
+extern "C" __global__ void __launch_bounds__(128)
+rmt_n1_sys(const double* __restrict__ consts, const i64 B, const double* __restrict__ y,
+           double* __restrict__ g, double* __restrict__ A)
+{
+    const i64 i = (i64)blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    Hot h; rmt_load_hot(consts, B, i, h);
+    double yh[RMT_N], go[RMT_M];
+#pragma unroll
+    for (int k = 0; k < RMT_N; ++k) yh[k] = y[(i64)k*B + i];
+    GlobalSys gs{A, B, i};
+    n1_eval_sys<true>(yh, h, go, gs);
+#pragma unroll
+    for (int k = 0; k < RMT_M; ++k) g[(i64)k*B + i] = go[k];
+}
+
 // ---------------------------------------------------------------------------------
 // N1 integrator: one reactor instance per lane, adaptive Rosenbrock (tableau from the
 // generated header), SciPy-style error test  rms(err / (atol + rtol*max(|y|,|y_new|))) <= 1.
@@ -798,9 +1035,9 @@ struct SolveArgs {
 };
 
 #define SM(slot) sm[(slot)*RMT_BLOCK]
-#define LU(r, c) SM((r)*RMT_N + (c))
-#define KS(s, i) SM(RMT_N*RMT_N + (s)*RMT_N + (i))
-#define RMT_SMEM_DOUBLES_PER_THREAD (RMT_N*RMT_N + RMT_ROS_S*RMT_N)
+#define LU(r, c) SM((r)*RMT_M + (c))
+#define KS(s, i) SM(RMT_M*RMT_M + (s)*RMT_M + (i))
+#define RMT_SMEM_DOUBLES_PER_THREAD (RMT_M*RMT_M + RMT_ROS_S*RMT_M)
 
 struct SmemJac {            // stores -J: the iteration matrix is W = I/(h*gamma) - J
     double* sm;
@@ -940,20 +1177,27 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
 #endif
 
         // ---- one step attempt ----
-        double f0[RMT_N];
+        double f0[RMT_M];
         SmemJac sj{sm};
-        n1_eval<true>(y, h, f0, sj);                          // f(y_n), and -J into LU(.,.)
+        n1_eval_sys<true>(y, h, f0, sj);                      // g(y_n), and -A into LU(.,.)
 
         if (fresh) {
             // initial step (Hairer-Wanner II.4 with the exact y'' = J f)
             double d0 = 0.0, d1 = 0.0, d2 = 0.0;
+            double ag[RMT_M], fy[RMT_N], jfy[RMT_N];
+#pragma unroll
+            for (int i = 0; i < RMT_M; ++i) {
+                double v = 0.0;
+#pragma unroll
+                for (int j = 0; j < RMT_M; ++j) v -= LU(i, j)*f0[j];
+                ag[i] = v;
+            }
+            rmt_expand(f0, fy);                               // y' = E g
+            rmt_expand(ag, jfy);                              // y'' = E A g
 #pragma unroll
             for (int i = 0; i < RMT_N; ++i) {
                 const double sc = a.ctrl[3]*(a.atol + a.rtol*fabs(y[i]));
-                double jf = 0.0;
-#pragma unroll
-                for (int j = 0; j < RMT_N; ++j) jf -= LU(i, j)*f0[j];
-                d0 += (y[i]/sc)*(y[i]/sc); d1 += (f0[i]/sc)*(f0[i]/sc); d2 += (jf/sc)*(jf/sc);
+                d0 += (y[i]/sc)*(y[i]/sc); d1 += (fy[i]/sc)*(fy[i]/sc); d2 += (jfy[i]/sc)*(jfy[i]/sc);
             }
             d0 = sqrt(d0/RMT_N); d1 = sqrt(d1/RMT_N); d2 = sqrt(d2/RMT_N);
             const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01*d0/d1;
@@ -973,52 +1217,52 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
         // shared-memory address of each (pivoted) row, so every access is [row + immediate].
         const double dg = 1.0/(hh*RMT_ROS_GAMMA);
 #pragma unroll
-        for (int i = 0; i < RMT_N; ++i) LU(i, i) += dg;
-        double* row[RMT_N];
-        int perm[RMT_N];
+        for (int i = 0; i < RMT_M; ++i) LU(i, i) += dg;
+        double* row[RMT_M];
+        int perm[RMT_M];
 #pragma unroll
-        for (int i = 0; i < RMT_N; ++i) { row[i] = sm + (i*RMT_N)*RMT_BLOCK; perm[i] = i; }
+        for (int i = 0; i < RMT_M; ++i) { row[i] = sm + (i*RMT_M)*RMT_BLOCK; perm[i] = i; }
 #define ROW(i, j) row[i][(j)*RMT_BLOCK]
 #pragma unroll
-        for (int k = 0; k < RMT_N; ++k) {
+        for (int k = 0; k < RMT_M; ++k) {
             double best = fabs(ROW(k, k));
             int bi = k;
 #pragma unroll
-            for (int i = k + 1; i < RMT_N; ++i) {
+            for (int i = k + 1; i < RMT_M; ++i) {
                 const double v = fabs(ROW(i, k));
                 if (v > best) { best = v; bi = i; }
             }
 #pragma unroll
-            for (int i = k + 1; i < RMT_N; ++i)
+            for (int i = k + 1; i < RMT_M; ++i)
                 if (i == bi) {
                     double* tr = row[k]; row[k] = row[i]; row[i] = tr;
                     const int tp = perm[k]; perm[k] = perm[i]; perm[i] = tp;
                 }
             const double piv = rmt_rcp(ROW(k, k));
             ROW(k, k) = piv;                                  // store reciprocal pivot
-            double urow[RMT_N];
+            double urow[RMT_M];
 #pragma unroll
-            for (int j = k + 1; j < RMT_N; ++j) urow[j] = ROW(k, j);
+            for (int j = k + 1; j < RMT_M; ++j) urow[j] = ROW(k, j);
 #pragma unroll
-            for (int i = k + 1; i < RMT_N; ++i) {
+            for (int i = k + 1; i < RMT_M; ++i) {
                 const double l = ROW(i, k)*piv;
                 ROW(i, k) = l;
 #pragma unroll
-                for (int j = k + 1; j < RMT_N; ++j) ROW(i, j) -= l*urow[j];
+                for (int j = k + 1; j < RMT_M; ++j) ROW(i, j) -= l*urow[j];
             }
         }
 
         // stages
 #if RMT_ROS_REUSE
-        double flast[RMT_N];                   // latest evaluated f (a re-using stage takes the previous stage's)
+        double flast[RMT_M];                   // latest evaluated f (a re-using stage takes the previous stage's)
 #pragma unroll
-        for (int i = 0; i < RMT_N; ++i) flast[i] = f0[i];
+        for (int i = 0; i < RMT_M; ++i) flast[i] = f0[i];
 #else
-        const double (&flast)[RMT_N] = f0;
+        const double (&flast)[RMT_M] = f0;
 #endif
-        double ynew[RMT_N], errv[RMT_N];
+        double dxs[RMT_M], evs[RMT_M];          // sum m_s k_s and sum e_s k_s in the integrator's unknowns
 #pragma unroll
-        for (int i = 0; i < RMT_N; ++i) { ynew[i] = y[i]; errv[i] = 0.0; }
+        for (int i = 0; i < RMT_M; ++i) { dxs[i] = 0.0; evs[i] = 0.0; }
         const double invh = 1.0/hh;
 #if RMT_ROLL
 #pragma unroll 1
@@ -1029,7 +1273,7 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
 #if RMT_SYNC == 2
             __syncthreads();
 #endif
-            double rhs[RMT_N];
+            double rhs[RMT_M];
 #if RMT_ROLL
             if (s == 0 || !RMT_cROS_NEWF[s]) {
 #else
@@ -1038,13 +1282,13 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
                 // first stage, or a stage with the same argument as the previous one: re-use its function value
                 // (flast == f(y_n) until a later stage has evaluated a new one)
 #pragma unroll
-                for (int i = 0; i < RMT_N; ++i) rhs[i] = flast[i];
+                for (int i = 0; i < RMT_M; ++i) rhs[i] = flast[i];
 #if RMT_ROLL
                 for (int j = 0; j < s; ++j) {
                     const double cj = RMT_cROS_C[s][j]*invh;
                     const double* kj = &KS(j, 0);
 #pragma unroll
-                    for (int i = 0; i < RMT_N; ++i) rhs[i] += cj*kj[i*RMT_BLOCK];
+                    for (int i = 0; i < RMT_M; ++i) rhs[i] += cj*kj[i*RMT_BLOCK];
                 }
 #else
 #pragma unroll
@@ -1052,21 +1296,21 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
                     if (RMT_ROS_C[s][j] != 0.0) {
                         const double cj = RMT_cROS_C[s][j]*invh;
 #pragma unroll
-                        for (int i = 0; i < RMT_N; ++i) rhs[i] += cj*KS(j, i);
+                        for (int i = 0; i < RMT_M; ++i) rhs[i] += cj*KS(j, i);
                     }
 #endif
             } else {
-                double u[RMT_N];
+                double ur[RMT_M];
 #pragma unroll
-                for (int i = 0; i < RMT_N; ++i) u[i] = y[i];
+                for (int i = 0; i < RMT_M; ++i) ur[i] = 0.0;
 #if RMT_ROLL
                 // rolled form: one copy of the RHS / triangular-solve code for all stages (instruction-cache
                 // footprint); tableau rows are read from the constant bank with a runtime stage index.
                 // Each K_j is read once for both the stage argument and the (c_sj/h) K_j sum.
 #if RMT_MERGE_KLOADS
-                double vc[RMT_N];
+                double vc[RMT_M];
 #pragma unroll
-                for (int i = 0; i < RMT_N; ++i) vc[i] = 0.0;
+                for (int i = 0; i < RMT_M; ++i) vc[i] = 0.0;
 #endif
                 for (int j = 0; j < s; ++j) {
                     const double aj = RMT_cROS_A[s][j];
@@ -1074,10 +1318,10 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
 #if RMT_MERGE_KLOADS
                     const double cj = RMT_cROS_C[s][j]*invh;
 #pragma unroll
-                    for (int i = 0; i < RMT_N; ++i) { const double kv = kj[i*RMT_BLOCK]; u[i] += aj*kv; vc[i] += cj*kv; }
+                    for (int i = 0; i < RMT_M; ++i) { const double kv = kj[i*RMT_BLOCK]; ur[i] += aj*kv; vc[i] += cj*kv; }
 #else
 #pragma unroll
-                    for (int i = 0; i < RMT_N; ++i) u[i] += aj*kj[i*RMT_BLOCK];
+                    for (int i = 0; i < RMT_M; ++i) ur[i] += aj*kj[i*RMT_BLOCK];
 #endif
                 }
 #else
@@ -1085,24 +1329,28 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
                 for (int j = 0; j < s; ++j)
                     if (RMT_ROS_A[s][j] != 0.0) {
 #pragma unroll
-                        for (int i = 0; i < RMT_N; ++i) u[i] += RMT_cROS_A[s][j]*KS(j, i);
+                        for (int i = 0; i < RMT_M; ++i) ur[i] += RMT_cROS_A[s][j]*KS(j, i);
                     }
 #endif
-                n1_eval<false>(u, h, rhs, NoJac());
+                double u[RMT_N];
+                rmt_expand(ur, u);
+#pragma unroll
+                for (int i = 0; i < RMT_N; ++i) u[i] += y[i];
+                n1_eval_sys<false>(u, h, rhs, NoJac());
 #if RMT_ROS_REUSE
 #pragma unroll
-                for (int i = 0; i < RMT_N; ++i) flast[i] = rhs[i];
+                for (int i = 0; i < RMT_M; ++i) flast[i] = rhs[i];
 #endif
 #if RMT_ROLL
 #if RMT_MERGE_KLOADS
 #pragma unroll
-                for (int i = 0; i < RMT_N; ++i) rhs[i] += vc[i];
+                for (int i = 0; i < RMT_M; ++i) rhs[i] += vc[i];
 #else
                 for (int j = 0; j < s; ++j) {
                     const double cj = RMT_cROS_C[s][j]*invh;
                     const double* kj = &KS(j, 0);
 #pragma unroll
-                    for (int i = 0; i < RMT_N; ++i) rhs[i] += cj*kj[i*RMT_BLOCK];
+                    for (int i = 0; i < RMT_M; ++i) rhs[i] += cj*kj[i*RMT_BLOCK];
                 }
 #endif
 #else
@@ -1111,7 +1359,7 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
                     if (RMT_ROS_C[s][j] != 0.0) {
                         const double cj = RMT_cROS_C[s][j]*invh;
 #pragma unroll
-                        for (int i = 0; i < RMT_N; ++i) rhs[i] += cj*KS(j, i);
+                        for (int i = 0; i < RMT_M; ++i) rhs[i] += cj*KS(j, i);
                     }
 #endif
             }
@@ -1119,42 +1367,47 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
             // is an address, not a register index
             double* ks = &KS(s, 0);
 #pragma unroll
-            for (int i = 0; i < RMT_N; ++i) ks[i*RMT_BLOCK] = rhs[i];
-            double x[RMT_N];
+            for (int i = 0; i < RMT_M; ++i) ks[i*RMT_BLOCK] = rhs[i];
+            double x[RMT_M];
 #pragma unroll
-            for (int i = 0; i < RMT_N; ++i) {
+            for (int i = 0; i < RMT_M; ++i) {
                 double v = ks[perm[i]*RMT_BLOCK];
 #pragma unroll
                 for (int j = 0; j < i; ++j) v -= ROW(i, j)*x[j];
                 x[i] = v;
             }
 #pragma unroll
-            for (int i = RMT_N - 1; i >= 0; --i) {
+            for (int i = RMT_M - 1; i >= 0; --i) {
                 double v = x[i];
 #pragma unroll
-                for (int j = i + 1; j < RMT_N; ++j) v -= ROW(i, j)*x[j];
+                for (int j = i + 1; j < RMT_M; ++j) v -= ROW(i, j)*x[j];
                 x[i] = v*ROW(i, i);
             }
 #if RMT_ROLL
             const double ms = RMT_cROS_M[s], es = RMT_cROS_E[s];
 #pragma unroll
-            for (int i = 0; i < RMT_N; ++i) {
+            for (int i = 0; i < RMT_M; ++i) {
                 ks[i*RMT_BLOCK] = x[i];
-                ynew[i] += ms*x[i];
-                errv[i] += es*x[i];
+                dxs[i] += ms*x[i];
+                evs[i] += es*x[i];
             }
 #else
 #pragma unroll
-            for (int i = 0; i < RMT_N; ++i) {
+            for (int i = 0; i < RMT_M; ++i) {
                 ks[i*RMT_BLOCK] = x[i];
-                if (RMT_ROS_M[s] == 1.0) ynew[i] += x[i];
-                else if (RMT_ROS_M[s] != 0.0) ynew[i] += RMT_cROS_M[s]*x[i];
-                if (RMT_ROS_E[s] == 1.0) errv[i] += x[i];
-                else if (RMT_ROS_E[s] != 0.0) errv[i] += RMT_ROS_E[s]*x[i];
+                if (RMT_ROS_M[s] == 1.0) dxs[i] += x[i];
+                else if (RMT_ROS_M[s] != 0.0) dxs[i] += RMT_cROS_M[s]*x[i];
+                if (RMT_ROS_E[s] == 1.0) evs[i] += x[i];
+                else if (RMT_ROS_E[s] != 0.0) evs[i] += RMT_ROS_E[s]*x[i];
             }
 #endif
         }
 #undef ROW
+        double ynew[RMT_N], errv[RMT_N];
+        rmt_expand(dxs, ynew);
+        rmt_expand(evs, errv);
+#pragma unroll
+        for (int i = 0; i < RMT_N; ++i) ynew[i] += y[i];
 
         // error norm (scipy/integrate/_ivp/common.py:63-65 rms norm; radau.py scale)
         double err = 0.0;
@@ -1209,16 +1462,20 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
                         for (int i = 0; i < RMT_N; ++i) v[i] = ynew[i];
                     } else {
                         const double th = (ze - t)*invh, th1 = 1.0 - th;
+                        double dr[RMT_M], dy[RMT_N];
 #pragma unroll
-                        for (int i = 0; i < RMT_N; ++i) {
+                        for (int i = 0; i < RMT_M; ++i) {
                             double d2 = 0.0, d3 = 0.0;
 #pragma unroll
                             for (int s = 0; s < RMT_ROS_S; ++s) {
                                 if (RMT_ROS_D[0][s] != 0.0) d2 += RMT_cROS_D[0][s]*KS(s, i);
                                 if (RMT_ROS_D[1][s] != 0.0) d3 += RMT_cROS_D[1][s]*KS(s, i);
                             }
-                            v[i] = y[i]*th1 + th*(ynew[i] + th1*(d2 + th*d3));
+                            dr[i] = d2 + th*d3;
                         }
+                        rmt_expand(dr, dy);
+#pragma unroll
+                        for (int i = 0; i < RMT_N; ++i) v[i] = y[i]*th1 + th*(ynew[i] + th1*dy[i]);
                     }
                     if (live) n1_write_point(a, h, inst, next_e, v);
                     ++next_e;

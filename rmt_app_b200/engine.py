@@ -11,7 +11,7 @@ import threading
 import numpy as np
 
 from . import capi
-from .codegen import generate_model_header, model_flops
+from .codegen import generate_model_header, model_flops, system_size, use_extents
 from .model import SCALAR_INPUTS, ModelSpec
 
 # The reference's only "config system" for the path: module-level mutable dict
@@ -37,12 +37,14 @@ def _torch():
 
 
 class CompiledModel:
-    def __init__(self, spec, block, method="rodas4"):
+    def __init__(self, spec, block, method="rodas4", reduced=None):
         self.spec = spec
         self.block = block
         self.method = method
-        self.header = generate_model_header(spec, tableau=method)
-        self.flops = model_flops(spec)
+        self.reduced = use_extents(spec) if reduced is None else bool(reduced)
+        self.m = system_size(spec, self.reduced)          # unknowns of the integrator's linear systems
+        self.header = generate_model_header(spec, tableau=method, reduced=self.reduced)
+        self.flops = model_flops(spec, self.reduced)
         self.module = None
 
     def load(self, device):
@@ -53,15 +55,20 @@ class CompiledModel:
         return self.module
 
 
-def default_block(spec, stages=6):
-    """Integrator block size.  Per-thread shared memory is (n^2 + s*n) doubles (LU + stage vectors).
-    One block per SM, as many warps as fit (<= 256 threads: the kernel needs ~250 registers per
-    thread): the warps of a block run in lockstep (one barrier per step attempt) so that they share
-    instruction-cache lines — measured 2x faster than two independent 128-thread blocks per SM."""
+def default_block(spec, stages=6, reduced=None):
+    """Integrator block size.  Per-thread shared memory is (m^2 + s*m) doubles (LU + stage vectors).
+    One block per SM, as many warps as fit: the warps of a block run in lockstep (one barrier per step
+    attempt) so that they share instruction-cache lines — measured 2x faster than two independent
+    128-thread blocks per SM.  256 threads leave ~250 registers per thread (no spills); when the linear
+    systems are small enough for 384 threads (reaction-extent form) the 168-register build spills a few
+    words but 12 warps hide more latency — measured 16.0 vs 18.4 ms per 2^20 config-3 reactors."""
     if spec.model == "N2":
         return 64
-    per_thread = 8*(spec.n*spec.n + stages*spec.n)
+    m = system_size(spec, reduced)
+    per_thread = 8*(m*m + stages*m)
     fit = (227*1024 - 1024)//per_thread
+    if fit >= 384:
+        return 384
     return int(max(32, min(256, (fit//32)*32)))
 
 
@@ -127,19 +134,20 @@ def _fast_key(modelInput, block):
 _fast = {}
 
 
-def compile_model(modelInput, block=None, method=None):
+def compile_model(modelInput, block=None, method=None, reduced=None):
     """Trace + generate + (lazily) NVRTC-compile; cached per model structure and integrator tableau.
-    `method` None resolves solver-config.method for a dense-output solve (Rodas4 unless stated)."""
+    `method` None resolves solver-config.method for a dense-output solve (Rodas4 unless stated);
+    `reduced` None integrates in reaction extents whenever nr < nc (codegen.use_extents)."""
     if method is None:
         method = choose_method(modelInput, rtol=0.0)
     try:
-        fk = _fast_key(modelInput, block) + (method,)
+        fk = _fast_key(modelInput, block) + (method, reduced)
         cm = _fast.get(fk)
         if cm is not None:
             return cm
     except Exception:
         fk = None
-    cm = _compile_model(modelInput, block, method)
+    cm = _compile_model(modelInput, block, method, reduced)
     if fk is not None:
         if len(_fast) > 256:
             _fast.clear()
@@ -147,15 +155,17 @@ def compile_model(modelInput, block=None, method=None):
     return cm
 
 
-def _compile_model(modelInput, block, method):
+def _compile_model(modelInput, block, method, reduced=None):
     from .tableau import TABLEAUX
     spec = ModelSpec(modelInput)
-    blk = block or default_block(spec, TABLEAUX[method]["stages"])
-    key = spec.key("b%d%s" % (blk, method))
+    if reduced is None:
+        reduced = use_extents(spec)
+    blk = block or default_block(spec, TABLEAUX[method]["stages"], reduced)
+    key = spec.key("b%d%s%s" % (blk, method, "x" if reduced else ""))
     with _lock:
         cm = _compiled.get(key)
         if cm is None:
-            cm = CompiledModel(spec, blk, method)
+            cm = CompiledModel(spec, blk, method, reduced)
             _compiled[key] = cm
     return cm
 
@@ -407,10 +417,11 @@ def n1_solve_ensemble(cm, modelInput, sweep=None, B=1, z_eval=None, rtol=None, a
     return res
 
 
-def n1_rhs_batch(cm, modelInput, Y, sweep=None, jac=False, device=None):
+def n1_rhs_batch(cm, modelInput, Y, sweep=None, jac=False, device=None, system=False):
     """modelEquationN1 (and optionally its Jacobian) at states Y [B][n]; every
     instance shares `modelInput` unless `sweep` varies inputs.  Returns
-    (F [B][n], J [B][n][n] or None, consts [nconst][B])."""
+    (F [B][n], J [B][n][n] or None, consts [nconst][B]).  `system=True` returns the integrator's
+    own form instead (rmt_n1_sys): (g [B][m], A [B][m][m], consts)."""
     torch = _torch()
     if not torch.cuda.is_available():
         raise capi.RmtError("rmt_app_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -429,6 +440,12 @@ def n1_rhs_batch(cm, modelInput, Y, sweep=None, jac=False, device=None):
         d_y = torch.from_numpy(np.ascontiguousarray(Y.T)).to(dev)
         d_f = torch.empty((n, B), dtype=torch.float64, device=dev)
         mod.setup(B, d_rows, rows.shape[0], row_map, uniform, d_consts, stream=stream)
+        if system:
+            m = mod.info.m
+            d_g = torch.empty((m, B), dtype=torch.float64, device=dev)
+            d_A = torch.empty((m*m, B), dtype=torch.float64, device=dev)
+            mod.n1_sys(B, d_consts, d_y, d_g, d_A, stream=stream)
+            return d_g.cpu().numpy().T.copy(), d_A.cpu().numpy().T.reshape(B, m, m), d_consts.cpu().numpy()
         if jac:
             d_J = torch.empty((n*n, B), dtype=torch.float64, device=dev)
             mod.n1_jac(B, d_consts, d_y, d_f, d_J, stream=stream)

@@ -55,13 +55,24 @@ def test_sweep_rows_mapping_and_errors():
 
 
 def test_block_size_keeps_one_block_per_sm_within_shared_memory():
-    for mk, n in ((lambda: cases.methanol_readme_input("N1"), 8), (lambda: cases.ch4_input("N1"), 5),
-                  (lambda: cases.ch4_input("N1", "iso-thermal"), 4)):
+    from rmt_app_b200.codegen import system_size, use_extents
+    for mk, n, m in ((lambda: cases.methanol_readme_input("N1"), 8, 5), (lambda: cases.ch4_input("N1"), 5, 3),
+                     (lambda: cases.ch4_input("N1", "iso-thermal"), 4, 2), (cases.methanol_m7_input, 8, 5)):
         spec = ModelSpec(mk())
         assert spec.n == n
-        b = engine.default_block(spec)
-        assert b % 32 == 0 and 32 <= b <= 256
-        assert b*8*(n*n + 6*n) + 1024 <= 227*1024
+        # fewer reactions than species: the integrator works in reaction extents (nr + P + T unknowns)
+        assert use_extents(spec) and system_size(spec) == m and system_size(spec, reduced=False) == n
+        for reduced, dim in ((None, m), (False, n)):
+            for stages in (4, 6):
+                b = engine.default_block(spec, stages, reduced)
+                assert b % 32 == 0 and 32 <= b <= 384
+                assert b*8*(dim*dim + stages*dim) + 1024 <= 227*1024
+    assert engine.default_block(ModelSpec(cases.methanol_readme_input("N1")), 6, False) == 256
+    assert engine.default_block(ModelSpec(cases.methanol_readme_input("N1")), 4) == 384
+    hdr = engine.compile_model(cases.methanol_readme_input("N1")).header
+    assert "#define RMT_REDUCED 1" in hdr
+    assert "#define RMT_REDUCED 0" in engine.compile_model(cases.methanol_readme_input("N1"), reduced=False).header
+    assert "RMT_REDUCED 0" in engine.compile_model(cases.methanol_readme_input("N2")).header
 
 
 def test_model_key_depends_on_structure_only():

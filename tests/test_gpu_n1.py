@@ -83,6 +83,38 @@ def test_analytic_jacobian_against_oracle_differences(golden_n1, name):
 
 
 @pytest.mark.parametrize("name", list(N1_CASES))
+def test_reaction_extent_system_is_the_projected_jacobian(golden_n1, name):
+    """The integrator solves in reaction extents (nr + 2 unknowns) when nr < nc.  With E = [[nu^T, 0], [0, I]]
+    its g and A = dg/dx must satisfy E g == f and E A == J E exactly (up to rounding): then the Rosenbrock
+    iterates are those of the full system."""
+    eng = _engine()
+    mi = N1_CASES[name]()
+    cm = eng.compile_model(mi)
+    spec = cm.spec
+    assert cm.reduced and cm.m == spec.nr + spec.n - spec.nc
+    Y = golden_n1[name + "__rhs_Y"][[0, 10, 13, 20]]
+    F, J, _ = eng.n1_rhs_batch(cm, mi, Y, jac=True)
+    g, A, _ = eng.n1_rhs_batch(cm, mi, Y, system=True)
+    nx = spec.n - spec.nc
+    E = np.zeros((spec.n, cm.m))
+    E[:spec.nc, :spec.nr] = spec.nu.T
+    E[spec.nc:, spec.nr:] = np.eye(nx)
+    for f, Jf, gi, Ai in zip(F, J, g, A):
+        np.testing.assert_allclose(E @ gi, f, rtol=0, atol=1e-13*np.max(np.abs(f)))
+        lhs, rhs = E @ Ai, Jf @ E
+        assert np.max(np.abs(lhs - rhs)) <= 1e-12*np.max(np.abs(rhs)), (name, lhs - rhs)
+    # the full-state build of the same model is still available and agrees to integration tolerance
+    cf = eng.compile_model(mi, reduced=False)
+    assert not cf.reduced and cf.m == spec.n
+    sweep = {"temperature": np.array([mi["operating-conditions"]["temperature"]]*3)*np.array([1.0, 1.01, 0.99])}
+    a = eng.n1_solve_ensemble(cm, mi, sweep, B=3, rtol=1e-9, atol=1e-12)
+    b = eng.n1_solve_ensemble(cf, mi, sweep, B=3, rtol=1e-9, atol=1e-12)
+    assert (a.status == 0).all() and (b.status == 0).all()
+    np.testing.assert_allclose(a.out, b.out, rtol=2e-8, atol=1e-12)
+    assert np.max(np.abs(a.stats[0] - b.stats[0])) <= 2      # same step sequence, up to rounding at the accept test
+
+
+@pytest.mark.parametrize("name", list(N1_CASES))
 def test_rmtexe_tight_matches_reference_tight(golden_n1, name):
     """Level 2: outlet mole fractions and the 101-point T profile within 1e-6 (north_star)."""
     from rmt_app_b200 import rmtExe

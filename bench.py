@@ -384,7 +384,7 @@ def run_gpu_arm(args, rank, world, local_rank):
         single_s = time.perf_counter() - t0
         solverSetting["N2"]["zNo"] = 20
         Bn, zn = 12500, 200                     # BASELINE configs[4]: 100k instances x 200 nodes over 8 GPUs
-        cm2 = engine.compile_model(mi2, block=engine.n2_block(Bn))
+        cm2 = engine.compile_model_n2(mi2, Bn, zn)
         sw2 = cases.config3_sweep(Bn, 20240613)
         for _ in range(2):
             torch.cuda.synchronize(); t0 = time.perf_counter()

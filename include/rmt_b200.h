@@ -59,6 +59,7 @@ typedef struct rmt_module_info {
     int32_t flops_jac_alg, flops_jac_wt;     /* per RHS+Jacobian evaluation    */
     int32_t m;            /* unknowns of the integrator's linear systems: n, or */
                           /* nr + (n - nc) when it works in reaction extents    */
+    int32_t lanes;        /* N2: threads per reactor (nodes handled in parallel)*/
 } rmt_module_info;
 
 const char* rmt_last_error(void);

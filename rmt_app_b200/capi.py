@@ -25,7 +25,7 @@ class RmtError(RuntimeError):
 class ModuleInfo(C.Structure):
     _fields_ = [(k, C.c_int32) for k in (
         "model", "n", "nc", "nr", "nin", "nconst", "nkp", "stages", "block", "iso",
-        "flops_rhs_alg", "flops_rhs_wt", "flops_jac_alg", "flops_jac_wt", "m")]
+        "flops_rhs_alg", "flops_rhs_wt", "flops_jac_alg", "flops_jac_wt", "m", "lanes")]
 
 
 _lib = None

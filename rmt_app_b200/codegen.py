@@ -195,7 +195,7 @@ def system_size(spec, reduced=None):
     return spec.nr + (spec.n - spec.nc) if reduced else spec.n
 
 
-def generate_model_header(spec, tableau="rodas4", reduced=None):
+def generate_model_header(spec, tableau="rodas4", reduced=None, lanes=1):
     kin, g = spec.kin, spec.kin.g
     nc, nr, nkp = spec.nc, spec.nr, spec.nkp
     if reduced is None:
@@ -231,6 +231,13 @@ def generate_model_header(spec, tableau="rodas4", reduced=None):
     A("#ifndef RMT_REDUCED")
     A("#define RMT_REDUCED %d" % (1 if reduced else 0))
     A("#endif")
+    if spec.model == "N2":
+        if lanes not in (1, 2, 4, 8, 16, 32):
+            raise ValueError("lanes per reactor must be a power of two <= 32")
+        A("// threads per reactor of the dynamic integrator (nodes evaluated in parallel)")
+        A("#ifndef RMT_N2_G")
+        A("#define RMT_N2_G %d" % lanes)
+        A("#endif")
     for k, nm in enumerate(kin.param_names):
         A("// kinetic parameter slot %d = VARS[%r] (default %r)" % (k, nm, kin.param_defaults[k]))
 

@@ -389,6 +389,7 @@ int rmt_module_load(const void* cubin, size_t size, rmt_module_t* module_out)
     I.stages = mv[7]; I.block = mv[8]; I.iso = mv[9];
     I.flops_rhs_alg = mv[10]; I.flops_rhs_wt = mv[11]; I.flops_jac_alg = mv[12]; I.flops_jac_wt = mv[13];
     I.m = mv[14] > 0 ? mv[14] : mv[1];
+    I.lanes = mv[15] > 0 ? mv[15] : 1;
     auto get = [&](const char* name) { CUfunction f = nullptr; drv.p_cuModuleGetFunction(&f, M->mod, name); return f; };
     M->f_setup = get("rmt_setup");
     M->f_n1_rhs = get("rmt_n1_rhs");
@@ -588,10 +589,11 @@ int rmt_n2_rhs(rmt_module_t m, int64_t B, int32_t zNo, const double* d_consts, c
     return launch(M->f_n2_rhs, (unsigned)((B + 63)/64), 64, 0, (CUstream)stream, params, "rmt_n2_rhs");
 }
 
+// threads of the N2 integrator launch: `lanes` threads per reactor, whole blocks, at most one resident wave
 static int64_t n2_slots(const Module* M, int64_t B)
 {
     const int block = M->info.block;
-    long long want = (B + block - 1)/block;
+    long long want = (B*M->info.lanes + block - 1)/block;
     long long cap = (long long)g_sm_count*std::max(M->solve_blocks_per_sm, 1);
     return (int64_t)std::max<long long>(1, std::min(want, cap))*block;
 }
@@ -602,10 +604,11 @@ int64_t rmt_n2_work_doubles(rmt_module_t m, int64_t B, int32_t zNo)
     if (!M) { fail("invalid module handle"); return -1; }
     if (B <= 0 || zNo < 2) { fail("rmt_n2_work_doubles: need B > 0 and zNo >= 2"); return -1; }
     const int64_t n = M->info.n, s = M->info.stages;
-    // per node and integrator thread: y_n, y_{n+1}, s stage vectors, LU (n x n), upwind / pressure
-    // coupling vectors (3n), d E/d P, packed pivots
-    const int64_t rows = n*(5 + s + n) + 2;
-    return rows*(int64_t)zNo*n2_slots(M, B);
+    // per node and integrator thread: y_n, y_{n+1}, s stage vectors, W_kk^{-1} (n x n), upwind / pressure
+    // coupling vectors (3n), d E/d P
+    const int64_t rows = n*(5 + s + n) + 1;
+    const int64_t groups = (zNo + M->info.lanes - 1)/M->info.lanes;      // node groups, one node per lane
+    return rows*groups*n2_slots(M, B);
 }
 
 int rmt_n2_solve(rmt_module_t m, int64_t B, int32_t zNo, int32_t tNo, double period, const double* d_consts,

@@ -220,6 +220,10 @@ __device__ __forceinline__ double rmt_sqrt(const double x)
 #ifndef RMT_BLOCK
 #define RMT_BLOCK 256
 #endif
+// N2 integrator: lanes per reactor (nodes evaluated in parallel), see rmt_n2_solve
+#ifndef RMT_N2_G
+#define RMT_N2_G 1
+#endif
 // warps of a block are kept in (loose) lockstep so that they share instruction-cache lines:
 // 0 = free running, 1 = one block barrier per step attempt, 2 = one per Rosenbrock stage
 #ifndef RMT_SYNC
@@ -271,7 +275,11 @@ extern "C" __global__ void rmt_meta(int* out)
 #else
     out[14] = 0;
 #endif
-    out[15] = 0;
+#if defined(RMT_MODEL_N2)
+    out[15] = RMT_N2_G;
+#else
+    out[15] = 1;
+#endif
 }
 
 // ---------------------------------------------------------------------------------
@@ -1714,7 +1722,7 @@ rmt_n2_rhs(const double* __restrict__ consts, const i64 B, const int zNo, const 
 // remainder from the pressure march which is carried EXACTLY by one running scalar
 // (the linearised pressure dP_k).  Every stage is therefore one forward sweep over the nodes
 // with an n x n solve per node — no approximation of the Jacobian, as Rosenbrock methods need.
-// Per-instance work arrays live in global memory, [slot-row][node][thread] so that the lanes of
+// Per-instance work arrays live in global memory, [slot-row][node group][thread] so that the lanes of
 // a warp read consecutive doubles.
 // ---------------------------------------------------------------------------------
 struct SolveArgsN2 {
@@ -1736,21 +1744,93 @@ struct SolveArgsN2 {
 // rows of the per-node work record
 enum {
     W_Y0 = 0, W_Y1 = RMT_N, W_K = 2*RMT_N, W_LU = W_K + RMT_ROS_S*RMT_N, W_L = W_LU + RMT_N*RMT_N,
-    W_G = W_L + RMT_N, W_E = W_G + RMT_N, W_EP = W_E + RMT_N, W_PERM = W_EP + 1, W_ROWS = W_PERM + 1
-};
+    W_G = W_L + RMT_N, W_E = W_G + RMT_N, W_EP = W_E + RMT_N, W_ROWS = W_EP + 1
+};                               // W_LU holds W_kk^{-1} (n x n, row-major)
+
+// solve with LU factors held in registers (rows permuted in place, reciprocal pivots on the diagonal)
+__device__ __forceinline__ void n2_lu_solve(const double (&A)[RMT_N][RMT_N], const int (&perm)[RMT_N],
+                                            const double (&b)[RMT_N], double (&x)[RMT_N])
+{
+#pragma unroll
+    for (int r = 0; r < RMT_N; ++r) {
+        double v = 0.0;
+#pragma unroll
+        for (int q = 0; q < RMT_N; ++q) if (q == perm[r]) v = b[q];
+#pragma unroll
+        for (int c = 0; c < r; ++c) v -= A[r][c]*x[c];
+        x[r] = v;
+    }
+#pragma unroll
+    for (int r = RMT_N - 1; r >= 0; --r) {
+        double v = x[r];
+#pragma unroll
+        for (int c = r + 1; c < RMT_N; ++c) v -= A[r][c]*x[c];
+        x[r] = v*A[r][r];
+    }
+}
 
 __device__ __forceinline__ int n2_out_rows(const int mode) { return mode == 2 ? 2*RMT_N + RMT_NC : RMT_N; }
 
-extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n2_solve(const SolveArgsN2 a)
+// Lanes per reactor.  G consecutive lanes serve one reactor; node k belongs to lane k % G of node group
+// k / G.  Per node group the physics (rates, Jacobian blocks, LU) of the G nodes is evaluated in parallel,
+// one node per lane; what is sequential in the node index — the Ergun pressure march and the block forward
+// substitution — is handed from lane to lane with shuffles, in node order, so the arithmetic (and every
+// result bit) is the same for every G.
+static_assert(RMT_N2_G >= 1 && RMT_N2_G <= 32 && (RMT_N2_G & (RMT_N2_G - 1)) == 0, "RMT_N2_G: power of two <= 32");
+static_assert(RMT_BLOCK % 32 == 0, "block size");
+
+// mixture molar mass [kg/mol] of a node state — the same arithmetic as rmt_point
+__device__ __forceinline__ double n2_mw(const double (&u)[RMT_N], const Hot& h)
 {
-    const i64 slots = (i64)gridDim.x*blockDim.x;
-    const i64 slot = (i64)blockIdx.x*blockDim.x + threadIdx.x;
-    const int zNo = a.zNo;
-    double* w = a.work + slot;
-#define WK(row, k) w[((i64)(row)*zNo + (k))*slots]
-    const double dz = 1.0/(zNo - 1), invdz = 1.0/dz;
+    double C[RMT_NC], S = 0.0;
+#pragma unroll
+    for (int i = 0; i < RMT_NC; ++i) { C[i] = fmax(u[i], RMT_EPS_CONST)*h.Cmax; S += C[i]; }
+    const double invS = rmt_rcp(S);
+    double mw = 0.0;
+#pragma unroll
+    for (int i = 0; i < RMT_NC; ++i) mw += (C[i]*invS)*RMT_cMW[i];
+    return mw*1e-3;
+}
+
+// Ergun march across the lanes of a group (:3970-3979): Pin = pressure at the group's first node; returns the
+// pressure at this lane's node, Pout = pressure at the first node of the next group.
+__device__ __forceinline__ double n2_pressure_chain(const double Pin, const double MWm, const double T, const Hot& h,
+                                                    const double dz, const int g, const unsigned gmask, double& Pout)
+{
+    constexpr int G = RMT_N2_G;
+    const double us = h.us0;
+    const double invRT = rmt_rcp(RMT_R_CONST*T);
+    double P = Pin, Pn = Pin;
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+        const double rho = (P*MWm)*invRT;
+        const double E = -1*(h.ergA*us + h.ergC*rho*(us*us));
+        Pn = fma(E, dz, P);
+        if (j + 1 < G) {
+            const double up = __shfl_up_sync(gmask, Pn, 1, G);
+            if (g == j + 1) P = up;
+        }
+    }
+    Pout = G > 1 ? __shfl_sync(gmask, Pn, G - 1, G) : Pn;
+    return P;
+}
+
+#ifndef RMT_N2_MINBLOCKS
+#define RMT_N2_MINBLOCKS 1
+#endif
+extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2_solve(const SolveArgsN2 a)
+{
+    constexpr int G = RMT_N2_G;
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
+    const int g = threadIdx.x & (G - 1);                       // lane within the reactor's group
+    const unsigned gmask = (G == 32) ? FULL : (((1u << G) - 1u) << (lane - g));
+    const i64 threads = (i64)gridDim.x*blockDim.x;
+    const i64 tid = (i64)blockIdx.x*blockDim.x + threadIdx.x;
+    const int zNo = a.zNo, NG = (zNo + G - 1)/G;
+    double* w = a.work + tid;
+#define WK(row, kg) w[((i64)(row)*NG + (kg))*threads]
+    const double dz = 1.0/(zNo - 1), invdz = 1.0/dz;
     const double SAFE = a.ctrl[0], FAC1 = a.ctrl[1], FAC2 = 1.0/a.ctrl[2], KAPPA = a.ctrl[3], BETA = a.ctrl[4];
 
     i64 inst = -1;
@@ -1761,24 +1841,25 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n2_solve(const Solve
     bool last_rejected = false, fresh = false;
 
     while (true) {
-        const bool need = (inst < 0) && !exhausted;
-        const unsigned m = __ballot_sync(FULL, need);
+        // ---- groups without a reactor pull one from the queue (one atomic per warp) ----
+        const bool need = (inst < 0) && !exhausted;              // uniform within a group
+        const unsigned m = __ballot_sync(FULL, need && g == 0);
         if (m) {
             unsigned long long base = 0;
             const int leader = __ffs(m) - 1;
             if (lane == leader) base = atomicAdd(a.queue, (unsigned long long)__popc(m));
             base = __shfl_sync(FULL, base, leader);
             if (need) {
-                const i64 cand = (i64)base + __popc(m & ((1u << lane) - 1));
+                const i64 cand = (i64)base + __popc(m & ((1u << (lane - g)) - 1));
                 if (cand >= a.B) exhausted = true;
                 else {
                     inst = cand;
                     rmt_load_hot(a.consts, a.B, inst, h);
-                    for (int k = 0; k < zNo; ++k) {                      // IV: feed composition at every node, T-hat = 0 (:3483-3497)
+                    for (int kg = 0; kg < NG; ++kg) {                    // IV: feed composition at every node, T-hat = 0 (:3483-3497)
 #pragma unroll
-                        for (int v = 0; v < RMT_NC; ++v) WK(W_Y0 + v, k) = h.iv[v];
+                        for (int v = 0; v < RMT_NC; ++v) WK(W_Y0 + v, kg) = h.iv[v];
 #if !RMT_ISO
-                        WK(W_Y0 + RMT_ITN, k) = 0.0;
+                        WK(W_Y0 + RMT_ITN, kg) = 0.0;
 #endif
                     }
                     t = 0.0; nacc = nrej = nanrej = 0; slab = 0; cur = 0; last_rejected = false; fresh = true;
@@ -1788,28 +1869,48 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n2_solve(const Solve
             }
         }
         // Lockstep: all warps of the block walk the same node loops (same zNo, same stage count), so a block
-        // barrier per node keeps them on the same instructions and lets them share instruction-cache lines
-        // (the sweep body is far larger than the I-cache).  Lanes without a reactor run as ghosts on their own
-        // work slot; every write to out / status / stats is predicated on `live`.
+        // barrier per node group keeps them on the same instructions and lets them share instruction-cache
+        // lines (the sweep body is far larger than the I-cache).  Groups without a reactor run as ghosts on
+        // their own work slots; every write to out / status / stats is predicated on `live`.  Lanes whose node
+        // index is past the outlet (zNo not a multiple of G) integrate padding nodes that nothing reads.
         if (__syncthreads_and(inst < 0)) break;
         const bool live = inst >= 0;
         const int YN = cur ? W_Y1 : W_Y0, YP = cur ? W_Y0 : W_Y1;
 
         if (fresh) {
             // starting step from ||y0|| / ||f(y0)|| (Hairer-Wanner II.4, first guess), scaled like N1
-            double d0 = 0.0, d1 = 0.0, P = h.Pf, E;
-            double ub[RMT_N] = {0}, u[RMT_N], fo[RMT_N];
+            double d0 = 0.0, d1 = 0.0, Pg = h.Pf, E;
+            double carry[RMT_N] = {0}, ub[RMT_N], u[RMT_N], fo[RMT_N];
             NodeJac nj;
-            for (int k = 0; k < zNo; ++k) {
+            for (int kg = 0; kg < NG; ++kg) {
 #pragma unroll
-                for (int v = 0; v < RMT_N; ++v) u[v] = WK(YN + v, k);
-                n2_node<false>(u, ub, k == 0, P, invdz, h, fo, E, nj);
+                for (int v = 0; v < RMT_N; ++v) {
+                    u[v] = WK(YN + v, kg);
+                    const double up = G > 1 ? __shfl_up_sync(gmask, u[v], 1, G) : 0.0;
+                    ub[v] = g == 0 ? carry[v] : up;
+                    carry[v] = G > 1 ? __shfl_sync(gmask, u[v], G - 1, G) : u[v];
+                }
+#if RMT_ISO
+                const double Tn = 0.0*h.Tf + h.Tf;
+#else
+                const double Tn = u[RMT_ITN]*h.Tf + h.Tf;
+#endif
+                double Pnext;
+                const double P = n2_pressure_chain(Pg, n2_mw(u, h), Tn, h, dz, g, gmask, Pnext);
+                n2_node<false>(u, ub, kg == 0 && g == 0, P, invdz, h, fo, E, nj);
+                Pg = Pnext;
+                double n0 = 0.0, n1 = 0.0;
 #pragma unroll
                 for (int v = 0; v < RMT_N; ++v) {
                     const double sc = KAPPA*(a.atol + a.rtol*fabs(u[v]));
-                    d0 += (u[v]/sc)*(u[v]/sc); d1 += (fo[v]/sc)*(fo[v]/sc); ub[v] = u[v];
+                    n0 += (u[v]/sc)*(u[v]/sc); n1 += (fo[v]/sc)*(fo[v]/sc);
                 }
-                P = E*dz + P;
+                if (kg*G + g >= zNo) { n0 = 0.0; n1 = 0.0; }
+#pragma unroll
+                for (int j = 0; j < G; ++j) {                            // node order, the same sum for every G
+                    d0 += G > 1 ? __shfl_sync(gmask, n0, j, G) : n0;
+                    d1 += G > 1 ? __shfl_sync(gmask, n1, j, G) : n1;
+                }
             }
             d0 = sqrt(d0/(RMT_N*zNo)); d1 = sqrt(d1/(RMT_N*zNo));
             const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01*d0/d1;
@@ -1821,16 +1922,29 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n2_solve(const Solve
         const double hh = clipped ? hlim : hstep;
         const double dg = 1.0/(hh*RMT_ROS_GAMMA), invh = 1.0/hh;
 
-        // ---- sweep 0: f(y_n), Jacobian blocks, LU of the diagonal blocks ----
+        // ---- sweep 0: f(y_n), Jacobian blocks, LU of the diagonal blocks (all nodes of a group in parallel) ----
         {
-            double P = h.Pf, E;
-            double ub[RMT_N] = {0}, u[RMT_N], fo[RMT_N];
+            double Pg = h.Pf, E;
+            double carry[RMT_N] = {0}, ub[RMT_N], u[RMT_N], fo[RMT_N];
             NodeJac nj;
-            for (int k = 0; k < zNo; ++k) {
+            for (int kg = 0; kg < NG; ++kg) {
                 __syncthreads();
 #pragma unroll
-                for (int v = 0; v < RMT_N; ++v) u[v] = WK(YN + v, k);
-                n2_node<true>(u, ub, k == 0, P, invdz, h, fo, E, nj);
+                for (int v = 0; v < RMT_N; ++v) {
+                    u[v] = WK(YN + v, kg);
+                    const double up = G > 1 ? __shfl_up_sync(gmask, u[v], 1, G) : 0.0;
+                    ub[v] = g == 0 ? carry[v] : up;
+                    carry[v] = G > 1 ? __shfl_sync(gmask, u[v], G - 1, G) : u[v];
+                }
+#if RMT_ISO
+                const double Tn = 0.0*h.Tf + h.Tf;
+#else
+                const double Tn = u[RMT_ITN]*h.Tf + h.Tf;
+#endif
+                double Pnext;
+                const double P = n2_pressure_chain(Pg, n2_mw(u, h), Tn, h, dz, g, gmask, Pnext);
+                n2_node<true>(u, ub, kg == 0 && g == 0, P, invdz, h, fo, E, nj);
+                Pg = Pnext;
                 // W_kk = I/(h*gamma) - A, LU with partial pivoting in registers
                 int perm[RMT_N];
 #pragma unroll
@@ -1862,20 +1976,25 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n2_solve(const Solve
                         for (int q = c + 1; q < RMT_N; ++q) nj.A[r][q] -= l*nj.A[c][q];
                     }
                 }
-                long long pk = 0;
+                // The diagonal blocks are applied as explicit inverses (columns by LU solves of the unit vectors,
+                // once per step): K_k = W_kk^{-1} (rhs_k + L_k*K_{k-1} + g_k dP_k) is then a matrix-vector product —
+                // seven independent dot products instead of two dependent triangular sweeps, which is what the
+                // lane-to-lane hand-over of the stage sweeps waits for.
+#pragma unroll 1
+                for (int c = 0; c < RMT_N; ++c) {
+                    double b[RMT_N], xs[RMT_N];
 #pragma unroll
-                for (int r = 0; r < RMT_N; ++r) pk |= (long long)perm[r] << (4*r);
+                    for (int q = 0; q < RMT_N; ++q) b[q] = q == c ? 1.0 : 0.0;
+                    n2_lu_solve(nj.A, perm, b, xs);
+#pragma unroll
+                    for (int q = 0; q < RMT_N; ++q) WK(W_LU + q*RMT_N + c, kg) = xs[q];
+                }
 #pragma unroll
                 for (int r = 0; r < RMT_N; ++r) {
-#pragma unroll
-                    for (int c = 0; c < RMT_N; ++c) WK(W_LU + r*RMT_N + c, k) = nj.A[r][c];
-                    WK(W_L + r, k) = nj.L[r]; WK(W_G + r, k) = nj.g[r]; WK(W_E + r, k) = nj.e[r];
-                    WK(W_K + r, k) = fo[r];                    // stage-1 right-hand side
-                    ub[r] = u[r];
+                    WK(W_L + r, kg) = nj.L[r]; WK(W_G + r, kg) = nj.g[r]; WK(W_E + r, kg) = nj.e[r];
+                    WK(W_K + r, kg) = fo[r];                   // stage-1 right-hand side
                 }
-                WK(W_EP, k) = nj.ep;
-                WK(W_PERM, k) = __longlong_as_double(pk);
-                P = E*dz + P;
+                WK(W_EP, kg) = nj.ep;
             }
         }
 
@@ -1884,89 +2003,130 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n2_solve(const Solve
         bool bad = false;
 #pragma unroll 1
         for (int s = 0; s < RMT_ROS_S; ++s) {
-            double P = h.Pf, dP = 0.0, E;
-            double ub[RMT_N] = {0}, kprev[RMT_N] = {0};
+            double Pg = h.Pf, dPg = 0.0, E;
+            double carry[RMT_N] = {0}, kcarry[RMT_N] = {0};
             const bool lastStage = s == RMT_ROS_S - 1;
-            for (int k = 0; k < zNo; ++k) {
+            for (int kg = 0; kg < NG; ++kg) {
                 __syncthreads();
-                double rhs[RMT_N], u[RMT_N];
+                double rhs[RMT_N];
                 if (s == 0) {
 #pragma unroll
-                    for (int v = 0; v < RMT_N; ++v) rhs[v] = WK(W_K + v, k);
+                    for (int v = 0; v < RMT_N; ++v) rhs[v] = WK(W_K + v, kg);
                 } else {
+                    double u[RMT_N], ub[RMT_N], vc[RMT_N];
 #pragma unroll
-                    for (int v = 0; v < RMT_N; ++v) u[v] = WK(YN + v, k);
+                    for (int v = 0; v < RMT_N; ++v) { u[v] = WK(YN + v, kg); vc[v] = 0.0; }
                     for (int j = 0; j < s; ++j) {
-                        const double aj = RMT_cROS_A[s][j];
+                        const double aj = RMT_cROS_A[s][j], cj = RMT_cROS_C[s][j]*invh;
 #pragma unroll
-                        for (int v = 0; v < RMT_N; ++v) u[v] += aj*WK(W_K + j*RMT_N + v, k);
+                        for (int v = 0; v < RMT_N; ++v) { const double kv = WK(W_K + j*RMT_N + v, kg); u[v] += aj*kv; vc[v] += cj*kv; }
                     }
-                    NodeJac njd;
-                    n2_node<false>(u, ub, k == 0, P, invdz, h, rhs, E, njd);
-                    P = E*dz + P;
-#pragma unroll
-                    for (int v = 0; v < RMT_N; ++v) ub[v] = u[v];
-                    for (int j = 0; j < s; ++j) {
-                        const double cj = RMT_cROS_C[s][j]*invh;
-#pragma unroll
-                        for (int v = 0; v < RMT_N; ++v) rhs[v] += cj*WK(W_K + j*RMT_N + v, k);
-                    }
-                }
-                // off-diagonal part of J*K: upwind block and the pressure column
-#pragma unroll
-                for (int v = 0; v < RMT_N; ++v) rhs[v] += WK(W_L + v, k)*kprev[v] + WK(W_G + v, k)*dP;
-                // solve with the stored LU of this node
-                const long long pk = __double_as_longlong(WK(W_PERM, k));
-                double x[RMT_N];
-#pragma unroll
-                for (int r = 0; r < RMT_N; ++r) {
-                    const int pr = (int)((pk >> (4*r)) & 15);
-                    double v = 0.0;
-#pragma unroll
-                    for (int q = 0; q < RMT_N; ++q) if (q == pr) v = rhs[q];
-#pragma unroll
-                    for (int c = 0; c < r; ++c) v -= WK(W_LU + r*RMT_N + c, k)*x[c];
-                    x[r] = v;
-                }
-#pragma unroll
-                for (int r = RMT_N - 1; r >= 0; --r) {
-                    double v = x[r];
-#pragma unroll
-                    for (int c = r + 1; c < RMT_N; ++c) v -= WK(W_LU + r*RMT_N + c, k)*x[c];
-                    x[r] = v*WK(W_LU + r*RMT_N + r, k);
-                }
-                // linearised pressure march: dP_{k+1} = dP_k + dz*(e_k . K_k + ep_k*dP_k)
-                double ek = 0.0;
-#pragma unroll
-                for (int v = 0; v < RMT_N; ++v) { ek += WK(W_E + v, k)*x[v]; kprev[v] = x[v]; }
-                dP = dP + dz*(ek + WK(W_EP, k)*dP);
-                if (!lastStage) {
-#pragma unroll
-                    for (int v = 0; v < RMT_N; ++v) WK(W_K + s*RMT_N + v, k) = x[v];
-                } else {
-                    // y_{n+1} = y_n + sum_j m_j K_j ; err = K_s (stiffly accurate pair)
 #pragma unroll
                     for (int v = 0; v < RMT_N; ++v) {
-                        const double yo = WK(YN + v, k);
+                        const double up = G > 1 ? __shfl_up_sync(gmask, u[v], 1, G) : 0.0;
+                        ub[v] = g == 0 ? carry[v] : up;
+                        carry[v] = G > 1 ? __shfl_sync(gmask, u[v], G - 1, G) : u[v];
+                    }
+#if RMT_ISO
+                    const double Tn = 0.0*h.Tf + h.Tf;
+#else
+                    const double Tn = u[RMT_ITN]*h.Tf + h.Tf;
+#endif
+                    double Pnext;
+                    const double P = n2_pressure_chain(Pg, n2_mw(u, h), Tn, h, dz, g, gmask, Pnext);
+                    NodeJac njd;
+                    n2_node<false>(u, ub, kg == 0 && g == 0, P, invdz, h, rhs, E, njd);
+                    Pg = Pnext;
+#pragma unroll
+                    for (int v = 0; v < RMT_N; ++v) rhs[v] += vc[v];
+                }
+                // x0 = W_kk^{-1} rhs_k: all nodes of the group in parallel
+                double Wi[RMT_N][RMT_N], Lk[RMT_N], gk[RMT_N], x0[RMT_N];
+#pragma unroll
+                for (int r = 0; r < RMT_N; ++r) {
+                    Lk[r] = WK(W_L + r, kg); gk[r] = WK(W_G + r, kg);
+#pragma unroll
+                    for (int c = 0; c < RMT_N; ++c) Wi[r][c] = WK(W_LU + r*RMT_N + c, kg);
+                }
+#pragma unroll
+                for (int r = 0; r < RMT_N; ++r) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int c = 0; c < RMT_N; ++c) acc += Wi[r][c]*rhs[c];
+                    x0[r] = acc;
+                }
+                // Block forward substitution, node by node = lane by lane: lane j adds what the node before it
+                // contributes (upwind block and the pressure column), K_k = x0 + W_kk^{-1}(L_k*K_{k-1} + g_k dP_k),
+                // and hands K_k and the linearised pressure dP_{k+1} = dP_k + dz*(e_k . K_k + ep_k*dP_k) to lane j + 1.
+                double x[RMT_N], kp[RMT_N], dP = dPg, dPn = dPg;
+#pragma unroll
+                for (int v = 0; v < RMT_N; ++v) { kp[v] = kcarry[v]; x[v] = 0.0; }
+#pragma unroll 1
+                for (int j = 0; j < G; ++j) {
+                    double xx[RMT_N], tv[RMT_N];
+#pragma unroll
+                    for (int c = 0; c < RMT_N; ++c) tv[c] = fma(Lk[c], kp[c], gk[c]*dP);     // explicit: the same bits for every G
+#pragma unroll
+                    for (int v = 0; v < RMT_N; ++v) {
+                        double acc = x0[v];
+#pragma unroll
+                        for (int c = 0; c < RMT_N; ++c) acc += Wi[v][c]*tv[c];
+                        xx[v] = acc;
+                    }
+                    double ek = 0.0;
+#pragma unroll
+                    for (int v = 0; v < RMT_N; ++v) ek += WK(W_E + v, kg)*xx[v];
+                    const double dnx = fma(dz, fma(WK(W_EP, kg), dP, ek), dP);
+                    if (g == j) {
+#pragma unroll
+                        for (int v = 0; v < RMT_N; ++v) x[v] = xx[v];
+                        dPn = dnx;
+                    }
+                    if (G > 1) {
+#pragma unroll
+                        for (int v = 0; v < RMT_N; ++v) {
+                            const double up = __shfl_up_sync(gmask, xx[v], 1, G);
+                            if (g == j + 1) kp[v] = up;
+                        }
+                        const double upP = __shfl_up_sync(gmask, dnx, 1, G);
+                        if (g == j + 1) dP = upP;
+                    }
+                }
+#pragma unroll
+                for (int v = 0; v < RMT_N; ++v) kcarry[v] = G > 1 ? __shfl_sync(gmask, x[v], G - 1, G) : x[v];
+                dPg = G > 1 ? __shfl_sync(gmask, dPn, G - 1, G) : dPn;
+                if (!lastStage) {
+#pragma unroll
+                    for (int v = 0; v < RMT_N; ++v) WK(W_K + s*RMT_N + v, kg) = x[v];
+                } else {
+                    // y_{n+1} = y_n + sum_j m_j K_j ; err = sum_j e_j K_j
+                    double ne = 0.0;
+#pragma unroll
+                    for (int v = 0; v < RMT_N; ++v) {
+                        const double yo = WK(YN + v, kg);
                         double yn = yo;
                         double ev = 0.0;
                         for (int j = 0; j < s; ++j) {
-                            const double kj = WK(W_K + j*RMT_N + v, k);
+                            const double kj = WK(W_K + j*RMT_N + v, kg);
                             yn += RMT_cROS_M[j]*kj; ev += RMT_cROS_E[j]*kj;
                         }
                         yn += RMT_cROS_M[s]*x[v]; ev += RMT_cROS_E[s]*x[v];
-                        WK(YP + v, k) = yn;
+                        WK(YP + v, kg) = yn;
                         const double sc = KAPPA*(a.atol + a.rtol*fmax(fabs(yo), fabs(yn)));
-                        errsum += (ev/sc)*(ev/sc);
-                        bad = bad || !(fabs(yn) <= 1.7e308);
+                        ne += (ev/sc)*(ev/sc);
+                        bad = bad || (kg*G + g < zNo && !(fabs(yn) <= 1.7e308));
                     }
+                    if (kg*G + g >= zNo) ne = 0.0;
+#pragma unroll
+                    for (int j = 0; j < G; ++j) errsum += G > 1 ? __shfl_sync(gmask, ne, j, G) : ne;   // node order
                 }
             }
         }
+        bad = (__ballot_sync(FULL, bad) & gmask) != 0u;
         double err = sqrt(errsum/(RMT_N*zNo));
         if (bad || !(err == err)) err = 1e30;
 
-        // ---- controller (same as N1) ----
+        // ---- controller (same as N1; identical in every lane of the group) ----
         const double errc = fmax(err, 1e-10);
         double fac;
         if (BETA > 0.0 && nacc > 0) fac = pow(errc, 1.0/(RMT_ROS_ORDER) - 0.75*BETA)*pow(erracc, -BETA)/SAFE;
@@ -1988,14 +2148,16 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n2_solve(const Solve
             if (last_rejected) hnew = fmin(hnew, hh);
             last_rejected = false;
             hstep = clipped ? fmax(hnew, hstep) : hnew;
-            if (t >= tend && live) {
+            if (t >= tend) {
                 // end of a slab: un-scale and store (sortResult5, solResultAnalysis.py:252-301; :3630-3661)
                 const int YC = cur ? W_Y1 : W_Y0;
                 const int rows = n2_out_rows(a.out_mode);
-                for (int k = 0; k < zNo; ++k) {
+                for (int kg = 0; kg < NG; ++kg) {
+                    const int k = kg*G + g;
+                    if (!live || k >= zNo) continue;
                     double v[RMT_N];
 #pragma unroll
-                    for (int q = 0; q < RMT_N; ++q) v[q] = WK(YC + q, k);
+                    for (int q = 0; q < RMT_N; ++q) v[q] = WK(YC + q, kg);
                     double* o = a.out + (((i64)slab*rows)*zNo + k)*a.B + inst;
                     const i64 rs = (i64)zNo*a.B;
                     if (a.out_mode != 1) {
@@ -2033,18 +2195,20 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n2_solve(const Solve
             else if (hstep < 1e-14*fmax(a.period, 1e-300)) fin = 2;
             else if (nanrej > 30) fin = 3;
         }
-        if (fin >= 0 && live) {
-            a.status[inst] = fin;
-            a.stats[inst] = nacc; a.stats[a.B + inst] = nrej;
-            a.stats[2*a.B + inst] = (nacc + nrej)*(RMT_ROS_S - 1); a.stats[3*a.B + inst] = nacc + nrej;
-            if (fin != 0) {
+        if (fin >= 0) {
+            if (live && g == 0) {
+                a.status[inst] = fin;
+                a.stats[inst] = nacc; a.stats[a.B + inst] = nrej;
+                a.stats[2*a.B + inst] = (nacc + nrej)*(RMT_ROS_S - 1); a.stats[3*a.B + inst] = nacc + nrej;
+            }
+            if (live && fin != 0) {
                 const int rows = n2_out_rows(a.out_mode);
                 const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-                for (; slab < a.tNo; ++slab)
+                for (int sl = slab; sl < a.tNo; ++sl)
                     for (int r = 0; r < rows; ++r)
-                        for (int k = 0; k < zNo; ++k) a.out[(((i64)slab*rows + r)*zNo + k)*a.B + inst] = qnan;
+                        for (int k = g; k < zNo; k += G) a.out[(((i64)sl*rows + r)*zNo + k)*a.B + inst] = qnan;
             }
-            inst = -1;
+            if (live) inst = -1;
         }
     }
 #undef WK

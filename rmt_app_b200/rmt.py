@@ -136,10 +136,10 @@ def _runM7(modelInput):
 def _runN2(modelInput):
     from .engine import n2_solve_ensemble
     start = timer()
-    cm = engine.compile_model(modelInput, block=engine.n2_block(1))
+    zNo, tNo = solverSetting['N2']['zNo'], solverSetting['N2']['tNo']
+    cm = engine.compile_model_n2(modelInput, 1, zNo)
     spec = cm.spec
     nc, n = spec.nc, spec.n
-    zNo, tNo = solverSetting['N2']['zNo'], solverSetting['N2']['tNo']
     opT = modelInput['operating-conditions']['period']
     res = n2_solve_ensemble(cm, modelInput, None, 1, zNo=zNo, tNo=tNo, period=opT, out_mode=2)
     if int(res.status[0]) != 0:
@@ -245,7 +245,7 @@ def rmtExeBatchN2(modelInput, sweep=None, B=None, *, zNo=None, tNo=None, rtol=No
         B = int(first.shape[0]) if hasattr(first, "shape") else len(first)
     zNo = int(solverSetting['N2']['zNo'] if zNo is None else zNo)
     tNo = int(solverSetting['N2']['tNo'] if tNo is None else tNo)
-    cm = engine.compile_model(modelInput, block=engine.n2_block(B))
+    cm = engine.compile_model_n2(modelInput, B, zNo)
     res = engine.n2_solve_ensemble(cm, modelInput, sweep, B, zNo=zNo, tNo=tNo, rtol=rtol, atol=atol, out_mode=1,
                                    keep_on_device=keep_on_device, workspace=workspace)
     out = res.out.permute(3, 0, 1, 2) if keep_on_device else np.transpose(res.out, (3, 0, 1, 2))

@@ -97,6 +97,33 @@ def test_n2_methanol_z50_default_vs_reference_bdf(n2_settings):
     assert rel[:, -1].max() < 5e-3 and rel[-1].max() < 2e-3
 
 
+@pytest.mark.parametrize("case", ["methanol", "ch4"])
+def test_n2_lanes_per_reactor_give_the_same_solution(n2_settings, case):
+    """The integrator spreads the nodes of a reactor over 1..32 lanes; the sequential parts (pressure march,
+    block substitution, error sum) are handed from lane to lane in node order, so the result does not depend
+    on the lane count beyond the compiler's choice of fused operations (<= 1e-11 relative), including node
+    counts that are not a multiple of the lane count."""
+    from rmt_app_b200 import engine
+    mi = cases.methanol_testfile_input("N2") if case == "methanol" else cases.ch4_input("N2")
+    B, zNo = 5, 21
+    rng = np.random.default_rng(3)
+    T0 = mi["operating-conditions"]["temperature"]
+    sw = {"temperature": T0*rng.uniform(0.98, 1.02, B)}
+    period = float(mi["operating-conditions"]["period"])
+    ref = None
+    for lanes, block in ((1, 64), (4, 32), (8, 64), (32, 32)):
+        cm = engine.compile_model(mi, block=block, lanes=lanes)
+        r = engine.n2_solve_ensemble(cm, mi, sw, B, zNo=zNo, tNo=3, period=period)
+        assert (r.status == 0).all(), (lanes, r.status)
+        if ref is None:
+            ref = r
+            continue
+        np.testing.assert_allclose(r.out, ref.out, rtol=1e-11, atol=0)
+        np.testing.assert_array_equal(r.stats[0], ref.stats[0])
+    assert engine.n2_lanes(1, 50) == 32 and engine.n2_lanes(12500, 200) == 8 and engine.n2_lanes(10**6, 50) == 1
+    assert engine.n2_lanes(1, 4) == 4
+
+
 def test_n2_ensemble_matches_single_and_reports_failures(n2_settings):
     from rmt_app_b200 import engine
     mi = cases.ch4_input("N2")

@@ -1,0 +1,38 @@
+"""N2 ensemble: lanes-per-reactor / block-size sweep; checks that every variant returns the same bits."""
+import os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import cases, torch
+from rmt_app_b200 import engine
+
+B = int(os.environ.get("B", 12500)); Z = int(os.environ.get("Z", 200))
+mi = cases.methanol_readme_input("N2")
+sw = cases.config3_sweep(B, 20240613) if B > 1 else None
+ref = None
+for v in sys.argv[1:]:
+    parts = v.split(",")
+    lanes, blk, defs = int(parts[0]), int(parts[1]), parts[2:]
+    cm = engine.compile_model(mi, block=blk, lanes=lanes)
+    if defs:        # extra -D options: bypass the cubin cache
+        from rmt_app_b200 import capi
+        capi.init(0)
+        cubin, _ = capi.nvrtc_compile(cm.header, block=blk, extra_opts=["-D" + d for d in defs])
+        import copy
+        cm = copy.copy(cm); cm.module = capi.Module(cubin)
+    try:
+        for rep in range(2):
+            torch.cuda.synchronize(); t0 = time.time()
+            res = engine.n2_solve_ensemble(cm, mi, sw, B, zNo=Z, tNo=5, period=0.5, keep_on_device=True)
+            torch.cuda.synchronize(); dt = time.time() - t0
+    except Exception as e:
+        print(v, "failed:", str(e)[:300]); continue
+    st = res.stats.cpu().numpy(); ok = int((res.status == 0).sum())
+    out = res.out.cpu().numpy()
+    if ref is None:
+        ref = out
+    same = np.array_equal(out, ref)
+    dev = float(np.nanmax(np.abs(out - ref)/np.abs(ref)))
+    print(",".join(defs), end=" ")
+    print("lanes %2d block %3d B=%d zNo=%d: %.4fs ok %d steps %.1f rej %.1f identical %s maxdev %.1e" % (
+        lanes, blk, B, Z, dt, ok, st[0].mean(), st[1].mean(), same, dev), flush=True)

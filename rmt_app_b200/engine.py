@@ -372,15 +372,36 @@ class N1Result:
                  "h2d_bytes", "d2h_bytes")
 
 
+# ensembles at least this large with host-side inputs are solved as a copy/compute pipeline
+PIPELINE_MIN_B = 1 << 18
+# fractions of the ensemble per pipeline chunk: a small first chunk starts the GPU early, a small last one
+# leaves little to copy back after the last kernel; every extra launch costs a kernel tail (0.3-0.6 ms).
+# Measured on 2^20 config-3 reactors, pinned inputs (tools/pipe_probe.py): one launch 19.04 ms, halves 18.78,
+# (1/4, 1/2, 1/4) 18.48, (1/8, 3/4, 1/8) 17.89, eight equal chunks 20.46; the kernel alone takes 16.25 ms.
+PIPELINE_SPLIT = (0.125, 0.75, 0.125)
+
+
+def _slice_sweep(sweep, b0, b1):
+    return {k: v[b0:b1] for k, v in (sweep or {}).items()}
+
+
+def _host_side(sweep):
+    torch = _torch()
+    return all(not (torch.is_tensor(v) and v.is_cuda) for v in (sweep or {}).values())
+
+
 def n1_solve_ensemble(cm, modelInput, sweep=None, B=1, z_eval=None, rtol=None, atol=None, out_mode=1,
                       dense=True, max_steps=100000, objective_ref=None, device=None, keep_on_device=False,
-                      workspace=None, ctrl=None, want_stats=True):
+                      workspace=None, ctrl=None, want_stats=True, pipeline=None):
     """Solve B independent steady-state reactors on the current CUDA device.
 
     Per call: stage the varying inputs in pinned memory -> H2D -> `rmt_setup`
-    (per-reactor constants) -> `rmt_n1_solve` -> D2H.  Returns an N1Result with
-    out[n_eval][rows][B].  Raises capi.RmtError when the CUDA library/driver is
-    unavailable (no CPU path exists)."""
+    (per-reactor constants) -> `rmt_n1_solve` -> D2H.  Large ensembles whose inputs and outputs
+    live on the host (`pipeline` None: B >= PIPELINE_MIN_B) are cut into three chunks on two streams,
+    so that the copies of one chunk run under the integrator kernel of another; the result does not
+    depend on the chunking (every reactor is an independent solve).  Returns an N1Result with
+    out[n_eval][rows][B].  Raises capi.RmtError when the CUDA library/driver is unavailable (no CPU
+    path exists)."""
     torch = _torch()
     if not torch.cuda.is_available():
         raise capi.RmtError("rmt_app_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -397,44 +418,89 @@ def n1_solve_ensemble(cm, modelInput, sweep=None, B=1, z_eval=None, rtol=None, a
     ws = workspace if workspace is not None else Workspace()
     n, nc = spec.n, spec.nc
     out_rows = 2*n + nc if out_mode == 2 else n
+    if ctrl is None:
+        ctrl = METHOD_CTRL.get(cm.method)
     res = N1Result()
     res.z_eval, res.n, res.nc, res.out_mode, res.flops = z_eval, n, nc, out_mode, cm.flops
-    with torch.cuda.device(dev):
+    if pipeline is None:
+        pipeline = B >= PIPELINE_MIN_B
+    pipeline = bool(pipeline) and not keep_on_device and bool(sweep) and _host_side(sweep) and B >= 3*1024
+
+    def device_part(sub, Bc, w):
+        """H2D + setup + integrator for one (sub-)ensemble on the current stream; device tensors."""
         stream = torch.cuda.current_stream().cuda_stream
-        d_rows, n_rows, row_map, res.h2d_bytes = sweep_rows_to_device(spec, sweep, B, ws, dev)
-        d_consts = ws.get("d_consts", (mod.info.nconst, B), torch.float64, device=dev)
-        d_out = ws.get("d_out", (z_eval.size, out_rows, B), torch.float64, device=dev)
-        d_status = ws.get("d_status", (B,), torch.int32, device=dev)
-        d_stats = ws.get("d_stats", (4, B), torch.int32, device=dev)
-        d_obj = ws.get("d_obj", (B,), torch.float64, device=dev) if objective_ref is not None else None
-        if ctrl is None:
-            ctrl = METHOD_CTRL.get(cm.method)
-        mod.setup(B, d_rows, n_rows, row_map, uniform, d_consts, stream=stream)
-        mod.n1_solve(B, d_consts, z_eval, rtol, atol, d_out, d_status, d_stats, max_steps=max_steps, dense=dense,
+        d_rows, n_rows, row_map, h2d = sweep_rows_to_device(spec, sub, Bc, w, dev)
+        d_consts = w.get("d_consts", (mod.info.nconst, Bc), torch.float64, device=dev)
+        d_out = w.get("d_out", (z_eval.size, out_rows, Bc), torch.float64, device=dev)
+        d_status = w.get("d_status", (Bc,), torch.int32, device=dev)
+        d_stats = w.get("d_stats", (4, Bc), torch.int32, device=dev)
+        d_obj = w.get("d_obj", (Bc,), torch.float64, device=dev) if objective_ref is not None else None
+        mod.setup(Bc, d_rows, n_rows, row_map, uniform, d_consts, stream=stream)
+        mod.n1_solve(Bc, d_consts, z_eval, rtol, atol, d_out, d_status, d_stats, max_steps=max_steps, dense=dense,
                      out_mode=out_mode, obj_ref=objective_ref, d_obj=d_obj, ctrl=ctrl, stream=stream)
-        res.consts = d_consts
+        return d_consts, d_out, d_status, d_stats, d_obj, h2d
+
+    with torch.cuda.device(dev):
         if keep_on_device:
-            res.out, res.status, res.stats, res.objective = d_out, d_status, d_stats, d_obj
+            res.consts, res.out, res.status, res.stats, res.objective, res.h2d_bytes = device_part(sweep, B, ws)
             res.d2h_bytes = 0
-        else:
-            h_out = ws.get("h_out", tuple(d_out.shape), torch.float64, pinned=True)
-            h_status = ws.get("h_status", (B,), torch.int32, pinned=True)
+            return res
+        h_out = ws.get("h_out", (z_eval.size, out_rows, B), torch.float64, pinned=True)
+        h_status = ws.get("h_status", (B,), torch.int32, pinned=True)
+        h_stats = ws.get("h_stats", (4, B), torch.int32, pinned=True) if want_stats else None
+        h_obj = ws.get("h_obj", (B,), torch.float64, pinned=True) if objective_ref is not None else None
+        res.d2h_bytes = h_out.numel()*8 + h_status.numel()*4 + (h_stats.numel()*4 if want_stats else 0) \
+            + (h_obj.numel()*8 if h_obj is not None else 0)
+        if not pipeline:
+            res.consts, d_out, d_status, d_stats, d_obj, res.h2d_bytes = device_part(sweep, B, ws)
             h_out.copy_(d_out, non_blocking=True)
             h_status.copy_(d_status, non_blocking=True)
-            res.d2h_bytes = h_out.numel()*8 + h_status.numel()*4
-            h_stats = h_obj = None
             if want_stats:
-                h_stats = ws.get("h_stats", (4, B), torch.int32, pinned=True)
                 h_stats.copy_(d_stats, non_blocking=True)
-                res.d2h_bytes += h_stats.numel()*4
             if d_obj is not None:
-                h_obj = ws.get("h_obj", (B,), torch.float64, pinned=True)
                 h_obj.copy_(d_obj, non_blocking=True)
-                res.d2h_bytes += h_obj.numel()*8
             torch.cuda.current_stream().synchronize()
-            res.out, res.status = h_out.numpy(), h_status.numpy()
-            res.stats = None if h_stats is None else h_stats.numpy()
-            res.objective = None if h_obj is None else h_obj.numpy()
+        else:
+            # chunk c runs on stream c % 2 with that stream's own device buffers: H2D(c+1) and D2H(c-1) overlap
+            # the integrator kernel of chunk c, and the blocks of the next kernel fill the tail of this one
+            if not hasattr(ws, "_pipe"):
+                ws._pipe = [(torch.cuda.Stream(device=dev), Workspace()) for _ in range(2)]
+            cuts = [0]
+            for f in PIPELINE_SPLIT[:-1]:
+                cuts.append(min(B, cuts[-1] + max(1024, int(round(f*B/1024))*1024)))
+            cuts.append(B)
+            ready = torch.cuda.Event()
+            ready.record()
+            res.h2d_bytes = 0
+            res.consts = None
+            staged = {}
+            for c in range(len(cuts) - 1):
+                b0, b1 = cuts[c], cuts[c + 1]
+                if b1 <= b0:
+                    continue
+                st, w = ws._pipe[c % 2]
+                if c - 2 in staged:
+                    staged[c - 2].synchronize()       # the pinned staging buffer of this stream is free again
+                st.wait_event(ready)
+                with torch.cuda.stream(st):
+                    _, d_out, d_status, d_stats, d_obj, h2d = device_part(_slice_sweep(sweep, b0, b1), b1 - b0, w)
+                    staged[c] = torch.cuda.Event()
+                    staged[c].record()
+                    res.h2d_bytes += h2d
+                    for e in range(z_eval.size):
+                        for r in range(out_rows):
+                            h_out[e, r, b0:b1].copy_(d_out[e, r], non_blocking=True)
+                    h_status[b0:b1].copy_(d_status, non_blocking=True)
+                    if want_stats:
+                        for r in range(4):
+                            h_stats[r, b0:b1].copy_(d_stats[r], non_blocking=True)
+                    if d_obj is not None:
+                        h_obj[b0:b1].copy_(d_obj, non_blocking=True)
+            for st, _ in ws._pipe:
+                st.synchronize()
+        res.out, res.status = h_out.numpy(), h_status.numpy()
+        res.stats = None if h_stats is None else h_stats.numpy()
+        res.objective = None if h_obj is None else h_obj.numpy()
     return res
 
 

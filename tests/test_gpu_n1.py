@@ -280,6 +280,35 @@ def test_full_size_ensemble_properties():
     assert y[:, 7].min() > 473.0 and y[:, 7].max() < 700.0                                # SURVEY App. B.4 extremes
     st = r["stats"]
     assert 30 < st[0].mean() < 80 and st[0].max() < 400
+    # an ensemble of this size with host inputs runs as a three-chunk copy/compute pipeline: same bits as one launch
+    from rmt_app_b200 import engine
+    cm = engine.compile_model(base, method=engine.choose_method(base, 1e-3, 1))
+    one = engine.n1_solve_ensemble(cm, base, sw, B, pipeline=False)
+    np.testing.assert_array_equal(one.out[0].T, y)
+    np.testing.assert_array_equal(one.status, r["status"])
+    np.testing.assert_array_equal(one.stats, st)
+
+
+def test_pipelined_ensemble_equals_single_launch():
+    """Chunked copy/compute pipeline (engine.n1_solve_ensemble, pipeline=True) against the one-launch path:
+    NumPy inputs (staged through pinned memory), pinned torch tensors, profiles and the fused objective."""
+    import torch
+    from rmt_app_b200 import engine
+    base = cases.methanol_readme_input("N1")
+    B = 7000
+    sw = cases.config3_sweep(B, seed=11)
+    cm = engine.compile_model(base)
+    z = np.linspace(0, 1, 6)
+    ref = np.array([0.6, 0.2, 0.02, 0.02, 0.15, 1e-4, 5e6, 600.0])
+    a = engine.n1_solve_ensemble(cm, base, sw, B, z_eval=z, objective_ref=ref, pipeline=False)
+    for form in ("numpy", "pinned"):
+        s2 = sw if form == "numpy" else {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in sw.items()}
+        b = engine.n1_solve_ensemble(cm, base, s2, B, z_eval=z, objective_ref=ref, pipeline=True, workspace=engine.Workspace())
+        np.testing.assert_array_equal(a.out, b.out)
+        np.testing.assert_array_equal(a.status, b.status)
+        np.testing.assert_array_equal(a.stats, b.stats)
+        np.testing.assert_array_equal(a.objective, b.objective)
+        assert b.h2d_bytes == a.h2d_bytes and b.d2h_bytes == a.d2h_bytes
 
 
 def test_branch_free_device_math_accuracy():

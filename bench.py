@@ -192,6 +192,12 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------
+# executed FP64 flop per step attempt of rmt_n1_solve on this workload (methanol kinetics, Ros4, reaction-extent
+# form), from ncu's smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on.sum of one launch divided by its
+# 54.25 M attempts (profiles/r01_ncu_n1_solve_v4_extents.csv); a calibration like `traffic`, not a live counter
+EXEC_FLOP_PER_ATTEMPT = 2*1470 + 679 + 329
+
+
 def solver_flops(info, stats, cm):
     """Algorithmic flops of one integrator launch from its per-instance counters.
     Per attempt: 1 evaluation of g and A = dg/dx, the other RHS evaluations, one m x m LU,
@@ -414,8 +420,15 @@ def run_gpu_arm(args, rank, world, local_rank):
                 "kernel": "rmt_n1_solve", "bound": "fp64", "achieved": alg/solve_s/1e12, "peak": fp64_peak,
                 "unit": "TFLOP/s", "frac": alg/solve_s/1e12/fp64_peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the ncu --set full capture of this
-                # command at 2^20 reactors (profiles/r01_ncu_n1_solve_v3_final.csv: 179.7 MB + 63.0 MB), scaled per reactor
-                "traffic": 231.5*B, "traffic_algorithmic": 8.0*(22 + n)*B + 20.0*B,
+                # command at 2^20 reactors (profiles/r01_ncu_n1_solve_v4_extents.csv: 179.4 MB + 63.9 MB), scaled per reactor
+                "traffic": 232.0*B, "traffic_algorithmic": 8.0*(22 + n)*B + 20.0*B,
+                # FP64 flops the hardware executed: thread-level DFMA (x2) + DMUL + DADD counts of the same ncu capture
+                # per step attempt (1470 + 679 + 329 instructions = 3948 flop), times this run's attempts
+                "achieved_executed": EXEC_FLOP_PER_ATTEMPT*att/solve_s/1e12,
+                "frac_executed": EXEC_FLOP_PER_ATTEMPT*att/solve_s/1e12/fp64_peak,
+                "fp64_pipe_busy_ncu": 0.529,
+                # model count with one FP64 instruction per operation and exp 25 / log 35 / div 10: an
+                # upper estimate of the instruction count — FMA fusion halves it in practice
                 "achieved_weighted": wt/solve_s/1e12, "frac_weighted": wt/solve_s/1e12/fp64_peak,
                 "peak_source": "rmt_dfma_peak measured in this run (MEASURED_PEAKS.json has no FP64 figure; "
                                "nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2)",

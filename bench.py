@@ -337,6 +337,34 @@ def run_gpu_arm(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
 
+    # ---- BASELINE configs[3]: parameter-estimation population, sharded, NCCL objective reduction + gather -------
+    config4 = None
+    if not args.no_config4:
+        from rmt_app_b200 import ensemble
+        base4 = cases.methanol_readme_input("N1")
+        base4["reaction-rates"] = cases.methanol_kinetics_param(1171.2)
+        B4 = 65536
+        pop = cases.config4_population(B4)
+        cm4 = engine.compile_model(base4, method=engine.choose_method(base4, RTOL, 1))
+        nominal = engine.n1_solve_ensemble(cm4, base4, None, 1, rtol=1e-9, atol=1e-12).out[0, :, 0]
+        ws4 = engine.Workspace()
+        r4 = ensemble.rmtExeBatchSharded(base4, pop, B4, objective_ref=nominal, workspace=ws4)      # warm-up
+        reps = 5
+        barrier()
+        c0 = torch.cuda.Event(enable_timing=True); c1 = torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(reps):
+            r4 = ensemble.rmtExeBatchSharded(base4, pop, B4, objective_ref=nominal, workspace=ws4)
+        c1.record(); torch.cuda.synchronize()
+        t4 = torch.tensor([c0.elapsed_time(c1)/reps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t4, op=dist.ReduceOp.MAX)
+        config4 = {"parameter_sets": B4, "ms_per_population": float(t4.item()), "parameter_sets_per_s": B4/(float(t4.item())*1e-3),
+                   "includes": "H2D of the rank's shard, setup, solve with fused objective, device reduction, "
+                               + ("NCCL all-gather of (sum, min, argmin) + all-gather of objectives and outlets" if world > 1
+                                  else "no collective (one rank)"),
+                   "objective_min": r4["objective_min"], "objective_argmin": r4["objective_argmin"], "failed": r4["failed"]}
+
     # ---- roofline denominators measured on this box ----------------------------------------------
     fp64_peak = mod.fp64_peak(iters=16384, repeats=5)
     peaks = {}
@@ -452,6 +480,8 @@ def run_gpu_arm(args, rank, world, local_rank):
         }
         if n2 is not None:
             line["n2_dynamic_model"] = n2
+        if config4 is not None:
+            line["config4_population"] = config4
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
         emit(line)
@@ -489,6 +519,7 @@ def main():
     ap.add_argument("--instances", type=int, default=B_PER_GPU, help="reactors per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-n2", action="store_true", help="skip the informational N2 (dynamic model) timings")
+    ap.add_argument("--no-config4", action="store_true", help="skip the informational parameter-estimation population timing")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

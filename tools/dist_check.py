@@ -15,7 +15,7 @@ B = int(os.environ.get("B", 65536))
 base = cases.methanol_readme_input("N1")
 base["reaction-rates"] = cases.methanol_kinetics_param(1171.2)
 pop = cases.config4_population(B)
-cm = engine.compile_model(base)
+cm = engine.compile_model(base, method=engine.choose_method(base, engine.DEFAULT_RTOL, 1))   # what rmtExeBatchSharded picks
 nominal = engine.n1_solve_ensemble(cm, base, None, 1).out[0, :, 0]
 ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
 r = ensemble.rmtExeBatchSharded(base, pop, B, objective_ref=nominal)       # warm-up

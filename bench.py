@@ -421,10 +421,25 @@ def run_gpu_arm(args, rank, world, local_rank):
             torch.cuda.synchronize(); t0 = time.perf_counter()
             r2 = engine.n2_solve_ensemble(cm2, mi2, sw2, Bn, zNo=zn, tNo=5, period=0.5, keep_on_device=True, workspace=ws)
             torch.cuda.synchronize(); ens_s = time.perf_counter() - t0
+        i2 = cm2.load(local_rank).info
+        att2 = float(r2.stats[3].double().sum().item())              # step attempts summed over the reactors
+        nn = i2.n
+        # per attempt and node: 1 f + Jacobian blocks, (s-1) RHS, LU + n unit-vector solves (explicit inverse), per stage
+        # two n x n matrix-vector products and the stage combinations
+        lin = (2.0*nn**3)/3.0 + nn*2.0*nn*nn + i2.stages*(4.0*nn*nn + 4.0*nn*i2.stages)
+        alg2 = att2*zn*(i2.flops_jac_alg + (i2.stages - 1)*i2.flops_rhs_alg + lin)
         n2 = {"config2_single_50_nodes_s": single_s, "reference_bdf_same_case_s": 446.3,
               "ensemble": {"instances": Bn, "nodes": zn, "period_s": 0.5, "seconds": ens_s, "instances_per_s": Bn/ens_s,
                            "converged": int((r2.status == 0).sum().item()),
-                           "steps_mean": float(r2.stats[0].double().mean().item())}}
+                           "steps_mean": float(r2.stats[0].double().mean().item()),
+                           "lanes_per_reactor": cm2.lanes, "block": cm2.block,
+                           "node_rhs_evals_per_s": att2*zn*i2.stages/ens_s,
+                           "fp64_tflops_algorithmic": alg2/ens_s/1e12,
+                           # dram bytes of one launch from ncu (profiles/r01_ncu_n2_solve_lanes8.csv: 619 + 135 GB at
+                           # 12 500 x 200 nodes x 43.0 attempts), scaled per node-attempt
+                           "hbm_traffic_gbs_ncu_calibrated": 7015.0*att2*zn/ens_s/1e9,
+                           "note": "wall time of engine.n2_solve_ensemble with device-resident results; bound: HBM "
+                                   "latency (work arrays streamed), see DESIGN.md 5.2"}}
 
     if rank == 0:
         steps = args.steps

@@ -78,10 +78,46 @@ __device__ __forceinline__ double rmt_exp_reduced(const double r, const int k)
     p = fma(p, r, 1.0);
     return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
 }
+// Table form: exp(x) = 2^k * 2^(j/32) * exp(r), |r| <= ln2/64, so a degree-6 polynomial is enough (truncation
+// 3.5e-18) — 13 FP64 instructions instead of 20 and a dependent chain of 7 instead of 14; the 32 table entries
+// (two cache lines) are read through the read-only path.  Same accuracy (<= 2 ulp), but measured no faster in the
+// integrator (16.09 vs 16.05 ms per 2^20 solves: the table load's latency eats the shorter chain) and 1 % slower
+// in the one-shot RHS kernel, so the polynomial-only form stays the default.
+#ifndef RMT_EXP_TABLE
+#define RMT_EXP_TABLE 0
+#endif
+__device__ const double RMT_EXP2_TAB[32] = {
+    1.0, 1.0218971486541166, 1.0442737824274138, 1.0671404006768237,
+    1.0905077326652577, 1.1143867425958924, 1.1387886347566916, 1.1637248587775775,
+    1.189207115002721, 1.215247359980469, 1.241857812073484, 1.2690509571917332,
+    1.2968395546510096, 1.3252366431597413, 1.3542555469368927, 1.383909881963832,
+    1.4142135623730951, 1.4451808069770467, 1.4768261459394993, 1.5091644275934228,
+    1.5422108254079407, 1.5759808451078865, 1.6104903319492543, 1.645755478153965,
+    1.681792830507429, 1.718619298122478, 1.7562521603732995, 1.7947090750031072,
+    1.8340080864093424, 1.8741676341103, 1.9152065613971474, 1.9571441241754002};
+__device__ __forceinline__ double rmt_exp_tab(const double r, const int n)
+{
+    // 2^(n/32) * exp(r): T*(1 + q), q = r + r^2 (1/2 + r/6 + ...), evaluated as fma(T, q, T)
+    double a = fma(r, 1.3888888888888889e-03, 8.3333333333333332e-03);   // 1/720, 1/120
+    a = fma(a, r, 4.1666666666666664e-02);
+    a = fma(a, r, 1.6666666666666666e-01);
+    a = fma(a, r, 0.5);
+    const double q = fma(r, a*r, r);
+    const double T = __ldg(&RMT_EXP2_TAB[n & 31]);
+    const double v = fma(T, q, T);
+    return __hiloint2double(__double2hiint(v) + ((n >> 5) << 20), __double2loint(v));
+}
 __device__ __forceinline__ double rmt_exp(double x)
 {
 #if RMT_EXACT_MATH
     return exp(x);
+#elif RMT_EXP_TABLE
+    x = fmin(fmax(x, -708.0), 709.0);
+    const double t = fma(x, 46.16624130844683, 6755399441055744.0);      // round(x*32/ln2) in the low word
+    const double nd = t - 6755399441055744.0;
+    double r = fma(nd, -0.02166084938653512, x);                          // ln2_hi/32 (exact product)
+    r = fma(nd, -5.9631716539705866e-12, r);                              // ln2_lo/32
+    return rmt_exp_tab(r, __double2loint(t));
 #else
     x = fmin(fmax(x, -708.0), 709.0);
     const double t = fma(x, 1.4426950408889634, 6755399441055744.0);     // round(x*log2(e)) in the low word
@@ -95,6 +131,16 @@ __device__ __forceinline__ double rmt_exp10(double x)
 {
 #if RMT_EXACT_MATH
     return exp10(x);
+#elif RMT_EXP_TABLE
+    x = fmin(fmax(x, -307.0), 308.0);
+    const double t = fma(x, 106.30169903639559, 6755399441055744.0);     // round(x*32*log2(10))
+    const double nd = t - 6755399441055744.0;
+    const double xh = x*2.302585092994045901e+00;
+    double r = fma(nd, -0.02166084938653512, xh);
+    r = fma(nd, -5.9631716539705866e-12, r);
+    r = fma(x, -2.1707562233822494e-16, r);                               // ln10 - ln10_hi
+    r += fma(x, 2.302585092994045901e+00, -xh);
+    return rmt_exp_tab(r, __double2loint(t));
 #else
     x = fmin(fmax(x, -307.0), 308.0);
     const double t = fma(x, 3.3219280948873622, 6755399441055744.0);     // round(x*log2(10))

@@ -37,7 +37,8 @@ Tref = 273.15 + 25.00       # core/constants.py:17-23
 
 # N1/N2 grid sizes, solvers/solSetting.py:30-39 (module-level mutable dict in
 # the reference; same here so tests can override zNo exactly as callers do).
-solverSetting = {"N1": {"zNo": 100}, "N2": {"zNo": 20, "rNo": 5, "tNo": 5, "timesNo": 5}, "M9": {"zNo": 30}}
+solverSetting = {"N1": {"zNo": 100}, "N2": {"zNo": 20, "rNo": 5, "tNo": 5, "timesNo": 5}, "M9": {"zNo": 30},
+                 "S2": {"tNo": 10, "zNo": 100, "rNo": 7, "timesNo": 5}}
 
 # ----------------------------------------------------------------------------
 # component data — data/componentData.py:11-22 (MW), :72-86 (dHf25),
@@ -535,6 +536,140 @@ class M7Oracle:
         return {"dataYs": dataYs, "XYList": XYList, "dataList": dataList, "nfev": sol.nfev, "solY": sol.y}
 
 
+class M9Oracle:
+    """Model M9 = PackedBedReactorClass.runM5 + modelEquationM5 (docs/pbReactor.py:1997-2660): the DIMENSIONAL
+    dynamic twin of N2.  Unknowns [C_i..., T] at zNo nodes (variable-major); pressure AND superficial velocity are
+    marched node by node inside the RHS (:2546-2612).  Grid/time settings come from solverSetting['S2']."""
+
+    def __init__(self, modelInput):
+        mi = self.modelInput = modelInput
+        self.P, self.T = mi['operating-conditions']['pressure'], mi['operating-conditions']['temperature']
+        self.opT = mi['operating-conditions']['period']
+        self.reactionList = list(mi['reactions'].values())
+        self.reactionListSorted, self.reactionStochCoeff = parse_reactions(mi['reactions'])
+        self.varis, self.rates = mi['reaction-rates']['VARS'], mi['reaction-rates']['RATES']
+        self.compList = list(mi['feed']['components']['shell'])
+        for c in self.compList:
+            if c not in componentSymbolList:
+                raise Exception("Component database is not up to date!")
+        self.compNo = nc = len(self.compList)
+        rs = self.ReSpec = mi['reactor']
+        self.ReLe, self.PaDi, self.BeVoFr = rs['ReLe'], rs['PaDi'], rs['BeVoFr']
+        self.CrSeAr = PI_CONST*(rs['ReInDi'] ** 2)/4                      # :2043
+        self.VoFlRa0 = mi['feed']['volumetric-flowrate']
+        self.SpCoi0 = np.array(mi['feed']['concentration'], dtype=float)
+        self.SpCo0 = np.sum(self.SpCoi0)
+        self.MoWei = [_DB[s][0] for s in self.compList]
+        self.ExHe = mi['external-heat']
+        self.GaMiVi = mi['feed']['mixture-viscosity']                     # :2069
+        s2 = solverSetting['S2']
+        self.zNo, self.tNo, self.timesNo = s2['zNo'], s2['tNo'], s2['timesNo']
+        self.dataXs = np.linspace(0, self.ReLe, self.zNo)
+        self.dz = self.ReLe/(self.zNo - 1)                                # :2076
+        self.varNo = nc + 1
+        IV2D = np.zeros((self.varNo, self.zNo))
+        for i in range(nc):
+            IV2D[i, :] = self.SpCoi0[i]
+        IV2D[nc, :] = self.T
+        self.IV = IV2D.flatten()                                          # :2090-2103
+        self.StHeRe25 = np.array([standard_enthalpy_of_reaction(r) for r in self.reactionList])
+
+    def rhs(self, t, y):
+        """modelEquationM5, :2296-2660."""
+        nc, zNo, dz = self.compNo, self.zNo, self.dz
+        BeVoFr, PaDi = self.BeVoFr, self.PaDi
+        CaDe, CaSpHeCa = self.ReSpec['CaDe'], self.ReSpec['CaSpHeCa']
+        InGaVe0 = self.VoFlRa0/(self.CrSeAr*BeVoFr)
+        SuGaVe0 = InGaVe0*BeVoFr                                          # :2421 (the feed's superficial-velocity is not used)
+        P_z = np.zeros(zNo + 1); P_z[0] = self.P
+        v_z = np.zeros(zNo + 1); v_z[0] = SuGaVe0
+        yLoop = np.reshape(y, (self.varNo, zNo))
+        SpCoi_z = yLoop[0:nc, :]
+        T_z = yLoop[nc, :]
+        dxdtMat = np.zeros((self.varNo, zNo))
+        MoWei = np.array(self.MoWei)
+        CoSpi = np.zeros(nc)
+        for z in range(zNo):
+            for i in range(nc):
+                CoSpi[i] = max(SpCoi_z[i][z], EPS_CONST)                  # :2487-2491
+            CoSp = np.sum(CoSpi)
+            T, P, v = T_z[z], P_z[z], v_z[z]
+            MoFri = CoSpi/np.sum(CoSpi)
+            SuGaVe = v
+            MoFlRa = CoSp*SuGaVe*self.CrSeAr
+            MoFl = MoFlRa/self.CrSeAr
+            MiMoWe = np.dot(MoFri, MoWei)*1e-3
+            GaDe = MiMoWe*CoSp                                            # calDensityIG (:2528)
+            ergA = 150*self.GaMiVi*SuGaVe/(PaDi**2)
+            ergB = ((1-BeVoFr)**2)/(BeVoFr**3)
+            ergC = 1.75*GaDe*(SuGaVe**2)/PaDi
+            ergD = (1-BeVoFr)/(BeVoFr**3)
+            dxdt_P = -1*(ergA*ergB + ergC*ergD)
+            P_z[z+1] = dxdt_P*dz + P_z[z]                                 # :2546
+            Ri = np.array(reaction_rate_exe((T_z[z], P_z[z], MoFri, CoSpi), self.varis, self.rates))
+            ri = component_formation_rate(nc, self.compList, self.reactionStochCoeff, Ri)
+            OvR = np.sum(ri)
+            CpMeanMixture = np.dot(MoFri, cp_mean_list(self.compList, T))
+            HeReT = np.array(np.array(enthalpy_change_of_reaction(self.reactionListSorted, T)) + self.StHeRe25)
+            OvHeReT = np.dot(Ri, HeReT)
+            Tm, U, a = self.ExHe['MeTe'], self.ExHe['OvHeTrCo'], self.ExHe['EfHeTrAr']
+            Qm = 0 if Tm == 0 else U*a*(Tm - T)                           # rmtUtility.py:424-452 with unit 'kJ/m^3.s'
+            if Qm != 0:
+                Qm = Qm*1e-3
+            T_b = self.T if z == 0 else T_z[z - 1]
+            dxdt_v_T = (T_z[z] - T_b)/dz
+            dxdt_v = (1/(CoSp*1000))*((-SuGaVe/R_CONST)*((1/T)*dxdt_P - (P/T**2)*dxdt_v_T) + OvR*1000)    # :2606-2608
+            v_z[z+1] = dxdt_v*dz + v_z[z]
+            const_F1 = 1/BeVoFr
+            const_T1 = MoFl*CpMeanMixture
+            const_T2 = 1/(CoSp*CpMeanMixture*BeVoFr + (1-BeVoFr)*CaDe*CaSpHeCa)
+            for i in range(nc):
+                Ci_c = SpCoi_z[i][z]
+                Ci_b = self.SpCoi0[i] if z == 0 else max(SpCoi_z[i][z - 1], EPS_CONST)
+                dCdz = (Ci_c - Ci_b)/dz
+                dxdtMat[i][z] = const_F1*(-v_z[z]*dCdz - Ci_c*dxdt_v + ri[i])
+            dTdz = (T_z[z] - T_b)/dz
+            dxdtMat[nc][z] = const_T2*(-const_T1*dTdz + (-OvHeReT + Qm))
+        return dxdtMat.flatten().tolist()
+
+    def solve(self, method=None, rtol=None, atol=None):
+        """Slab loop of runM5 :2161-2216 and the plot lists it returns (:2262-2294): the (x, y) series of the LAST
+        variable (temperature) at the end of every slab."""
+        ivp = self.modelInput['solver-config']['ivp']
+        method = method or ("LSODA" if ivp == 'default' else ivp)
+        kw = {}
+        if rtol is not None:
+            kw["rtol"] = rtol
+        if atol is not None:
+            kw["atol"] = atol
+        opTSpan = np.linspace(0, self.opT, self.tNo + 1)
+        IV = self.IV
+        nc, zNo = self.compNo, self.zNo
+        dataPack, nfev = [], 0
+        dataPacktime = np.zeros((self.varNo, self.tNo, zNo))
+        for i in range(self.tNo):
+            t = np.array([opTSpan[i], opTSpan[i+1]])
+            sol = solve_ivp(lambda tt, yy: self.rhs(tt, yy), t, IV, method=method,
+                            t_eval=np.linspace(t[0], t[1], self.timesNo), **kw)
+            if sol.success is False:
+                raise RuntimeError("ODE Error")
+            nfev += sol.nfev
+            C = np.reshape(sol.y[0:nc*zNo, -1], (nc, zNo))
+            Tr = np.array([sol.y[nc*zNo:(nc + 1)*zNo, -1]])
+            dataYs = np.concatenate((C/np.sum(C, axis=0), Tr), axis=0)
+            dataPack.append({"successStatus": sol.success, "dataTime": sol.t[-1], "dataYCons": C, "dataYTemp": Tr,
+                             "dataYs": dataYs, "solY": sol.y[:, -1]})
+            for m in range(self.varNo):
+                dataPacktime[m][i, :] = dataYs[m, :]
+            IV = sol.y[:, -1]
+        self.nfev = nfev
+        labelList = self.compList.copy() + ["Temperature"]
+        XYList = [[self.dataXs, item] for item in dataPacktime[self.varNo - 1]]
+        names = [labelList[self.varNo - 1] + " at t=" + str(opTSpan[t + 1]) for t in range(self.tNo)]
+        dataList = [{"x": XYList[i][0], "y": XYList[i][1], "leg": names[i]} for i in range(len(XYList))]
+        return {"XYList": XYList, "dataList": dataList, "dataPack": dataPack}
+
+
 def rmtExe(modelInput, method=None, rtol=None, atol=None):
     """rmt.py:21-80 restricted to the N1/N2 branch of rmtCore.py:63-127."""
     if modelInput['model'] == "N1":
@@ -547,6 +682,8 @@ def rmtExe(modelInput, method=None, rtol=None, atol=None):
     elif modelInput['model'] == "N2":
         o = N2Oracle(modelInput)
         res = o.solve(method=method, rtol=rtol, atol=atol)
+    elif modelInput['model'] == "M9":
+        res = M9Oracle(modelInput).solve(method=method, rtol=rtol, atol=atol)
     elif modelInput['model'] == "M7":
         o = M7Oracle(modelInput)
         sol = o.solve(method=method, rtol=rtol, atol=atol)

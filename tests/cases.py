@@ -231,6 +231,24 @@ def methanol_m7_input(ivp="default"):
     }
 
 
+def methanol_m9_input(ivp="default", period=2.0):
+    """`PyREMOT/tests/test_rmt_DME5.py:20-232` instance: model M9, the dimensional dynamic twin of N2
+    (pbReactor.py runM5 :1997-2660).  Concentrations in kmol/m^3 and rates in kmol/(m^3 s) as that script has them
+    (its RATES lack the factor 1000 of the M7 script)."""
+    mi = methanol_m7_input(ivp)
+    kin = mi["reaction-rates"]
+    rates = {
+        "r1": lambda x: x['K1']*(x['ra1']/(math.pow(x['ra2'], 3)))*(1-x['ra3'])*x['CaBeDe'],
+        "r2": lambda x: x['K2']*(1/x['ra2'])*x['ra4']*x['CaBeDe'],
+        "r3": lambda x: x['K3']*x['ra5']*x['CaBeDe'],
+    }
+    mi["model"] = "M9"
+    mi["operating-conditions"] = dict(mi["operating-conditions"], period=period)
+    mi["feed"] = dict(mi["feed"], concentration=np.array(mi["feed"]["concentration"])/1000, **{"superficial-velocity": 0.2})
+    mi["reaction-rates"] = {"VARS": kin["VARS"], "RATES": rates}
+    return mi
+
+
 def ch4_input(model="N1", process_type="non-iso-thermal", ivp="default"):
     """Methane-coupling instance of `PyREMOT/tests/test_rmt_N2_CH4.py:23-250`
     (SURVEY.md App. B.5)."""

@@ -309,6 +309,49 @@ def part_m7():
     print("m7 done: default nfev %d wall %.2f, tight nfev %d" % (c["nfev"], wall, ct["nfev"]))
 
 
+def part_m9():
+    """Model M9 (pbReactor.runM5, the dimensional dynamic twin of N2): RHS known answers and the slab-end states of
+    a default-tolerance run, on a 12-node grid (solverSetting['S2'] is the reference's module-level setting)."""
+    PyREMOT, H, solverSetting = load_reference()
+    import PyREMOT.docs.pbReactor as PB
+    PB.pltc.plots2DSub = staticmethod(lambda *a, **k: None)      # runM5 always plots (pbReactor.py:2243-2246)
+    old = dict(solverSetting["S2"])
+    solverSetting["S2"].update(zNo=12, tNo=3)
+    rng = np.random.default_rng(17)
+    out = {}
+    orig = PB.solve_ivp
+    calls = []
+
+    def patched(fun, t_span, y0, **kw):
+        sol = orig(fun, t_span, y0, **kw)
+        calls.append(dict(fun=fun, y0=np.array(y0, float), args=kw.get("args"), nfev=sol.nfev, y=sol.y, t=sol.t))
+        return sol
+    PB.solve_ivp = patched
+    try:
+        res, wall = run_ref(PyREMOT, cases.methanol_m9_input())
+    finally:
+        PB.solve_ivp = orig
+        solverSetting["S2"].update(old)
+    rm = res["resModel"]
+    out["default__T_profiles"] = np.array([xy[1] for xy in rm["XYList"]])            # temperature at the end of each slab
+    out["default__x"] = np.array(rm["XYList"][0][0])
+    out["default__legends"] = np.array([d["leg"] for d in rm["dataList"]])
+    out["default__slab_end_states"] = np.array([c["y"][:, -1] for c in calls])       # [tNo][(nc+1)*zNo]
+    out["default__nfev_wall"] = np.array([sum(c["nfev"] for c in calls), wall])
+    fun, args = calls[0]["fun"], calls[0]["args"]
+    Y = [calls[0]["y0"]] + [c["y"][:, k] for c in calls for k in (1, -1)]
+    for c in calls:
+        for _ in range(2):
+            Y.append(c["y"][:, -1]*(1 + 0.05*rng.uniform(-1, 1, c["y"].shape[0])))
+    neg = np.array(calls[0]["y"][:, 2]); neg[[29, 41, 64]] = -1e-9                    # clamped entries (:2487-2491): H2O, CO, DME
+    Y.append(neg)
+    Y = np.array(Y)
+    out["rhs_Y"] = Y
+    out["rhs_F"] = np.array([fun(0.0, y, *args) for y in Y])
+    np.savez_compressed(os.path.join(HERE, "m9_reference.npz"), **out)
+    print("m9 done: nfev %d wall %.1f s, %d RHS states" % (out["default__nfev_wall"][0], wall, len(Y)))
+
+
 def part_props():
     """Component-table known answers: Cp_i(T), viscosity_i(T), dHf25, MW for all 12 species,
     Wilke mixture viscosity and reaction parsing, straight from the reference's helpers."""
@@ -344,6 +387,8 @@ if __name__ == "__main__":
             part_corners()
         elif part == "m7":
             part_m7()
+        elif part == "m9":
+            part_m9()
         elif part == "props":
             part_props()
         elif part == "n2rhs":

@@ -45,7 +45,8 @@ typedef uint64_t rmt_module_t;   /* module loaded on the current device       */
 /* model description read back from a loaded module */
 typedef struct rmt_module_info {
     int32_t model;        /* 1 = N1, 2 = N2, 7 = M7 (dimensional twin of N1;    */
-                          /* served by the rmt_n1_* entry points)               */
+                          /* served by the rmt_n1_* entry points), 9 = M9       */
+                          /* (dimensional twin of N2; rmt_n2_* entry points)    */
     int32_t n;            /* unknowns per axial point                          */
     int32_t nc;           /* species                                           */
     int32_t nr;           /* reactions                                         */
@@ -92,8 +93,9 @@ int rmt_module_free(rmt_module_t m);
  * nin) is the row of input q in d_rows or -1, in which case uniform[q] is used
  * for every instance.  Input order: temperature, pressure, concentration[nc],
  * volumetric-flowrate, ReInDi, ReLe, PaDi, BeVoFr, OvHeTrCo, MeTe,
- * mixture-viscosity, EfHeTrAr (the last two are read by model M7 only), then the
- * scalar VARS entries in VARS order.  d_consts [nconst][B]. */
+ * mixture-viscosity, EfHeTrAr (read by the dimensional models M7 / M9 only), CaDe,
+ * CaSpHeCa (M9 only), then the scalar VARS entries in VARS order.
+ * d_consts [nconst][B]. */
 int rmt_setup(rmt_module_t m, int64_t B, const double* d_rows, int32_t n_rows, const int32_t* row_map,
               const double* uniform, double* d_consts, void* stream);
 

@@ -231,7 +231,9 @@ def generate_model_header(spec, tableau="rodas4", reduced=None, lanes=1):
     A("#ifndef RMT_REDUCED")
     A("#define RMT_REDUCED %d" % (1 if reduced else 0))
     A("#endif")
-    if spec.model == "N2":
+    if spec.model == "M9" and lanes != 1:
+        raise ValueError("M9 marches the velocity through the kinetics node by node: one lane per reactor")
+    if spec.model in ("N2", "M9"):
         if lanes not in (1, 2, 4, 8, 16, 32):
             raise ValueError("lanes per reactor must be a power of two <= 32")
         A("// threads per reactor of the dynamic integrator (nodes evaluated in parallel)")

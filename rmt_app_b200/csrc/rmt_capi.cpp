@@ -402,8 +402,9 @@ int rmt_module_load(const void* cubin, size_t size, rmt_module_t* module_out)
     M->f_peak = get("rmt_dfma_peak");
     M->f_probe = get("rmt_math_probe");
     if (!M->f_setup) { drv.p_cuModuleUnload(M->mod); delete M; return fail("module lacks rmt_setup"); }
-    CUfunction fs = I.model != 2 ? M->f_n1_solve : M->f_n2_solve;
-    if (fs && I.model != 2) {
+    const bool dynamic = I.model == 2 || I.model == 9;       // N2 and its dimensional twin M9: rmt_n2_* entry points
+    CUfunction fs = !dynamic ? M->f_n1_solve : M->f_n2_solve;
+    if (fs && !dynamic) {
         M->solve_smem = (size_t)I.block*8*((size_t)I.m*I.m + (size_t)I.stages*I.m);
         CU(cuFuncSetAttribute(fs, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)M->solve_smem));
         CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&M->solve_blocks_per_sm, fs, I.block, M->solve_smem));
@@ -506,7 +507,7 @@ int rmt_n1_solve(rmt_module_t m, int64_t B, const double* d_consts, int32_t n_ev
     Module* M = get_module(m);
     if (!M) return fail("invalid module handle");
     if (ensure_ctx()) return 1;
-    if (M->info.model == 2) return fail("rmt_n1_solve: module was generated for model N2");
+    if (M->info.model == 2 || M->info.model == 9) return fail("rmt_n1_solve: module was generated for a dynamic model (N2/M9)");
     if (B <= 0 || n_eval < 1 || !z_eval) return fail("rmt_n1_solve: need B > 0 and at least one output position");
     for (int e = 1; e < n_eval; ++e)
         if (!(z_eval[e] > z_eval[e - 1])) return fail("rmt_n1_solve: z_eval must be strictly increasing");
@@ -580,7 +581,7 @@ int rmt_n2_rhs(rmt_module_t m, int64_t B, int32_t zNo, const double* d_consts, c
     Module* M = get_module(m);
     if (!M) return fail("invalid module handle");
     if (ensure_ctx()) return 1;
-    if (M->info.model != 2) return fail("rmt_n2_rhs: module was generated for model N1");
+    if (M->info.model != 2 && M->info.model != 9) return fail("rmt_n2_rhs: module was generated for a steady-state model");
     if (zNo < 2) return fail("rmt_n2_rhs: zNo must be >= 2");
     CUdeviceptr c = (CUdeviceptr)d_consts, y = (CUdeviceptr)d_y, f = (CUdeviceptr)d_f;
     long long b = B;
@@ -606,7 +607,8 @@ int64_t rmt_n2_work_doubles(rmt_module_t m, int64_t B, int32_t zNo)
     const int64_t n = M->info.n, s = M->info.stages;
     // per node and integrator thread: y_n, y_{n+1}, s stage vectors, W_kk^{-1} (n x n), upwind / pressure
     // coupling vectors (3n), d E/d P
-    const int64_t rows = n*(5 + s + n) + 1;
+    // (M9 adds the velocity march: two more coupling vectors, one more gradient vector, four scalars)
+    const int64_t rows = n*(5 + s + n) + 1 + (M->info.model == 9 ? 3*n + 4 : 0);
     const int64_t groups = (zNo + M->info.lanes - 1)/M->info.lanes;      // node groups, one node per lane
     return rows*groups*n2_slots(M, B);
 }
@@ -618,7 +620,7 @@ int rmt_n2_solve(rmt_module_t m, int64_t B, int32_t zNo, int32_t tNo, double per
     Module* M = get_module(m);
     if (!M) return fail("invalid module handle");
     if (ensure_ctx()) return 1;
-    if (M->info.model != 2) return fail("rmt_n2_solve: module was generated for model N1");
+    if (M->info.model != 2 && M->info.model != 9) return fail("rmt_n2_solve: module was generated for a steady-state model");
     if (B <= 0 || zNo < 2 || tNo < 1 || !(period > 0.0)) return fail("rmt_n2_solve: need B > 0, zNo >= 2, tNo >= 1, period > 0");
     if (!(rtol > 0.0) || !(atol >= 0.0)) return fail("rmt_n2_solve: rtol must be > 0 and atol >= 0");
     if (!d_work) return fail("rmt_n2_solve: d_work is required (rmt_n2_work_doubles)");

@@ -235,6 +235,12 @@ __device__ __forceinline__ double rmt_sqrt(const double x)
 #if defined(RMT_MODEL_N1) || defined(RMT_MODEL_M7)
 #define RMT_STEADY 1
 #endif
+#if defined(RMT_MODEL_M7) || defined(RMT_MODEL_M9)
+#define RMT_DIMENSIONAL 1                        // pbReactor.py twins: no scaling, viscosity and exchange area are inputs
+#endif
+#if defined(RMT_MODEL_N2) || defined(RMT_MODEL_M9)
+#define RMT_DYNAMIC 1                            // method-of-lines models served by the rmt_n2_* kernels
+#endif
 #if defined(RMT_MODEL_M7)
 #define RMT_N (RMT_NC + 2)                       // Ci [mol/m^3]..., T [K], P [Pa]
 #define RMT_IT RMT_NC
@@ -310,6 +316,8 @@ extern "C" __global__ void rmt_meta(int* out)
     out[0] = 1;
 #elif defined(RMT_MODEL_M7)
     out[0] = 7;
+#elif defined(RMT_MODEL_M9)
+    out[0] = 9;
 #else
     out[0] = 2;
 #endif
@@ -321,7 +329,7 @@ extern "C" __global__ void rmt_meta(int* out)
 #else
     out[14] = 0;
 #endif
-#if defined(RMT_MODEL_N2)
+#if defined(RMT_MODEL_N2) || defined(RMT_MODEL_M9)
     out[15] = RMT_N2_G;
 #else
     out[15] = 1;
@@ -334,7 +342,8 @@ extern "C" __global__ void rmt_meta(int* out)
 enum {
     IN_T = 0, IN_P = 1, IN_C0 = 2,
     IN_Q = 2 + RMT_NC, IN_D, IN_L, IN_DP, IN_EPS, IN_U, IN_TM,
-    IN_MUG, IN_AEX,            // feed.mixture-viscosity and external-heat.EfHeTrAr: read by M7 only
+    IN_MUG, IN_AEX,            // feed.mixture-viscosity and external-heat.EfHeTrAr: read by M7 / M9 only
+    IN_CADE, IN_CASP,          // reactor.CaDe, reactor.CaSpHeCa: M9's energy balance only (pbReactor.py:2619)
     IN_KP0
 };
 static_assert(IN_KP0 + RMT_NKP == RMT_NIN, "input row count");
@@ -402,8 +411,8 @@ extern "C" __global__ void __launch_bounds__(128) rmt_setup(const RmtInputs in, 
 #else
     const double vf = us0;                                   // :3452
 #endif
-#if defined(RMT_MODEL_M7)
-    const double a = rmt_in(in, IN_AEX, i);                  // M7 uses EfHeTrAr as given (pbReactor.py:1508)
+#if defined(RMT_DIMENSIONAL)
+    const double a = rmt_in(in, IN_AEX, i);                  // M7 / M9 use EfHeTrAr as given (pbReactor.py:1508, :2589)
 #else
     const double a = 4/D;                                    // :2778 (EfHeTrAr input ignored)
 #endif
@@ -435,8 +444,8 @@ extern "C" __global__ void __launch_bounds__(128) rmt_setup(const RmtInputs in, 
         }
         mumix += (mu[p]*y0[p])/den;
     }
-#if defined(RMT_MODEL_M7)
-    mumix = rmt_in(in, IN_MUG, i);                           // feed.mixture-viscosity (pbReactor.py:1235)
+#if defined(RMT_DIMENSIONAL)
+    mumix = rmt_in(in, IN_MUG, i);                           // feed.mixture-viscosity (pbReactor.py:1235, :2069)
 #endif
     const double T2 = T*T, T3 = T*T*T;
     double Cpf = 0.0, MWf = 0.0;
@@ -466,14 +475,18 @@ extern "C" __global__ void __launch_bounds__(128) rmt_setup(const RmtInputs in, 
 #if defined(RMT_STEADY)
     c[(i64)H_X0*B] = L/P;                  // 1/(Pf/zf), the Ergun scale (N1)
     c[(i64)H_X1*B] = 0.0;
+#elif defined(RMT_MODEL_M9)
+    c[(i64)H_X0*B] = 1/eps;                // const_F1, pbReactor.py:2615
+    c[(i64)H_X1*B] = (1 - eps)*rmt_in(in, IN_CADE, i)*rmt_in(in, IN_CASP, i);      // catalyst term of const_T2, :2619
+    c[(i64)H_EPSCPF*B] = eps;
 #else
     c[(i64)H_X0*B] = 1/(eps*(L/vf));       // const_F1, :4075
     c[(i64)H_X1*B] = 1/(L/vf);
 #endif
 #pragma unroll
     for (int k = 0; k < RMT_NC; ++k)
-#if defined(RMT_MODEL_M7)
-        c[(i64)(K_IV0 + k)*B] = C0i[k];            // dimensional initial state (pbReactor.py:1240-1246)
+#if defined(RMT_DIMENSIONAL)
+        c[(i64)(K_IV0 + k)*B] = C0i[k];            // dimensional initial state (pbReactor.py:1240-1246, :2090-2103)
 #else
         c[(i64)(K_IV0 + k)*B] = C0i[k]/Cmax;       // :2833 / :3489
 #endif
@@ -488,8 +501,11 @@ struct Hot {
 #if defined(RMT_STEADY)
     double invBeta;              // zf/Pf
 #else
-    double F1, invZv;            // 1/(eps*(zf/vf)), vf/zf
-    double iv[RMT_NC];           // inlet boundary values C0_i/Cmax
+    double F1, invZv;            // N2: 1/(eps*(zf/vf)), vf/zf;  M9: 1/eps, (1-eps)*CaDe*CaSpHeCa (epsCpf holds eps)
+    double iv[RMT_NC];           // inlet boundary values C0_i/Cmax (M9: C0_i)
+#if defined(RMT_MODEL_M9)
+    double zf;                   // reactor length [m]: the grid is dimensional
+#endif
 #endif
     double kp[RMT_NKP > 0 ? RMT_NKP : 1];
 };
@@ -512,6 +528,9 @@ __device__ __forceinline__ void rmt_load_hot(const double* __restrict__ consts, 
     h.invZv = __ldg(c + (i64)H_X1*B);
 #pragma unroll
     for (int k = 0; k < RMT_NC; ++k) h.iv[k] = __ldg(c + (i64)(K_IV0 + k)*B);
+#if defined(RMT_MODEL_M9)
+    h.zf = __ldg(c + (i64)K_ZF*B);
+#endif
 #endif
 #pragma unroll
     for (int k = 0; k < RMT_NKP; ++k) h.kp[k] = __ldg(c + (i64)(K_KP0 + k)*B);
@@ -1600,7 +1619,7 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
 }
 #endif  // RMT_STEADY
 
-#if defined(RMT_MODEL_N2)
+#if defined(RMT_DYNAMIC)
 // ---------------------------------------------------------------------------------
 // N2: dynamic model by the method of lines (modelEquationN2, pbHomoReactor.py:3706-4134).
 // State yhat[(nc+1)][zNo] variable-major as in the reference (:3873); on the device
@@ -1616,6 +1635,15 @@ struct NodeJac {                             // derivative blocks of one node
     double L[RMT_N];                         // d f_k / d u_{k-1}  (diagonal: upwind differences)
     double e[RMT_N];                         // d E_k / d u_k
     double ep;                               // d E_k / d P_k
+#if defined(RMT_MODEL_M9)
+    // M9 marches the superficial velocity as well (v_{k+1} = v_k + dz*V_k, pbReactor.py:2606-2612), and V_k sees
+    // the temperature of the node before (dT/dz), which puts a T_{k-1} column into every species balance
+    double gv[RMT_N];                        // d f_k / d v_k
+    double Lt[RMT_N];                        // d f_k / d T_{k-1} beyond the diagonal (species rows)
+    double ev;                               // d E_k / d v_k
+    double eV[RMT_N];                        // d V_k / d u_k
+    double eVb, eVP, eVv;                    // d V_k / d T_{k-1}, d P_k, d v_k
+#endif
 };
 
 // f_k and the Ergun gradient E_k [Pa/m] at one node.  u: node state, ub: upwind node state (or the
@@ -1739,6 +1767,147 @@ __device__ __forceinline__ void n2_node(const double (&u)[RMT_N], const double (
     }
 }
 
+#if defined(RMT_MODEL_M9)
+// ---------------------------------------------------------------------------------
+// M9 node (modelEquationM5, docs/pbReactor.py:2296-2660): the dimensional twin of the N2 node.  u = (C_i
+// [kmol/m^3 in the reference's own script], T [K]); pressure P and superficial velocity v at the node come from the
+// marches P_{k+1} = P_k + dz*E_k (:2546) and v_{k+1} = v_k + dz*V_k (:2606-2612).  Differences from N2 besides the
+// scaling: rho = MW*C (not the EOS density), the velocity is not frozen, species balances carry -C_i*dv/dz, the
+// energy balance has the catalyst's heat capacity, the coolant duty is in kJ.
+// ---------------------------------------------------------------------------------
+template <bool JAC>
+__device__ __forceinline__ void m9_node(const double (&u)[RMT_N], const double (&ub)[RMT_N], const bool inlet,
+                                        const double P, const double v, const double invdz, const Hot& h,
+                                        double (&f)[RMT_N], double& E, double& V, NodeJac& nj)
+{
+    double C[RMT_NC];
+#pragma unroll
+    for (int i = 0; i < RMT_NC; ++i) C[i] = fmax(u[i], RMT_EPS_CONST);            // :2487-2491
+    const double T = u[RMT_ITN];
+    Point p; PointJac pj;
+    rmt_point<JAC>(C, T, P, h, p, pj);
+    const double gade = p.MWm*p.S;                                                 // calDensityIG, :2528
+    E = -1*(h.ergA*v + h.ergC*gade*(v*v));                                         // :2534-2544
+    double OvR = 0.0;
+#pragma unroll
+    for (int i = 0; i < RMT_NC; ++i) OvR += p.r[i];                                // :2559
+    const double Qm = p.Qm*1e-3;                                                   // 'kJ/m^3.s', rmtUtility.py:446-447
+    const double tb = inlet ? h.Tf : ub[RMT_ITN];                                  // :2597-2600
+    const double dTdz = (T - tb)*invdz;
+    const double invT = rmt_rcp(T);
+    const double PT2 = P*invT*invT;
+    const double a1 = rmt_rcp(p.S*1000);
+    const double vR = -v*(1.0/RMT_R_CONST);
+    const double br = invT*E - PT2*dTdz;                                           // (1/T)*dP/dz - (P/T^2)*dT/dz
+    V = a1*(vR*br + OvR*1000);                                                     // :2606-2608
+    double cb[RMT_NC];
+#pragma unroll
+    for (int i = 0; i < RMT_NC; ++i) {
+        cb[i] = inlet ? h.iv[i] : fmax(ub[i], RMT_EPS_CONST);
+        f[i] = h.F1*(-v*((u[i] - cb[i])*invdz) - u[i]*V + p.r[i]);                 // :2626-2640 (centre value un-clamped)
+    }
+    const double SCp = p.S*p.Cp;
+    const double Svc = (p.S*v)*p.Cp;                                               // const_T1 = MoFl*CpMeanMixture
+    const double invD = rmt_rcp(SCp*h.epsCpf + h.invZv);                           // const_T2, :2619
+    f[RMT_ITN] = invD*(-Svc*dTdz + (-p.q + Qm));                                   // :2651
+    if (JAC) {
+        const double invS = p.invS;
+        double sy[RMT_NR];
+#pragma unroll
+        for (int j = 0; j < RMT_NR; ++j) {
+            double a = 0.0;
+#if RMT_RATES_DEP_Y
+#pragma unroll
+            for (int i = 0; i < RMT_NC; ++i) a += pj.dRdy[j][i]*p.y[i];
+#endif
+            sy[j] = a;
+        }
+        nj.ev = -1*(h.ergA + 2.0*h.ergC*gade*v);
+        nj.ep = 0.0;
+        // columns: local species, local temperature, pressure (col == RMT_N), velocity (col == RMT_N + 1)
+#pragma unroll
+        for (int col = 0; col <= RMT_N + 1; ++col) {
+            const bool isC = col < RMT_NC, isT = col == RMT_ITN, isP = col == RMT_N, isV = col == RMT_N + 1;
+            const int c = col < RMT_NC ? col : 0;
+            double dS = 0.0, dE = 0.0, dSCp = 0.0, dR[RMT_NR];
+#pragma unroll
+            for (int j = 0; j < RMT_NR; ++j) dR[j] = 0.0;
+            if (isC) {
+                const double sc = (u[c] > RMT_EPS_CONST) ? 1.0 : 0.0;             // d max(u, eps)/du
+                dS = sc;
+                dE = -1*h.ergC*(v*v)*(sc*1e-3*RMT_cMW[c]);
+                dSCp = sc*p.cpm[c];
+#pragma unroll
+                for (int j = 0; j < RMT_NR; ++j) {
+                    double a = 0.0;
+#if RMT_RATES_DEP_Y
+                    a = (pj.dRdy[j][c] - sy[j])*invS;
+#endif
+#if RMT_RATES_DEP_C
+                    a += pj.dRdC[j][c];
+#endif
+                    dR[j] = sc*a;
+                }
+            } else if (isT) {
+                dSCp = p.S*pj.dCpdT;
+#pragma unroll
+                for (int j = 0; j < RMT_NR; ++j) dR[j] = pj.dRdT[j];
+            } else if (isP) {
+#pragma unroll
+                for (int j = 0; j < RMT_NR; ++j) dR[j] = pj.dRdP[j];
+            } else {
+                dE = nj.ev;
+            }
+            double dr[RMT_NC], dOvR = 0.0;
+#pragma unroll
+            for (int i = 0; i < RMT_NC; ++i) {
+                double a = 0.0;
+#pragma unroll
+                for (int j = 0; j < RMT_NR; ++j) if (RMT_NU[j][i] != 0.0) a += RMT_NU[j][i]*dR[j];
+                dr[i] = a; dOvR += a;
+            }
+            double dbr;                                                            // d(vR*br)
+            if (isC) dbr = vR*(invT*dE);
+            else if (isT) dbr = vR*(-(E*invT*invT) + 2.0*PT2*invT*dTdz - PT2*invdz);
+            else if (isP) dbr = vR*(-(invT*invT)*dTdz);
+            else dbr = -(1.0/RMT_R_CONST)*br + vR*(invT*dE);
+            const double dV = a1*(dbr + 1000*dOvR) - V*dS*invS;
+#pragma unroll
+            for (int i = 0; i < RMT_NC; ++i) {
+                double val = h.F1*(-u[i]*dV + dr[i]);
+                if (isC && i == col) val -= h.F1*(v*invdz + V);
+                if (isV) val -= h.F1*((u[i] - cb[i])*invdz);
+                if (isP) nj.g[i] = val; else if (isV) nj.gv[i] = val; else nj.A[i][col < RMT_N ? col : 0] = val;
+            }
+            double dq = 0.0;
+#pragma unroll
+            for (int j = 0; j < RMT_NR; ++j) dq += dR[j]*p.dH[j];
+            double dN = -v*dTdz*dSCp - dq;
+            if (isT) {
+#pragma unroll
+                for (int j = 0; j < RMT_NR; ++j) dN -= p.R[j]*pj.ddHdT[j];
+                dN += -Svc*invdz + ((h.Tm == 0.0) ? 0.0 : -h.Ua*1e-3);
+            }
+            if (isV) dN -= SCp*dTdz;
+            const double valT = (dN - f[RMT_ITN]*(h.epsCpf*dSCp))*invD;
+            if (isP) { nj.g[RMT_ITN] = valT; nj.eVP = dV; }
+            else if (isV) { nj.gv[RMT_ITN] = valT; nj.eVv = dV; }
+            else { nj.A[RMT_ITN][col < RMT_N ? col : 0] = valT; nj.e[col < RMT_N ? col : 0] = dE; nj.eV[col < RMT_N ? col : 0] = dV; }
+        }
+        // node before: upwind concentrations (diagonal) and its temperature (through dT/dz in V and in the energy balance)
+        const double dVb = inlet ? 0.0 : a1*(vR*(PT2*invdz));
+        nj.eVb = dVb;
+#pragma unroll
+        for (int i = 0; i < RMT_NC; ++i) {
+            nj.L[i] = inlet ? 0.0 : ((ub[i] > RMT_EPS_CONST) ? h.F1*(v*invdz) : 0.0);
+            nj.Lt[i] = h.F1*(-u[i]*dVb);
+        }
+        nj.L[RMT_ITN] = inlet ? 0.0 : (Svc*invdz)*invD;
+        nj.Lt[RMT_ITN] = 0.0;
+    }
+}
+#endif  // RMT_MODEL_M9
+
 // stand-alone batched RHS: y [n][zNo][B] -> f [n][zNo][B]
 extern "C" __global__ void __launch_bounds__(64)
 rmt_n2_rhs(const double* __restrict__ consts, const i64 B, const int zNo, const double* __restrict__ y, double* __restrict__ f)
@@ -1746,15 +1915,27 @@ rmt_n2_rhs(const double* __restrict__ consts, const i64 B, const int zNo, const 
     const i64 i = (i64)blockIdx.x*blockDim.x + threadIdx.x;
     if (i >= B) return;
     Hot h; rmt_load_hot(consts, B, i, h);
+#if defined(RMT_MODEL_M9)
+    const double dz = h.zf/(zNo - 1);                                              // pbReactor.py:2076
+#else
     const double dz = 1.0/(zNo - 1);                                               // :3439
+#endif
     const double invdz = 1.0/dz;
     double P = h.Pf;                                                               // P_z[0] = P0, :3848
     double ub[RMT_N] = {0}, u[RMT_N], fo[RMT_N], E;
     NodeJac nj;
+#if defined(RMT_MODEL_M9)
+    double vs = h.us0, V;                                                          // v_z[0] = SuGaVe0, pbReactor.py:2433
+#endif
     for (int k = 0; k < zNo; ++k) {
 #pragma unroll
         for (int v = 0; v < RMT_N; ++v) u[v] = y[((i64)v*zNo + k)*B + i];
+#if defined(RMT_MODEL_M9)
+        m9_node<false>(u, ub, k == 0, P, vs, invdz, h, fo, E, V, nj);
+        vs = V*dz + vs;                                                            // pbReactor.py:2612
+#else
         n2_node<false>(u, ub, k == 0, P, invdz, h, fo, E, nj);
+#endif
 #pragma unroll
         for (int v = 0; v < RMT_N; ++v) { f[((i64)v*zNo + k)*B + i] = fo[v]; ub[v] = u[v]; }
         P = E*dz + P;                                                              // :3979 (dimensionless dz, kept)
@@ -1790,7 +1971,13 @@ struct SolveArgsN2 {
 // rows of the per-node work record
 enum {
     W_Y0 = 0, W_Y1 = RMT_N, W_K = 2*RMT_N, W_LU = W_K + RMT_ROS_S*RMT_N, W_L = W_LU + RMT_N*RMT_N,
-    W_G = W_L + RMT_N, W_E = W_G + RMT_N, W_EP = W_E + RMT_N, W_ROWS = W_EP + 1
+    W_G = W_L + RMT_N, W_E = W_G + RMT_N, W_EP = W_E + RMT_N,
+#if defined(RMT_MODEL_M9)
+    W_GV = W_EP + 1, W_LT = W_GV + RMT_N, W_EV = W_LT + RMT_N, W_S4 = W_EV + RMT_N,     // velocity-march couplings
+    W_ROWS = W_S4 + 4
+#else
+    W_ROWS = W_EP + 1
+#endif
 };                               // W_LU holds W_kk^{-1} (n x n, row-major)
 
 // solve with LU factors held in registers (rows permuted in place, reciprocal pivots on the diagonal)
@@ -1861,6 +2048,35 @@ __device__ __forceinline__ double n2_pressure_chain(const double Pin, const doub
     return P;
 }
 
+// One node group of a sweep: pressures (M9: and velocities) at the nodes, then the node functions.  Pg (vg) enter as
+// the values at the group's first node and leave as those of the next group's.
+template <bool JAC>
+__device__ __forceinline__ void dyn_eval(const double (&u)[RMT_N], const double (&ub)[RMT_N], const bool inlet,
+                                         double& Pg, double& vg, const double dz, const double invdz, const Hot& h,
+                                         const int g, const unsigned gmask, double (&f)[RMT_N], NodeJac& nj)
+{
+    double E;
+#if defined(RMT_MODEL_M9)
+    static_assert(RMT_N2_G == 1, "M9: the velocity march runs through the kinetics, one lane per reactor");
+    double V;
+    m9_node<JAC>(u, ub, inlet, Pg, vg, invdz, h, f, E, V, nj);
+    Pg = E*dz + Pg;                                                                // pbReactor.py:2546
+    vg = V*dz + vg;                                                                // pbReactor.py:2612
+    (void)g; (void)gmask;
+#else
+#if RMT_ISO
+    const double Tn = 0.0*h.Tf + h.Tf;
+#else
+    const double Tn = u[RMT_ITN]*h.Tf + h.Tf;
+#endif
+    double Pnext;
+    const double P = n2_pressure_chain(Pg, n2_mw(u, h), Tn, h, dz, g, gmask, Pnext);
+    n2_node<JAC>(u, ub, inlet, P, invdz, h, f, E, nj);
+    Pg = Pnext;
+    (void)vg;
+#endif
+}
+
 #ifndef RMT_N2_MINBLOCKS
 #define RMT_N2_MINBLOCKS 1
 #endif
@@ -1890,7 +2106,9 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
     const int zNo = a.zNo, NG = (zNo + G - 1)/G;
     double* w = a.work + tid;
 #define WK(row, kg) w[((i64)(row)*NG + (kg))*threads]
+#if !defined(RMT_MODEL_M9)
     const double dz = 1.0/(zNo - 1), invdz = 1.0/dz;
+#endif
     const double SAFE = a.ctrl[0], FAC1 = a.ctrl[1], FAC2 = 1.0/a.ctrl[2], KAPPA = a.ctrl[3], BETA = a.ctrl[4];
 
     i64 inst = -1;
@@ -1918,7 +2136,9 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
                     for (int kg = 0; kg < NG; ++kg) {                    // IV: feed composition at every node, T-hat = 0 (:3483-3497)
 #pragma unroll
                         for (int v = 0; v < RMT_NC; ++v) WK(W_Y0 + v, kg) = h.iv[v];
-#if !RMT_ISO
+#if defined(RMT_MODEL_M9)
+                        WK(W_Y0 + RMT_ITN, kg) = h.Tf;                   // pbReactor.py:2099-2100
+#elif !RMT_ISO
                         WK(W_Y0 + RMT_ITN, kg) = 0.0;
 #endif
                     }
@@ -1936,10 +2156,13 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
         if (__syncthreads_and(inst < 0)) break;
         const bool live = inst >= 0;
         const int YN = cur ? W_Y1 : W_Y0, YP = cur ? W_Y0 : W_Y1;
+#if defined(RMT_MODEL_M9)
+        const double dz = h.zf/(zNo - 1), invdz = 1.0/dz;       // dimensional grid, pbReactor.py:2076
+#endif
 
         if (fresh) {
             // starting step from ||y0|| / ||f(y0)|| (Hairer-Wanner II.4, first guess), scaled like N1
-            double d0 = 0.0, d1 = 0.0, Pg = h.Pf, E;
+            double d0 = 0.0, d1 = 0.0, Pg = h.Pf, vg = h.us0;
             double carry[RMT_N] = {0}, ub[RMT_N], u[RMT_N], fo[RMT_N];
             NodeJac nj;
             for (int kg = 0; kg < NG; ++kg) {
@@ -1950,15 +2173,7 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
                     ub[v] = g == 0 ? carry[v] : up;
                     carry[v] = G > 1 ? __shfl_sync(gmask, u[v], G - 1, G) : u[v];
                 }
-#if RMT_ISO
-                const double Tn = 0.0*h.Tf + h.Tf;
-#else
-                const double Tn = u[RMT_ITN]*h.Tf + h.Tf;
-#endif
-                double Pnext;
-                const double P = n2_pressure_chain(Pg, n2_mw(u, h), Tn, h, dz, g, gmask, Pnext);
-                n2_node<false>(u, ub, kg == 0 && g == 0, P, invdz, h, fo, E, nj);
-                Pg = Pnext;
+                dyn_eval<false>(u, ub, kg == 0 && g == 0, Pg, vg, dz, invdz, h, g, gmask, fo, nj);
                 double n0 = 0.0, n1 = 0.0;
 #pragma unroll
                 for (int v = 0; v < RMT_N; ++v) {
@@ -1984,7 +2199,7 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
 
         // ---- sweep 0: f(y_n), Jacobian blocks, LU of the diagonal blocks (all nodes of a group in parallel) ----
         {
-            double Pg = h.Pf, E;
+            double Pg = h.Pf, vg = h.us0;
             double carry[RMT_N] = {0}, ub[RMT_N], u[RMT_N], fo[RMT_N];
             NodeJac nj;
             for (int kg = 0; kg < NG; ++kg) {
@@ -1996,15 +2211,7 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
                     ub[v] = g == 0 ? carry[v] : up;
                     carry[v] = G > 1 ? __shfl_sync(gmask, u[v], G - 1, G) : u[v];
                 }
-#if RMT_ISO
-                const double Tn = 0.0*h.Tf + h.Tf;
-#else
-                const double Tn = u[RMT_ITN]*h.Tf + h.Tf;
-#endif
-                double Pnext;
-                const double P = n2_pressure_chain(Pg, n2_mw(u, h), Tn, h, dz, g, gmask, Pnext);
-                n2_node<true>(u, ub, kg == 0 && g == 0, P, invdz, h, fo, E, nj);
-                Pg = Pnext;
+                dyn_eval<true>(u, ub, kg == 0 && g == 0, Pg, vg, dz, invdz, h, g, gmask, fo, nj);
                 // W_kk = I/(h*gamma) - A, LU with partial pivoting in registers
                 int perm[RMT_N];
 #pragma unroll
@@ -2053,8 +2260,14 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
                 for (int r = 0; r < RMT_N; ++r) {
                     WK(W_L + r, kg) = nj.L[r]; WK(W_G + r, kg) = nj.g[r]; WK(W_E + r, kg) = nj.e[r];
                     WK(W_K + r, kg) = fo[r];                   // stage-1 right-hand side
+#if defined(RMT_MODEL_M9)
+                    WK(W_GV + r, kg) = nj.gv[r]; WK(W_LT + r, kg) = nj.Lt[r]; WK(W_EV + r, kg) = nj.eV[r];
+#endif
                 }
                 WK(W_EP, kg) = nj.ep;
+#if defined(RMT_MODEL_M9)
+                WK(W_S4, kg) = nj.ev; WK(W_S4 + 1, kg) = nj.eVb; WK(W_S4 + 2, kg) = nj.eVP; WK(W_S4 + 3, kg) = nj.eVv;
+#endif
             }
         }
 
@@ -2063,8 +2276,11 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
         bool bad = false;
 #pragma unroll 1
         for (int s = 0; s < RMT_ROS_S; ++s) {
-            double Pg = h.Pf, dPg = 0.0, E;
+            double Pg = h.Pf, vg = h.us0, dPg = 0.0;
             double carry[RMT_N] = {0}, kcarry[RMT_N] = {0};
+#if defined(RMT_MODEL_M9)
+            double dvg = 0.0;                                  // linearised velocity march
+#endif
             const bool lastStage = s == RMT_ROS_S - 1;
             for (int kg = 0; kg < NG; ++kg) {
                 __syncthreads();
@@ -2094,16 +2310,8 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
                         ub[v] = g == 0 ? carry[v] : up;
                         carry[v] = G > 1 ? __shfl_sync(gmask, u[v], G - 1, G) : u[v];
                     }
-#if RMT_ISO
-                    const double Tn = 0.0*h.Tf + h.Tf;
-#else
-                    const double Tn = u[RMT_ITN]*h.Tf + h.Tf;
-#endif
-                    double Pnext;
-                    const double P = n2_pressure_chain(Pg, n2_mw(u, h), Tn, h, dz, g, gmask, Pnext);
                     NodeJac njd;
-                    n2_node<false>(u, ub, kg == 0 && g == 0, P, invdz, h, rhs, E, njd);
-                    Pg = Pnext;
+                    dyn_eval<false>(u, ub, kg == 0 && g == 0, Pg, vg, dz, invdz, h, g, gmask, rhs, njd);
 #pragma unroll
                     for (int v = 0; v < RMT_N; ++v) rhs[v] += vc[v];
                 }
@@ -2131,8 +2339,15 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
 #pragma unroll 1
                 for (int j = 0; j < G; ++j) {
                     double xx[RMT_N], tv[RMT_N];
+#if defined(RMT_MODEL_M9)
+                    // M9: besides the upwind block and the pressure column, the velocity column and the T_{k-1} column
+#pragma unroll
+                    for (int c = 0; c < RMT_N; ++c)
+                        tv[c] = fma(Lk[c], kp[c], gk[c]*dP) + (WK(W_GV + c, kg)*dvg + WK(W_LT + c, kg)*kp[RMT_ITN]);
+#else
 #pragma unroll
                     for (int c = 0; c < RMT_N; ++c) tv[c] = fma(Lk[c], kp[c], gk[c]*dP);     // explicit: the same bits for every G
+#endif
 #pragma unroll
                     for (int v = 0; v < RMT_N; ++v) {
                         double acc = x0[v];
@@ -2143,7 +2358,17 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
                     double ek = 0.0;
 #pragma unroll
                     for (int v = 0; v < RMT_N; ++v) ek += WK(W_E + v, kg)*xx[v];
+#if defined(RMT_MODEL_M9)
+                    // dP_{k+1} = dP_k + dz*(e_k.K_k + (dE/dv) dv_k);  dv_{k+1} = dv_k + dz*(eV_k.K_k + (dV/dT_{k-1}) K_{k-1,T}
+                    //            + (dV/dP) dP_k + (dV/dv) dv_k)
+                    double evk = 0.0;
+#pragma unroll
+                    for (int v = 0; v < RMT_N; ++v) evk += WK(W_EV + v, kg)*xx[v];
+                    const double dnx = fma(dz, ek + WK(W_S4, kg)*dvg, dP);
+                    dvg = fma(dz, evk + WK(W_S4 + 1, kg)*kp[RMT_ITN] + WK(W_S4 + 2, kg)*dP + WK(W_S4 + 3, kg)*dvg, dvg);
+#else
                     const double dnx = fma(dz, fma(WK(W_EP, kg), dP, ek), dP);
+#endif
                     if (g == j) {
 #pragma unroll
                         for (int v = 0; v < RMT_N; ++v) x[v] = xx[v];
@@ -2234,8 +2459,13 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
                     }
                     if (a.out_mode != 0) {
                         double S = 0.0, C[RMT_NC];
+#if defined(RMT_MODEL_M9)
+#pragma unroll
+                        for (int q = 0; q < RMT_NC; ++q) { C[q] = v[q]; S += C[q]; }           // pbReactor.py:2189-2196
+#else
 #pragma unroll
                         for (int q = 0; q < RMT_NC; ++q) { C[q] = v[q]*h.Cmax; S += C[q]; }
+#endif
                         if (a.out_mode == 2) {
 #pragma unroll
                             for (int q = 0; q < RMT_NC; ++q) o[q*rs] = C[q];
@@ -2243,7 +2473,9 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
                         }
 #pragma unroll
                         for (int q = 0; q < RMT_NC; ++q) o[q*rs] = C[q]/S;
-#if !RMT_ISO
+#if defined(RMT_MODEL_M9)
+                        o[RMT_ITN*rs] = v[RMT_ITN];
+#elif !RMT_ISO
                         o[RMT_ITN*rs] = v[RMT_ITN]*h.Tf + h.Tf;
 #endif
                     }
@@ -2280,7 +2512,7 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
     }
 #undef WK
 }
-#endif  // RMT_MODEL_N2
+#endif  // RMT_DYNAMIC
 
 // ---------------------------------------------------------------------------------
 // deterministic objective reduction: per-block (sum, min, argmin) partials, then one

@@ -21,6 +21,7 @@ solverSetting = {
     "N1": {"zNo": 100},
     "N2": {"zNo": 20, "rNo": 5, "tNo": 5, "timesNo": 5},
     "M9": {"zNo": 30},          # runM3 (model M7) takes its number of output points from here (pbReactor.py:1283)
+    "S2": {"tNo": 10, "zNo": 100, "rNo": 7, "timesNo": 5},      # grid of the dynamic model M9 (runM5, pbReactor.py:2072)
 }
 
 # SciPy defaults the reference inherits by never passing tolerances
@@ -43,7 +44,7 @@ class CompiledModel:
         self.method = method
         self.reduced = use_extents(spec) if reduced is None else bool(reduced)
         self.m = system_size(spec, self.reduced)          # unknowns of the integrator's linear systems
-        self.lanes = int(lanes) if spec.model == "N2" else 1     # N2: threads per reactor
+        self.lanes = int(lanes) if spec.model in ("N2", "M9") else 1     # dynamic models: threads per reactor
         self.header = generate_model_header(spec, tableau=method, reduced=self.reduced, lanes=self.lanes)
         self.flops = model_flops(spec, self.reduced)
         self.module = None
@@ -63,7 +64,7 @@ def default_block(spec, stages=6, reduced=None):
     128-thread blocks per SM.  256 threads leave ~250 registers per thread (no spills); when the linear
     systems are small enough for 384 threads (reaction-extent form) the 168-register build spills a few
     words but 12 warps hide more latency — measured 16.0 vs 18.4 ms per 2^20 config-3 reactors."""
-    if spec.model == "N2":
+    if spec.model in ("N2", "M9"):
         return 64
     m = system_size(spec, reduced)
     per_thread = 8*(m*m + stages*m)
@@ -112,7 +113,7 @@ def n2_block(B, sm_count=148, lanes=1):
 
 def compile_model_n2(modelInput, B, zNo, method=None):
     """compile_model with the launch shape (lanes per reactor, block size) for an ensemble of B reactors."""
-    lanes = n2_lanes(B, zNo)
+    lanes = n2_lanes(B, zNo) if modelInput["model"] == "N2" else 1       # M9: the velocity march is sequential
     return compile_model(modelInput, block=n2_block(B, lanes=lanes), method=method, lanes=lanes)
 
 
@@ -204,8 +205,10 @@ def uniform_inputs(spec, modelInput):
     vals = [float(oc["temperature"]), float(oc["pressure"])] + [float(c) for c in conc]
     vals += [float(feed["volumetric-flowrate"]), float(rs["ReInDi"]), float(rs["ReLe"]), float(rs["PaDi"]),
              float(rs["BeVoFr"]), float(eh["OvHeTrCo"]), float(eh["MeTe"]),
-             float(feed.get("mixture-viscosity", 0.0) or 0.0),      # read by M7 only (pbReactor.py:1235)
-             float(eh.get("EfHeTrAr", 0.0) or 0.0)]                 # used by M7 only; N1/N2 overwrite it with 4/ReInDi
+             float(feed.get("mixture-viscosity", 0.0) or 0.0),      # read by M7/M9 only (pbReactor.py:1235, :2069)
+             float(eh.get("EfHeTrAr", 0.0) or 0.0),                 # used by M7/M9 only; N1/N2 overwrite it with 4/ReInDi
+             float(rs.get("CaDe", 0.0) or 0.0),                     # catalyst density and heat capacity: M9's energy
+             float(rs.get("CaSpHeCa", 0.0) or 0.0)]                 # balance only (pbReactor.py:2619)
     # scalar VARS entries of THIS modelInput (the compiled model is shared by every input with the same structure)
     varis = modelInput["reaction-rates"]["VARS"]
     vals += [float(varis[name]) for name in spec.kin.param_names]
@@ -559,13 +562,14 @@ def n2_solve_ensemble(cm, modelInput, sweep=None, B=1, zNo=None, tNo=None, perio
         raise capi.RmtError("rmt_app_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
     dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
     spec = cm.spec
-    assert spec.model == "N2"
+    assert spec.model in ("N2", "M9")
     mod = cm.load(dev.index)
     sc = modelInput.get("solver-config", {})
     rtol = float(sc.get("rtol", DEFAULT_RTOL) if rtol is None else rtol)
     atol = float(sc.get("atol", DEFAULT_ATOL) if atol is None else atol)
-    zNo = int(solverSetting["N2"]["zNo"] if zNo is None else zNo)
-    tNo = int(solverSetting["N2"]["tNo"] if tNo is None else tNo)
+    grid = solverSetting["N2" if spec.model == "N2" else "S2"]       # runN2 :3436-3440 / runM5 :2072, :2145
+    zNo = int(grid["zNo"] if zNo is None else zNo)
+    tNo = int(grid["tNo"] if tNo is None else tNo)
     period = float(modelInput["operating-conditions"]["period"] if period is None else period)
     uniform = uniform_inputs(spec, modelInput)
     ws = workspace if workspace is not None else Workspace()

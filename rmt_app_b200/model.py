@@ -21,7 +21,7 @@ _TERM = re.compile(r"([0-9.]*)([a-zA-Z0-9.]+)")
 # per-instance primary inputs of the device setup kernel, in row order.
 # "concentration" expands to nc rows; kinetic parameter slots follow.
 SCALAR_INPUTS = ("temperature", "pressure", "volumetric-flowrate", "ReInDi", "ReLe", "PaDi", "BeVoFr",
-                 "OvHeTrCo", "MeTe", "mixture-viscosity", "EfHeTrAr")
+                 "OvHeTrCo", "MeTe", "mixture-viscosity", "EfHeTrAr", "CaDe", "CaSpHeCa")
 
 
 def parse_reaction(expr):
@@ -41,9 +41,9 @@ class ModelSpec:
     def __init__(self, modelInput):
         mi = modelInput
         self.model = mi["model"]
-        if self.model not in ("N1", "N2", "M7"):
+        if self.model not in ("N1", "N2", "M7", "M9"):
             raise NotImplementedError(
-                "rmt_app_b200 implements the pseudo-homogeneous packed-bed models N1, N2 and M7 only "
+                "rmt_app_b200 implements the pseudo-homogeneous packed-bed models N1, N2, M7 and M9 only "
                 "(got model=%r)" % (self.model,))
         self.compList = list(mi["feed"]["components"]["shell"])
         for c in self.compList:
@@ -51,7 +51,7 @@ class ModelSpec:
                 raise Exception("Component database is not up to date!")
         self.nc = len(self.compList)
         # modelSetting.py:21-23; M7 (pbReactor.runM3) has no process-type switch: always with the energy balance
-        self.iso = self.model != "M7" and mi["operating-conditions"]["process-type"] == "iso-thermal"
+        self.iso = self.model not in ("M7", "M9") and mi["operating-conditions"]["process-type"] == "iso-thermal"
         self.reactions = list(mi["reactions"].values())
         self.nr = len(self.reactions)
         self.components = [COMPONENTS[c] for c in self.compList]

@@ -47,9 +47,11 @@ def rmtExe(modelInput):
             resModel = _runN2(modelInput)
         elif modelType == "M7":
             resModel = _runM7(modelInput)
+        elif modelType == "M9":
+            resModel = _runM9(modelInput)
         else:
             raise NotImplementedError(
-                "model %r: this build accelerates the pseudo-homogeneous packed-bed models N1, N2 and M7 only"
+                "model %r: this build accelerates the pseudo-homogeneous packed-bed models N1, N2, M7 and M9 only"
                 % (modelType,))
         return {"resModel": resModel, "comTime": (timer() - tic)*1000}
     except Exception as e:
@@ -130,6 +132,41 @@ def _runM7(modelInput):
         from .plotting import plotResultsSteadyState
         plotResultsSteadyState([{"dataXs": times, "dataYs": rows, "labelList": labelList[:nc] + ["Pressure", "Temperature"],
                                  "indexList": [nc, nc + 1, nc], "modelId": "M7", "computation-time": 0.0}])
+    return out
+
+
+def _runM9(modelInput):
+    """runM5 (PyREMOT/docs/pbReactor.py:1997-2294), model id "M9": the dimensional twin of N2.  Grid and slabs come
+    from solverSetting['S2'] (:2072, :2145).  The reference returns only the plot lists of the LAST variable it looped
+    over — the temperature profile at the end of every slab (:2262-2294); the per-slab records it builds on the way
+    (:2203-2209) are returned here as well under "dataPack"."""
+    from .engine import n2_solve_ensemble
+    zNo, tNo = solverSetting['S2']['zNo'], solverSetting['S2']['tNo']
+    cm = engine.compile_model(modelInput, block=engine.n2_block(1))
+    spec = cm.spec
+    nc, n = spec.nc, spec.n
+    opT = modelInput['operating-conditions']['period']
+    res = n2_solve_ensemble(cm, modelInput, None, 1, zNo=zNo, tNo=tNo, period=opT, out_mode=2)
+    if int(res.status[0]) != 0:
+        raise RuntimeError("ODE Error: integrator status %d (%s)" % (res.status[0], STATUS_TEXT.get(int(res.status[0]))))
+    opTSpan = np.linspace(0, opT, tNo + 1)
+    dataXs = np.linspace(0, float(modelInput['reactor']['ReLe']), zNo)
+    labelList = list(spec.compList) + ["Temperature"]
+    dataPack = []
+    for i in range(tNo):
+        o = res.out[i, :, :, 0]                 # [rows][zNo]: raw state | C_i | (y_i, T)
+        raw, allv = o[:n], o[n + nc:]
+        dataPack.append({"successStatus": True, "dataTime": opTSpan[i + 1], "dataYCons": raw[:nc].copy(),
+                         "dataYTemp": raw[nc:nc + 1].copy(), "dataYs": allv.copy()})
+    Tt = np.array([d["dataYs"][nc] for d in dataPack])                      # dataPacktime[indexTemp], :2211-2212
+    XYList = [[dataXs, item] for item in Tt]                                # library/plot.py:85-90
+    names = [labelList[nc] + " at t=" + str(opTSpan[t + 1]) for t in range(tNo)]
+    dataList = [{"x": XYList[i][0], "y": XYList[i][1], "leg": names[i]} for i in range(len(XYList))]
+    out = {"XYList": XYList, "dataList": dataList, "dataPack": dataPack}
+    if _display(modelInput):
+        from .plotting import plotResultsDynamic
+        plotResultsDynamic({"dataPack": [dict(d, dataXs=dataXs, labelList=labelList, indexList=[nc, nc + 1, nc],
+                                              modelId="M9") for d in dataPack]}, tNo)
     return out
 
 
@@ -236,15 +273,16 @@ def rmtExeBatchN2(modelInput, sweep=None, B=None, *, zNo=None, tNo=None, rtol=No
     entry's dataYs, pbHomoReactor.py:3660-3677), "dataTime": [tNo], "dataXs": [zNo], "status": [B], ...}."""
     tic = timer()
     _check_components(modelInput)
-    if modelInput['model'] != "N2":
-        raise NotImplementedError("rmtExeBatchN2 covers model N2")
+    if modelInput['model'] not in ("N2", "M9"):
+        raise NotImplementedError("rmtExeBatchN2 covers the dynamic models N2 and M9")
     if B is None:
         if not sweep:
             raise ValueError("give B or a non-empty sweep")
         first = next(iter(sweep.values()))
         B = int(first.shape[0]) if hasattr(first, "shape") else len(first)
-    zNo = int(solverSetting['N2']['zNo'] if zNo is None else zNo)
-    tNo = int(solverSetting['N2']['tNo'] if tNo is None else tNo)
+    grid = solverSetting['N2' if modelInput['model'] == "N2" else 'S2']
+    zNo = int(grid['zNo'] if zNo is None else zNo)
+    tNo = int(grid['tNo'] if tNo is None else tNo)
     cm = engine.compile_model_n2(modelInput, B, zNo)
     res = engine.n2_solve_ensemble(cm, modelInput, sweep, B, zNo=zNo, tNo=tNo, rtol=rtol, atol=atol, out_mode=1,
                                    keep_on_device=keep_on_device, workspace=workspace)

@@ -343,7 +343,7 @@ def part_m9():
     for c in calls:
         for _ in range(2):
             Y.append(c["y"][:, -1]*(1 + 0.05*rng.uniform(-1, 1, c["y"].shape[0])))
-    neg = np.array(calls[0]["y"][:, 2]); neg[[29, 41, 64]] = -1e-9                    # clamped entries (:2487-2491): H2O, CO, DME
+    neg = np.array(calls[0]["y"][:, 2]); neg[[62, 64, 70]] = -1e-9                    # clamped entries (:2487-2491): DME at three nodes (a clamped reactant makes the rates 1e31)
     Y.append(neg)
     Y = np.array(Y)
     out["rhs_Y"] = Y

@@ -27,7 +27,25 @@ CFG = {
     "ch4": (lambda: cases.ch4_input("N2"), 20, "LSODA", 1e-11, 1e-13),
 }
 
+def m9_tight():
+    """Converged M9 solution (12 nodes, 3 slabs: the grid of m9_reference.npz) from the oracle port, whose RHS and
+    default-tolerance run are pinned to the reference (test_oracle_golden_m9.py)."""
+    O.solverSetting["S2"].update(zNo=12, tNo=3)
+    t0 = time.time()
+    o = O.M9Oracle(cases.methanol_m9_input())
+    res = o.solve(method="BDF", rtol=1e-10, atol=1e-13)
+    dps = res["dataPack"]
+    np.savez_compressed(os.path.join(HERE, "m9_sol_oracle_tight.npz"),
+                        dataYs=np.array([d["dataYs"] for d in dps]), solY=np.array([d["solY"] for d in dps]),
+                        dataTime=np.array([d["dataTime"] for d in dps]), zNo=np.array(12), nfev=np.array(o.nfev),
+                        wall=np.array(time.time() - t0))
+    print("m9 done in %.0f s, nfev %d" % (time.time() - t0, o.nfev), flush=True)
+
+
 if __name__ == "__main__":
+    if "m9" in sys.argv[1:]:
+        m9_tight()
+        sys.argv.remove("m9")
     for which in sys.argv[1:]:
         mk, zNo, method, rtol, atol = CFG[which]
         O.solverSetting["N2"]["zNo"] = zNo

@@ -19,8 +19,8 @@ def test_uniform_inputs_follow_header_order():
     u = engine.uniform_inputs(spec, mi)
     assert spec.input_names() == ["temperature", "pressure"] + ["concentration[%d]" % i for i in range(6)] + [
         "volumetric-flowrate", "ReInDi", "ReLe", "PaDi", "BeVoFr", "OvHeTrCo", "MeTe", "mixture-viscosity", "EfHeTrAr",
-        "VARS:CaBeDe"]
-    assert u.size == spec.nin == 18
+        "CaDe", "CaSpHeCa", "VARS:CaBeDe"]
+    assert u.size == spec.nin == 20
     assert u[0] == 523 and u[1] == 5e6 and u[-1] == pytest.approx(1982*0.61)
     np.testing.assert_array_equal(u[2:8], mi["feed"]["concentration"])
     assert u[13] == 100 and u[14] == 522
@@ -40,7 +40,7 @@ def test_sweep_rows_mapping_and_errors():
           "E1": -np.ones(B), "MeTe": np.full(B, 500.0)}
     rows, row_map = engine.sweep_rows(spec, sw, B)
     assert rows.shape == (9, B)
-    assert spec.nin == 2 + 6 + 9 + 13
+    assert spec.nin == 2 + 6 + 11 + 13
     assert row_map[1] == 0 and list(row_map[2:8]) == [1, 2, 3, 4, 5, 6]
     names = spec.input_names()
     assert row_map[names.index("VARS:E1")] == 7 and row_map[names.index("MeTe")] == 8
@@ -93,6 +93,23 @@ def test_m7_inputs():
     names = spec.input_names()
     assert u[names.index("mixture-viscosity")] == 1e-5 and u[names.index("EfHeTrAr")] == pytest.approx(4/0.0381)
     assert spec.kin.param_names == ["CaDe", "CaBeDe", "CaPo"]
+
+
+def test_m9_inputs_and_launch_shape():
+    mi = cases.methanol_m9_input()
+    spec = ModelSpec(mi)
+    assert spec.model == "M9" and spec.n == 7 and not spec.iso
+    u = engine.uniform_inputs(spec, mi)
+    names = spec.input_names()
+    assert u[names.index("CaDe")] == 1982 and u[names.index("CaSpHeCa")] == pytest.approx(0.96)
+    assert u[names.index("concentration[0]")] == pytest.approx(0.5749, rel=1e-3)        # kmol/m^3, as test_rmt_DME5.py
+    cm = engine.compile_model_n2(mi, 5000, 100)
+    assert cm.lanes == 1 and "#define RMT_MODEL_M9 1" in cm.header and "#define RMT_N2_G 1" in cm.header
+    with pytest.raises(ValueError, match="one lane per reactor"):
+        engine.compile_model(mi, lanes=4)
+    assert engine.solverSetting["S2"] == {"tNo": 10, "zNo": 100, "rNo": 7, "timesNo": 5}
+    # the steady-state models ignore the two extra inputs; their headers are unchanged in size
+    assert ModelSpec(cases.methanol_readme_input("N1")).nin == spec.nin - spec.nkp + ModelSpec(cases.methanol_readme_input("N1")).nkp
 
 
 def test_automatic_method_choice():

@@ -96,3 +96,52 @@ def test_m7_dimensional_twin_parity():
     got = r["dataYs"][i]
     np.testing.assert_allclose(got[6:], want[6:], rtol=1e-6)
     np.testing.assert_allclose(got[:6], want[:6]/want[:6].sum(), rtol=1e-6)
+
+
+def test_m9_dimensional_dynamic_twin_parity():
+    """Model M9 (pbReactor.runM5): RHS against the reference's modelEquationM5 (fixture), solution at tight tolerance
+    against the converged oracle run (1e-6: a wrong Jacobian block would cost the Rosenbrock method its order and show
+    here), default tolerance against the reference's own default run, rmtExe's plot lists, and the ensemble form."""
+    import os
+    import pyremot_oracle as O
+    from conftest import GOLDEN
+    from rmt_app_b200 import engine, rmtExe, rmtExeBatchN2, solverSetting
+    g = np.load(os.path.join(GOLDEN, "m9_reference.npz"))
+    t = np.load(os.path.join(GOLDEN, "m9_sol_oracle_tight.npz"))
+    mi = cases.methanol_m9_input()
+    cm = engine.compile_model(mi)
+    assert cm.spec.model == "M9" and cm.spec.n == 7 and cm.lanes == 1
+    zNo, tNo = 12, 3
+    Y, F = g["rhs_Y"], g["rhs_F"]
+    Fg = engine.n2_rhs_batch(cm, mi, Y, zNo)
+    Fr, Fq = F.reshape(len(F), 7, zNo), Fg.reshape(len(F), 7, zNo)
+    scale = np.max(np.abs(Fr), axis=1, keepdims=True)
+    assert np.max(np.abs(Fq - Fr)/scale) < 2e-9
+    assert np.max(np.abs(Fq[0] - Fr[0])/np.maximum(np.abs(Fr[0]), 1e-9*scale[0])) < 1e-10
+    old = dict(solverSetting["S2"])
+    solverSetting["S2"].update(zNo=zNo, tNo=tNo)
+    try:
+        tight = dict(mi); tight["solver-config"] = dict(mi["solver-config"], rtol=1e-9, atol=1e-12)
+        res = rmtExe(tight)["resModel"]
+        ours = np.array([d["dataYs"] for d in res["dataPack"]])
+        assert ours.shape == t["dataYs"].shape == (tNo, 7, zNo)
+        assert np.max(np.abs(ours - t["dataYs"])/np.abs(t["dataYs"])) < 1e-6
+        assert len(res["XYList"]) == tNo and [d["leg"] for d in res["dataList"]] == list(g["default__legends"])
+        np.testing.assert_array_equal(res["XYList"][0][0], g["default__x"])
+        dflt = rmtExe(mi)["resModel"]
+        Td = np.array([xy[1] for xy in dflt["XYList"]])
+        theirs = np.max(np.abs(g["default__T_profiles"] - t["dataYs"][:, 6])/t["dataYs"][:, 6])
+        assert np.max(np.abs(Td - t["dataYs"][:, 6])/t["dataYs"][:, 6]) < max(3*theirs, 2e-3)
+        # ensemble form: a few inlet temperatures, one checked against the oracle
+        B = 6
+        sw = {"temperature": 523.0 + np.arange(B)*2.0}
+        r = rmtExeBatchN2(mi, sw, rtol=1e-8, atol=1e-11)
+        assert r["success"].all() and r["dataYs"].shape == (B, tNo, 7, zNo)
+        O.solverSetting["S2"].update(zNo=zNo, tNo=tNo)
+        one = dict(mi); one["operating-conditions"] = dict(mi["operating-conditions"], temperature=float(sw["temperature"][4]))
+        want = O.rmtExe(one, method="BDF", rtol=1e-10, atol=1e-13)["resModel"]["dataPack"]
+        for i in range(tNo):
+            np.testing.assert_allclose(r["dataYs"][4, i], want[i]["dataYs"], rtol=1e-6)
+    finally:
+        solverSetting["S2"].update(old)
+        O.solverSetting["S2"].update(tNo=10, zNo=100)

@@ -365,6 +365,28 @@ def run_gpu_arm(args, rank, world, local_rank):
                                   else "no collective (one rank)"),
                    "objective_min": r4["objective_min"], "objective_argmin": r4["objective_argmin"], "failed": r4["failed"]}
 
+    # ---- the reference's own output shape: 101-point profiles of every reactor (runN1's t_eval, :2931) -----------
+    profile = None
+    if rank == 0 and not args.no_profile:
+        Bp = min(B, 1 << 18)
+        zp = np.linspace(0, 1, 101)
+        cmp_ = engine.compile_model(base, method=engine.choose_method(base, RTOL, zp.size))
+        dsw = {k: torch.from_numpy(np.ascontiguousarray(v[:Bp])).to(dev) for k, v in sweep.items()}
+        wsp = engine.Workspace()
+        for _ in range(2):
+            rp = engine.n1_solve_ensemble(cmp_, base, dsw, Bp, z_eval=zp, rtol=RTOL, atol=ATOL, keep_on_device=True, workspace=wsp)
+        p0 = torch.cuda.Event(enable_timing=True); p1 = torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for _ in range(3):
+            rp = engine.n1_solve_ensemble(cmp_, base, dsw, Bp, z_eval=zp, rtol=RTOL, atol=ATOL, keep_on_device=True, workspace=wsp)
+        p1.record(); torch.cuda.synchronize()
+        pms = p0.elapsed_time(p1)/3
+        profile = {"instances": Bp, "points": int(zp.size), "ms": pms, "solves_per_s": Bp/(pms*1e-3),
+                   "output_bytes": int(8*n*zp.size*Bp), "integrator": cmp_.method + ", dense output",
+                   "converged": int((rp.status == 0).sum().item()),
+                   "note": "what rmtExe returns per reactor (dataYs 8 x 101); inputs and results device-resident"}
+        del rp, wsp, dsw
+
     # ---- roofline denominators measured on this box ----------------------------------------------
     fp64_peak = mod.fp64_peak(iters=16384, repeats=5)
     peaks = {}
@@ -497,6 +519,8 @@ def run_gpu_arm(args, rank, world, local_rank):
             line["n2_dynamic_model"] = n2
         if config4 is not None:
             line["config4_population"] = config4
+        if profile is not None:
+            line["profile_101_points"] = profile
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
         emit(line)
@@ -535,6 +559,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-n2", action="store_true", help="skip the informational N2 (dynamic model) timings")
     ap.add_argument("--no-config4", action="store_true", help="skip the informational parameter-estimation population timing")
+    ap.add_argument("--no-profile", action="store_true", help="skip the informational 101-point-profile timing")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -1623,7 +1623,7 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
 // ---------------------------------------------------------------------------------
 // N2: dynamic model by the method of lines (modelEquationN2, pbHomoReactor.py:3706-4134).
 // State yhat[(nc+1)][zNo] variable-major as in the reference (:3873); on the device
-// [var][node][B].  One reactor per thread; the nodes are swept in flow direction because
+// [var][node][B].  The nodes are swept in flow direction (1..32 lanes per reactor, see rmt_n2_solve) because
 // the pressure is marched node by node (:3979) and the convection is first-order upwind
 // (:4082-4128), so node k depends on nodes <= k only.
 // ---------------------------------------------------------------------------------

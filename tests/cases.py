@@ -293,6 +293,23 @@ def ch4_input(model="N1", process_type="non-iso-thermal", ivp="default"):
 # ----------------------------------------------------------------------------
 # synthetic sweeps
 # ----------------------------------------------------------------------------
+def ch4_three_reaction_input(model="N1", process_type="iso-thermal"):
+    """Synthetic variant of the methane-coupling case with as many reactions as species (forward, reverse and a slow
+    side path written as separate reactions): nr = nc = 3, so the steady-state integrator keeps the full state
+    instead of switching to reaction extents."""
+    mi = ch4_input(model, process_type)
+    mi["reactions"] = {"R1": "2CH4 <=> C2H4 + 2H2", "R2": "C2H4 + 2H2 <=> 2CH4", "R3": "2CH4 <=> C2H4 + 2H2"}
+    varis = dict(mi["reaction-rates"]["VARS"])
+    varis["C_C2H4"] = lambda x: x['SpCoi'][1]
+    varis["C_H2"] = lambda x: x['SpCoi'][2]
+    mi["reaction-rates"] = {"VARS": varis, "RATES": {
+        "r1": lambda x: x['k0']*(x['C_CH4']**2),
+        "r2": lambda x: 0.05*x['k0']*x['C_C2H4']*x['C_H2'],
+        "r3": lambda x: 0.01*x['k0']*x['C_CH4'],
+    }}
+    return mi
+
+
 def config3_sweep(B, seed=20240611):
     """Config 3: T0 ~ U[473,573] K, P0 ~ U[2e6,8e6] Pa, H2/COx ~ U[1,3],
     CO2/COx ~ U[0.2,0.8]; float64 feed C0 = y*P0/(R*T0); Tm = T0.

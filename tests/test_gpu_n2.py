@@ -137,3 +137,28 @@ def test_n2_ensemble_matches_single_and_reports_failures(n2_settings):
     assert np.isnan(r.out[:, :, :, 5]).all()
     one = engine.n2_solve_ensemble(cm, mi, {k: v[11:12] for k, v in sw.items()}, 1, zNo=12, tNo=3, period=5.0)
     np.testing.assert_array_equal(one.out[..., 0], r.out[..., 11])
+
+
+def test_n2_config5_share_properties(n2_settings):
+    """BASELINE configs[4] per-GPU share (12 500 reactors x 200 nodes, period 0.5 s, 5 slabs): everything converges,
+    the profiles are physical, and a reactor solved inside the ensemble (8 lanes) equals the same reactor solved
+    alone (32 lanes) to rounding."""
+    from rmt_app_b200 import engine, rmtExeBatchN2
+    mi = cases.methanol_readme_input("N2")
+    B, zNo = 12500, 200
+    sw = cases.config3_sweep(B, 20240613)
+    r = rmtExeBatchN2(mi, sw, zNo=zNo, tNo=5)
+    assert r["success"].all()
+    Y = r["dataYs"]                                            # [B][tNo][nc+1][zNo]
+    assert Y.shape == (B, 5, 7, zNo)
+    np.testing.assert_allclose(Y[:, :, :6, :].sum(axis=2), 1.0, rtol=1e-12)
+    assert (Y[:, :, :6, :] > 0).all()
+    T = Y[:, :, 6, :]
+    assert T.min() > 440.0 and T.max() < 760.0                                   # reverse water-gas shift cools a few K below the feed
+    assert np.median(np.abs(T[:, :, 0] - sw["temperature"][:, None])) < 5.0       # the first node mostly stays near the feed temperature
+    st = r["stats"]
+    assert 20 < st[0].mean() < 80
+    for i in (0, 6789, B - 1):
+        one = rmtExeBatchN2(mi, {k: v[i:i + 1] for k, v in sw.items()}, zNo=zNo, tNo=5)
+        np.testing.assert_allclose(one["dataYs"][0], Y[i], rtol=1e-10, atol=0)
+    assert engine.n2_lanes(B, zNo) == 8 and engine.n2_lanes(1, zNo) == 32

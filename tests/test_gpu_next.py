@@ -145,3 +145,28 @@ def test_m9_dimensional_dynamic_twin_parity():
     finally:
         solverSetting["S2"].update(old)
         O.solverSetting["S2"].update(tNo=10, zNo=100)
+
+
+def test_full_state_integrator_when_reactions_do_not_outnumber_species():
+    """nr >= nc: no reaction-extent form (codegen.use_extents), the integrator works on the full state; the solution
+    must match the oracle on the same synthetic three-reaction methane case, for the outlet-only (Ros4) and the
+    profile (Rodas4) paths."""
+    import pyremot_oracle as O
+    from rmt_app_b200 import engine, rmtExe, rmtExeBatch
+    mi = cases.ch4_three_reaction_input("N1")
+    cm = engine.compile_model(mi)
+    assert not cm.reduced and cm.m == cm.spec.n == 4 and "#define RMT_REDUCED 0" in cm.header
+    ref = O.rmtExe(mi, method="LSODA", rtol=1e-11, atol=1e-13)["resModel"][0]["dataYs"]
+    tight = dict(mi); tight["solver-config"] = dict(mi["solver-config"], rtol=1e-9, atol=1e-12)
+    ours = rmtExe(tight)["resModel"][0]["dataYs"]
+    assert np.max(np.abs(ours - ref)/np.abs(ref)) < 1e-6
+    B = 64
+    sw = {"temperature": np.linspace(940, 1000, B)}
+    r = rmtExeBatch(mi, sw)                                  # default tolerance, outlet only -> Ros4
+    assert r["success"].all()
+    i = 40
+    one = dict(mi); one["operating-conditions"] = dict(mi["operating-conditions"], temperature=float(sw["temperature"][i]))
+    want = O.rmtExe(one, method="LSODA", rtol=1e-11, atol=1e-13)["resModel"][0]["dataYs"][:, -1]
+    np.testing.assert_allclose(r["dataYs"][i], want, rtol=5e-3)
+    r9 = rmtExeBatch(mi, sw, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(r9["dataYs"][i], want, rtol=1e-6)

@@ -212,6 +212,17 @@ __device__ __forceinline__ double rmt_sqrt(const double x)
     return x == 0.0 ? 0.0 : g;
 #endif
 }
+// x^a for the step-size controllers (x > 0): exp(a*log(x)) with the branch-free pair above.  libdevice's pow is a
+// ~180-instruction function with branches, called 2.2 times per step attempt — 6.5 % of the integrator's
+// instructions (ncu, profiles/r01_ncu_n1_solve_v4_extents.csv); the controller needs a few digits only.
+__device__ __forceinline__ double rmt_powc(const double x, const double a)
+{
+#if RMT_EXACT_MATH
+    return pow(x, a);
+#else
+    return rmt_exp(a*rmt_log(fmax(x, 1e-300)));
+#endif
+}
 #define RMT_EXP(x) rmt_exp(x)
 #define RMT_EXP10(x) rmt_exp10(x)
 #define RMT_LOG(x) rmt_log(x)
@@ -1275,7 +1286,7 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
             d0 = sqrt(d0/RMT_N); d1 = sqrt(d1/RMT_N); d2 = sqrt(d2/RMT_N);
             const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01*d0/d1;
             const double dm = fmax(d1, d2);
-            const double h1 = dm <= 1e-15 ? fmax(1e-6, h0*1e-3) : pow(0.01/dm, 1.0/(RMT_ROS_ORDER + 1));
+            const double h1 = dm <= 1e-15 ? fmax(1e-6, h0*1e-3) : rmt_powc(0.01/dm, 1.0/(RMT_ROS_ORDER + 1));
             hstep = fmin(a.ctrl[5]*fmin(100.0*h0, h1), tend);
             fresh = false;
         }
@@ -1509,15 +1520,15 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
         const double errc = fmax(err, 1e-10);
         double fac;
         if (BETA > 0.0 && nacc > 0)            // PI controller (Gustafsson 1991): uses the previous accepted error
-            fac = pow(errc, 1.0/(RMT_ROS_ORDER) - 0.75*BETA)*pow(erracc, -BETA)/SAFE;   // note erracc^(-beta): small previous error -> grow
+            fac = rmt_powc(errc, 1.0/(RMT_ROS_ORDER) - 0.75*BETA)*rmt_powc(erracc, -BETA)/SAFE;   // note erracc^(-beta): small previous error -> grow
         else
-            fac = pow(errc, 1.0/(RMT_ROS_ORDER))/SAFE;
+            fac = rmt_powc(errc, 1.0/(RMT_ROS_ORDER))/SAFE;
         fac = fmax(FAC2, fmin(FAC1, fac));
         double hnew = hh/fac;
         int fin = -1;
         if (err <= 1.0) {
             if (nacc > 0 && BETA <= 0.0) {
-                double facgus = (hacc/hh)*pow(err*err/erracc, 1.0/(RMT_ROS_ORDER))/SAFE;
+                double facgus = (hacc/hh)*rmt_powc(err*err/erracc, 1.0/(RMT_ROS_ORDER))/SAFE;
                 facgus = fmax(FAC2, fmin(FAC1, facgus));
                 fac = fmax(fac, facgus);
                 hnew = hh/fac;
@@ -2421,14 +2432,14 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
         // ---- controller (same as N1; identical in every lane of the group) ----
         const double errc = fmax(err, 1e-10);
         double fac;
-        if (BETA > 0.0 && nacc > 0) fac = pow(errc, 1.0/(RMT_ROS_ORDER) - 0.75*BETA)*pow(erracc, -BETA)/SAFE;
-        else fac = pow(errc, 1.0/(RMT_ROS_ORDER))/SAFE;
+        if (BETA > 0.0 && nacc > 0) fac = rmt_powc(errc, 1.0/(RMT_ROS_ORDER) - 0.75*BETA)*rmt_powc(erracc, -BETA)/SAFE;
+        else fac = rmt_powc(errc, 1.0/(RMT_ROS_ORDER))/SAFE;
         fac = fmax(FAC2, fmin(FAC1, fac));
         double hnew = hh/fac;
         int fin = -1;
         if (err <= 1.0) {
             if (nacc > 0 && BETA <= 0.0) {
-                double facgus = (hacc/hh)*pow(err*err/erracc, 1.0/(RMT_ROS_ORDER))/SAFE;
+                double facgus = (hacc/hh)*rmt_powc(err*err/erracc, 1.0/(RMT_ROS_ORDER))/SAFE;
                 facgus = fmax(FAC2, fmin(FAC1, facgus));
                 fac = fmax(fac, facgus);
                 hnew = hh/fac;

@@ -1960,7 +1960,7 @@ rmt_n2_rhs(const double* __restrict__ consts, const i64 B, const int zNo, const 
 // remainder from the pressure march which is carried EXACTLY by one running scalar
 // (the linearised pressure dP_k).  Every stage is therefore one forward sweep over the nodes
 // with an n x n solve per node — no approximation of the Jacobian, as Rosenbrock methods need.
-// Per-instance work arrays live in global memory, [slot-row][node group][thread] so that the lanes of
+// Per-instance work arrays live in global memory, [block][node group][row][thread] so that the lanes of
 // a warp read consecutive doubles.
 // ---------------------------------------------------------------------------------
 struct SolveArgsN2 {
@@ -2115,8 +2115,11 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
     const i64 threads = (i64)gridDim.x*blockDim.x;
     const i64 tid = (i64)blockIdx.x*blockDim.x + threadIdx.x;
     const int zNo = a.zNo, NG = (zNo + G - 1)/G;
-    double* w = a.work + tid;
-#define WK(row, kg) w[((i64)(row)*NG + (kg))*threads]
+    // work layout [block][node group][row][thread of the block]: within a node group every row is a compile-time
+    // offset from one base pointer, so an access costs no address arithmetic (the [row][group][thread] layout spent
+    // a quarter of the kernel's instructions on 64-bit index multiplies)
+    double* w = a.work + (i64)blockIdx.x*((i64)NG*W_ROWS*RMT_BLOCK) + threadIdx.x;
+#define WK(row, kg) w[((i64)(kg)*W_ROWS + (row))*RMT_BLOCK]
 #if !defined(RMT_MODEL_M9)
     const double dz = 1.0/(zNo - 1), invdz = 1.0/dz;
 #endif
@@ -2386,13 +2389,10 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
                         dPn = dnx;
                     }
                     if (G > 1) {
+                        // lane j's result goes to everybody; only lane j + 1 uses it (in the next iteration)
 #pragma unroll
-                        for (int v = 0; v < RMT_N; ++v) {
-                            const double up = __shfl_up_sync(gmask, xx[v], 1, G);
-                            if (g == j + 1) kp[v] = up;
-                        }
-                        const double upP = __shfl_up_sync(gmask, dnx, 1, G);
-                        if (g == j + 1) dP = upP;
+                        for (int v = 0; v < RMT_N; ++v) kp[v] = __shfl_sync(gmask, xx[v], j, G);
+                        dP = __shfl_sync(gmask, dnx, j, G);
                     }
                 }
 #pragma unroll

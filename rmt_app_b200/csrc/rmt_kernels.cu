@@ -1280,13 +1280,13 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
             rmt_expand(ag, jfy);                              // y'' = E A g
 #pragma unroll
             for (int i = 0; i < RMT_N; ++i) {
-                const double sc = a.ctrl[3]*(a.atol + a.rtol*fabs(y[i]));
-                d0 += (y[i]/sc)*(y[i]/sc); d1 += (fy[i]/sc)*(fy[i]/sc); d2 += (jfy[i]/sc)*(jfy[i]/sc);
+                const double isc = rmt_rcp(a.ctrl[3]*(a.atol + a.rtol*fabs(y[i])));
+                d0 += (y[i]*isc)*(y[i]*isc); d1 += (fy[i]*isc)*(fy[i]*isc); d2 += (jfy[i]*isc)*(jfy[i]*isc);
             }
-            d0 = sqrt(d0/RMT_N); d1 = sqrt(d1/RMT_N); d2 = sqrt(d2/RMT_N);
-            const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01*d0/d1;
+            d0 = rmt_sqrt(d0*(1.0/RMT_N)); d1 = rmt_sqrt(d1*(1.0/RMT_N)); d2 = rmt_sqrt(d2*(1.0/RMT_N));
+            const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01*d0*rmt_rcp(d1);
             const double dm = fmax(d1, d2);
-            const double h1 = dm <= 1e-15 ? fmax(1e-6, h0*1e-3) : rmt_powc(0.01/dm, 1.0/(RMT_ROS_ORDER + 1));
+            const double h1 = dm <= 1e-15 ? fmax(1e-6, h0*1e-3) : rmt_powc(0.01*rmt_rcp(dm), 1.0/(RMT_ROS_ORDER + 1));
             hstep = fmin(a.ctrl[5]*fmin(100.0*h0, h1), tend);
             fresh = false;
         }
@@ -1299,7 +1299,8 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
 
         // W = I/(h*gamma) - J, LU with partial pivoting.  The row permutation lives in registers as the
         // shared-memory address of each (pivoted) row, so every access is [row + immediate].
-        const double dg = 1.0/(hh*RMT_ROS_GAMMA);
+        const double invh = rmt_rcp(hh);                      // (refined reciprocal: IEEE division costs 2-3x the instructions)
+        const double dg = invh*(1.0/RMT_ROS_GAMMA);
 #pragma unroll
         for (int i = 0; i < RMT_M; ++i) LU(i, i) += dg;
         double* row[RMT_M];
@@ -1347,7 +1348,7 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
         double dxs[RMT_M], evs[RMT_M];          // sum m_s k_s and sum e_s k_s in the integrator's unknowns
 #pragma unroll
         for (int i = 0; i < RMT_M; ++i) { dxs[i] = 0.0; evs[i] = 0.0; }
-        const double invh = 1.0/hh;
+
 #if RMT_ROLL
 #pragma unroll 1
 #else
@@ -1499,11 +1500,11 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
 #pragma unroll
         for (int i = 0; i < RMT_N; ++i) {
             const double sc = a.ctrl[3]*(a.atol + a.rtol*fmax(fabs(y[i]), fabs(ynew[i])));
-            const double e = errv[i]/sc;
+            const double e = errv[i]*rmt_rcp(sc);
             err += e*e;
             bad = bad || !(fabs(ynew[i]) <= 1.7e308);
         }
-        err = sqrt(err/RMT_N);
+        err = rmt_sqrt(err*(1.0/RMT_N));
         // domain guard: concentrations never change sign in the exact solution (a negative one can run away
         // through second-order terms, e.g. -k*C^2); a species that sits in a denominator / log / sqrt of the
         // kinetics must stay strictly positive.  A step that violates this is rejected like a failed error test.
@@ -1516,22 +1517,22 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
             double* tr = a.trace + 4*(nacc + nrej);
             tr[0] = t; tr[1] = hh; tr[2] = err; tr[3] = err <= 1.0 ? 1.0 : 0.0;
         }
-        const double SAFE = a.ctrl[0], FAC1 = a.ctrl[1], FAC2 = 1.0/a.ctrl[2], BETA = a.ctrl[4];
+        const double ISAFE = rmt_rcp(a.ctrl[0]), FAC1 = a.ctrl[1], FAC2 = rmt_rcp(a.ctrl[2]), BETA = a.ctrl[4];
         const double errc = fmax(err, 1e-10);
         double fac;
         if (BETA > 0.0 && nacc > 0)            // PI controller (Gustafsson 1991): uses the previous accepted error
-            fac = rmt_powc(errc, 1.0/(RMT_ROS_ORDER) - 0.75*BETA)*rmt_powc(erracc, -BETA)/SAFE;   // note erracc^(-beta): small previous error -> grow
+            fac = rmt_powc(errc, 1.0/(RMT_ROS_ORDER) - 0.75*BETA)*rmt_powc(erracc, -BETA)*ISAFE;   // note erracc^(-beta): small previous error -> grow
         else
-            fac = rmt_powc(errc, 1.0/(RMT_ROS_ORDER))/SAFE;
+            fac = rmt_powc(errc, 1.0/(RMT_ROS_ORDER))*ISAFE;
         fac = fmax(FAC2, fmin(FAC1, fac));
-        double hnew = hh/fac;
+        double hnew = hh*rmt_rcp(fac);
         int fin = -1;
         if (err <= 1.0) {
             if (nacc > 0 && BETA <= 0.0) {
-                double facgus = (hacc/hh)*rmt_powc(err*err/erracc, 1.0/(RMT_ROS_ORDER))/SAFE;
+                double facgus = (hacc*invh)*rmt_powc(err*err*rmt_rcp(erracc), 1.0/(RMT_ROS_ORDER))*ISAFE;
                 facgus = fmax(FAC2, fmin(FAC1, facgus));
                 fac = fmax(fac, facgus);
-                hnew = hh/fac;
+                hnew = hh*rmt_rcp(fac);
             }
             hacc = hh; erracc = fmax(1e-2, err);
             ++nacc; nanrej = 0;

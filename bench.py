@@ -194,8 +194,8 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------
 # executed FP64 flop per step attempt of rmt_n1_solve on this workload (methanol kinetics, Ros4, reaction-extent
 # form), from ncu's smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on.sum of one launch divided by its
-# 54.25 M attempts (profiles/r01_ncu_n1_solve_v5_final.csv); a calibration like `traffic`, not a live counter
-EXEC_FLOP_PER_ATTEMPT = 2*1448 + 679 + 276
+# 54.25 M attempts (profiles/r01_ncu_n1_solve_v6_final.csv); a calibration like `traffic`, not a live counter
+EXEC_FLOP_PER_ATTEMPT = 2*1400 + 693 + 272
 
 
 def solver_flops(info, stats, cm):
@@ -482,13 +482,13 @@ def run_gpu_arm(args, rank, world, local_rank):
                 "kernel": "rmt_n1_solve", "bound": "fp64", "achieved": alg/solve_s/1e12, "peak": fp64_peak,
                 "unit": "TFLOP/s", "frac": alg/solve_s/1e12/fp64_peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the ncu --set full capture of this
-                # command at 2^20 reactors (profiles/r01_ncu_n1_solve_v5_final.csv: 180.1 MB + 63.1 MB), scaled per reactor
+                # command at 2^20 reactors (profiles/r01_ncu_n1_solve_v6_final.csv: 179.7 MB + 63.2 MB), scaled per reactor
                 "traffic": 232.0*B, "traffic_algorithmic": 8.0*(22 + n)*B + 20.0*B,
                 # FP64 flops the hardware executed: thread-level DFMA (x2) + DMUL + DADD counts of the same ncu capture
-                # per step attempt (1448 + 679 + 276 instructions = 3851 flop), times this run's attempts
+                # per step attempt (1400 + 693 + 272 instructions = 3765 flop), times this run's attempts
                 "achieved_executed": EXEC_FLOP_PER_ATTEMPT*att/solve_s/1e12,
                 "frac_executed": EXEC_FLOP_PER_ATTEMPT*att/solve_s/1e12/fp64_peak,
-                "fp64_pipe_busy_ncu": 0.529,
+                "fp64_pipe_busy_ncu": 0.565,
                 # model count with one FP64 instruction per operation and exp 25 / log 35 / div 10: an
                 # upper estimate of the instruction count — FMA fusion halves it in practice
                 "achieved_weighted": wt/solve_s/1e12, "frac_weighted": wt/solve_s/1e12/fp64_peak,

@@ -149,6 +149,9 @@ int ws_reserve(Module* M, int slot, size_t bytes, CUdeviceptr* out)
     return 0;
 }
 
+// Per-launch scratch (work-queue counter, z_eval, objective reference): a ring of 8 slots per module, so that up
+// to 8 launches of one module may be in flight on different streams (the Python pipeline uses 3 per call and
+// synchronises before returning); a slot is re-used only after 8 further launches.
 int scratch_get(Module* M, size_t bytes, CUdeviceptr* out)
 {
     Scratch& s = M->ring[M->ring_next];

@@ -260,6 +260,15 @@ class Workspace:
 
     def __init__(self):
         self._bufs = {}
+        self._pipe = None
+
+    def pipeline(self, device):
+        """Two (stream, private Workspace) pairs for the copy/compute pipeline of large host-side ensembles:
+        chunk c runs on pair c % 2, so consecutive chunks never share device or staging buffers."""
+        torch = _torch()
+        if self._pipe is None or self._pipe[0] != str(device):
+            self._pipe = (str(device), [(torch.cuda.Stream(device=device), Workspace()) for _ in range(2)])
+        return self._pipe[1]
 
     def get(self, name, shape, dtype, device=None, pinned=False):
         torch = _torch()
@@ -467,8 +476,7 @@ def n1_solve_ensemble(cm, modelInput, sweep=None, B=1, z_eval=None, rtol=None, a
         else:
             # chunk c runs on stream c % 2 with that stream's own device buffers: H2D(c+1) and D2H(c-1) overlap
             # the integrator kernel of chunk c, and the blocks of the next kernel fill the tail of this one
-            if not hasattr(ws, "_pipe"):
-                ws._pipe = [(torch.cuda.Stream(device=dev), Workspace()) for _ in range(2)]
+            pipe = ws.pipeline(dev)
             cuts = [0]
             for f in PIPELINE_SPLIT[:-1]:
                 cuts.append(min(B, cuts[-1] + max(1024, int(round(f*B/1024))*1024)))
@@ -482,7 +490,7 @@ def n1_solve_ensemble(cm, modelInput, sweep=None, B=1, z_eval=None, rtol=None, a
                 b0, b1 = cuts[c], cuts[c + 1]
                 if b1 <= b0:
                     continue
-                st, w = ws._pipe[c % 2]
+                st, w = pipe[c % 2]
                 if c - 2 in staged:
                     staged[c - 2].synchronize()       # the pinned staging buffer of this stream is free again
                 st.wait_event(ready)
@@ -500,7 +508,7 @@ def n1_solve_ensemble(cm, modelInput, sweep=None, B=1, z_eval=None, rtol=None, a
                             h_stats[r, b0:b1].copy_(d_stats[r], non_blocking=True)
                     if d_obj is not None:
                         h_obj[b0:b1].copy_(d_obj, non_blocking=True)
-            for st, _ in ws._pipe:
+            for st, _ in pipe:
                 st.synchronize()
         res.out, res.status = h_out.numpy(), h_status.numpy()
         res.stats = None if h_stats is None else h_stats.numpy()

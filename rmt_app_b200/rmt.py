@@ -188,6 +188,9 @@ def _runN2(modelInput):
     for i in range(tNo):
         o = res.out[i, :, :, 0]                 # [rows][zNo]
         raw, C, allv = o[:n], o[n:n + nc], o[n + nc:]
+        if spec.iso:
+            # the reference still appends a temperature row: T-hat = 0 everywhere, i.e. the feed temperature (:3641-3661)
+            allv = np.concatenate((allv, np.full((1, zNo), float(modelInput['operating-conditions']['temperature']))), axis=0)
         dataPack.append({
             "modelId": modelInput['model'],
             "processType": processType,
@@ -287,6 +290,16 @@ def rmtExeBatchN2(modelInput, sweep=None, B=None, *, zNo=None, tNo=None, rtol=No
     res = engine.n2_solve_ensemble(cm, modelInput, sweep, B, zNo=zNo, tNo=tNo, rtol=rtol, atol=atol, out_mode=1,
                                    keep_on_device=keep_on_device, workspace=workspace)
     out = res.out.permute(3, 0, 1, 2) if keep_on_device else np.transpose(res.out, (3, 0, 1, 2))
+    if cm.spec.iso:
+        # iso-thermal: the reference's dataYs still carries a temperature row (the feed temperature, per reactor)
+        T0 = sweep["temperature"] if sweep and "temperature" in sweep else np.full(B, float(modelInput['operating-conditions']['temperature']))
+        if keep_on_device:
+            import torch
+            Tr = torch.as_tensor(np.asarray(T0, dtype=np.float64), device=out.device).view(B, 1, 1, 1).expand(B, tNo, 1, zNo)
+            out = torch.cat((out, Tr), dim=2)
+        else:
+            Tr = np.broadcast_to(np.asarray(T0, dtype=np.float64).reshape(B, 1, 1, 1), (B, tNo, 1, zNo))
+            out = np.concatenate((out, Tr), axis=2)
     period = float(modelInput['operating-conditions']['period'])
     return {"dataYs": out, "dataTime": np.linspace(0, period, tNo + 1)[1:], "dataXs": np.linspace(0, 1, zNo),
             "status": res.status, "success": res.status == 0, "stats": res.stats,

@@ -233,6 +233,37 @@ def part_n2rhs():
     np.savez_compressed(os.path.join(HERE, "n2_rhs_reference.npz"), **out)
 
 
+def part_n2rhs_iso():
+    """N2 with process-type "iso-thermal" (nc unknowns per node, T frozen at the feed temperature): RHS known answers
+    and the reference's own default-tolerance run (methane case, 20 nodes)."""
+    from scipy.integrate import solve_ivp
+    PyREMOT, H, solverSetting = load_reference()
+    rng = np.random.default_rng(19)
+    out = {}
+    zNo = 20
+    solverSetting['N2']['zNo'] = zNo
+    mi = cases.ch4_input("N2", "iso-thermal")
+    mi["operating-conditions"]["period"] = 1e-9
+    res, wall, calls = _capture_n2(PyREMOT, H, mi)
+    fun, ps, y0 = calls[0]["fun"], calls[0]["args"][0], calls[0]["y0"]
+    sol = solve_ivp(fun, [0, 2.0], y0, method="BDF", args=(ps,), rtol=1e-5, atol=1e-8)
+    ymid = sol.y[:, -1]
+    Y = [y0, ymid, sol.y[:, len(sol.t)//2]]
+    for base in (y0, ymid):
+        for _ in range(3):
+            Y.append(base*(1 + 0.05*rng.uniform(-1, 1, base.size)) + 1e-4*rng.uniform(0, 1, base.size))
+    yneg = ymid.copy(); yneg[1*zNo + 3] = -1e-7; yneg[2*zNo + 5] = 0.0
+    Y.append(yneg)
+    Y = np.array(Y)
+    out["rhs_Y"] = Y
+    out["rhs_F"] = np.array([fun(0.0, y, ps) for y in Y])
+    out["zNo"] = np.array(zNo)
+    res, wall, calls = _capture_n2(PyREMOT, H, cases.ch4_input("N2", "iso-thermal"))
+    out.update({"default__" + k: v for k, v in _n2_pack(res, calls, wall).items()})
+    np.savez_compressed(os.path.join(HERE, "n2_iso_reference.npz"), **out)
+    print("n2 iso done: %d RHS states, default run nfev %s wall %.1f" % (len(Y), out["default__nfev"], wall))
+
+
 def _n2_pack(res, calls, wall):
     dps = res["resModel"]["dataPack"]
     return dict(dataYs=np.array([d["dataYs"] for d in dps]),
@@ -389,6 +420,8 @@ if __name__ == "__main__":
             part_m7()
         elif part == "m9":
             part_m9()
+        elif part == "n2rhs_iso":
+            part_n2rhs_iso()
         elif part == "props":
             part_props()
         elif part == "n2rhs":

@@ -162,3 +162,46 @@ def test_n2_config5_share_properties(n2_settings):
         one = rmtExeBatchN2(mi, {k: v[i:i + 1] for k, v in sw.items()}, zNo=zNo, tNo=5)
         np.testing.assert_allclose(one["dataYs"][0], Y[i], rtol=1e-10, atol=0)
     assert engine.n2_lanes(B, zNo) == 8 and engine.n2_lanes(1, zNo) == 32
+
+
+def test_n2_isothermal_parity(n2_settings):
+    """N2 with process-type "iso-thermal" (nc unknowns per node): RHS against the reference fixture, rmtExe against
+    the converged oracle run (1e-6) and against the reference's default run, several lanes per reactor."""
+    from rmt_app_b200 import engine, rmtExe
+    g = np.load(os.path.join(GOLDEN, "n2_iso_reference.npz"))
+    z = int(g["zNo"])
+    mi = cases.ch4_input("N2", "iso-thermal")
+    cm = engine.compile_model(mi)
+    assert cm.spec.iso and cm.spec.n == 3
+    Y, F = g["rhs_Y"], g["rhs_F"]
+    Fg = engine.n2_rhs_batch(cm, mi, Y, z)
+    Fr, Fq = F.reshape(len(F), 3, z), Fg.reshape(len(F), 3, z)
+    scale = np.max(np.abs(Fr), axis=1, keepdims=True)
+    assert np.max(np.abs(Fq - Fr)/scale) < 2e-9
+    n2_settings["N2"]["zNo"] = z
+    O.solverSetting["N2"]["zNo"] = z
+    want = O.rmtExe(mi, method="LSODA", rtol=1e-11, atol=1e-13)["resModel"]["dataPack"]
+    tight = dict(mi); tight["solver-config"] = dict(mi["solver-config"], rtol=1e-9, atol=1e-12)
+    ours = rmtExe(tight)["resModel"]["dataPack"]
+    assert len(ours) == 5
+    for a, b in zip(ours, want):
+        assert a["dataYs"].shape == b["dataYs"].shape
+        np.testing.assert_allclose(a["dataYs"], b["dataYs"], rtol=1e-6)
+        np.testing.assert_allclose(a["dataYCons2"], b["dataYCons2"], rtol=1e-6)
+    dflt = rmtExe(mi)["resModel"]["dataPack"]
+    for i, d in enumerate(dflt):
+        np.testing.assert_allclose(d["dataYs"], g["default__dataYs"][i], rtol=5e-3)
+    ref = None
+    for lanes, block in ((1, 64), (8, 64), (32, 32)):
+        c2 = engine.compile_model(mi, block=block, lanes=lanes)
+        r = engine.n2_solve_ensemble(c2, mi, None, 1, zNo=z, tNo=5, period=10.0, rtol=1e-8, atol=1e-11)
+        assert r.status[0] == 0
+        ref = r if ref is None else ref
+        np.testing.assert_allclose(r.out, ref.out, rtol=1e-11)
+    # ensemble form: the temperature row of the iso-thermal dataYs is each reactor's own feed temperature
+    from rmt_app_b200 import rmtExeBatchN2
+    sw = {"temperature": np.array([960.0, 973.0, 985.0])}
+    rb = rmtExeBatchN2(mi, sw, zNo=z, tNo=5)
+    assert rb["dataYs"].shape == (3, 5, 4, z) and rb["success"].all()
+    np.testing.assert_array_equal(rb["dataYs"][:, :, 3, :], np.broadcast_to(sw["temperature"].reshape(3, 1, 1), (3, 5, z)))
+    np.testing.assert_allclose(rb["dataYs"][1, :, :3, :], np.array([d["dataYs"][:3] for d in dflt]), rtol=1e-12)

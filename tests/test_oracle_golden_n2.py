@@ -65,3 +65,20 @@ def test_n2_methanol_first_slab_bdf(zno):
     from scipy.integrate import solve_ivp
     sol = solve_ivp(lambda t, y: o.rhs(t, y), [0, 0.1], o.IV, method="BDF", t_eval=np.linspace(0, 0.1, 5))
     np.testing.assert_allclose(sol.y[:, -1], g["soly_last"][0], rtol=1e-8, atol=1e-12)
+
+
+def test_n2_isothermal_rhs_and_solution(zno):
+    """process-type "iso-thermal": nc unknowns per node, temperature frozen (pbHomoReactor.py:3873-3914, :3638)."""
+    g = np.load(os.path.join(GOLDEN, "n2_iso_reference.npz"))
+    z = int(g["zNo"])
+    O.solverSetting["N2"]["zNo"] = z
+    mi = cases.ch4_input("N2", "iso-thermal")
+    o = O.N2Oracle(mi)
+    assert o.varNo == 3 and g["rhs_Y"].shape[1] == 3*z
+    Fo = np.array([o.rhs(0.0, y) for y in g["rhs_Y"]])
+    F = g["rhs_F"]
+    scale = np.maximum(np.abs(F), 1e-12*np.max(np.abs(F), axis=1, keepdims=True))
+    assert np.max(np.abs(Fo - F)/scale) < 1e-12
+    res = O.rmtExe(mi)["resModel"]
+    for i, dp in enumerate(res["dataPack"]):
+        np.testing.assert_allclose(dp["dataYs"], g["default__dataYs"][i], rtol=1e-9)

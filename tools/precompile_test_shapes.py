@@ -23,6 +23,11 @@ def main(verbose=True):
             put(engine.compile_model(mi, block=block, lanes=lanes))
         for B, z in ((1, 20), (1, 50), (40, 16), (70, 12), (1, 12), (1, 16)):
             put(engine.compile_model_n2(mi, B, z))
+    mi = cases.ch4_input("N2", "iso-thermal")
+    for lanes, block in ((1, 64), (8, 64), (32, 32)):
+        put(engine.compile_model(mi, block=block, lanes=lanes))
+    for B, z in ((1, 20), (3, 20)):
+        put(engine.compile_model_n2(mi, B, z))
     mi = cases.methanol_readme_input("N2")
     for B, z in ((1, 20), (1, 50), (12500, 200), (1, 200)):
         put(engine.compile_model_n2(mi, B, z))

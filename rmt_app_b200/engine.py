@@ -394,6 +394,20 @@ PIPELINE_MIN_B = 1 << 18
 PIPELINE_SPLIT = (0.125, 0.75, 0.125)
 
 
+def pipeline_cuts(B, split=None):
+    """Chunk boundaries [0, ..., B] of the copy/compute pipeline: fractions `split` of the ensemble, rounded to
+    multiples of 1024 reactors, every chunk non-empty."""
+    split = PIPELINE_SPLIT if split is None else split
+    cuts = [0]
+    for f in split[:-1]:
+        nxt = min(B, cuts[-1] + max(1024, int(round(f*B/1024))*1024))
+        if nxt > cuts[-1]:
+            cuts.append(nxt)
+    if cuts[-1] < B:
+        cuts.append(B)
+    return cuts
+
+
 def _slice_sweep(sweep, b0, b1):
     return {k: v[b0:b1] for k, v in (sweep or {}).items()}
 
@@ -477,10 +491,7 @@ def n1_solve_ensemble(cm, modelInput, sweep=None, B=1, z_eval=None, rtol=None, a
             # chunk c runs on stream c % 2 with that stream's own device buffers: H2D(c+1) and D2H(c-1) overlap
             # the integrator kernel of chunk c, and the blocks of the next kernel fill the tail of this one
             pipe = ws.pipeline(dev)
-            cuts = [0]
-            for f in PIPELINE_SPLIT[:-1]:
-                cuts.append(min(B, cuts[-1] + max(1024, int(round(f*B/1024))*1024)))
-            cuts.append(B)
+            cuts = pipeline_cuts(B)
             ready = torch.cuda.Event()
             ready.record()
             res.h2d_bytes = 0
@@ -488,8 +499,6 @@ def n1_solve_ensemble(cm, modelInput, sweep=None, B=1, z_eval=None, rtol=None, a
             staged = {}
             for c in range(len(cuts) - 1):
                 b0, b1 = cuts[c], cuts[c + 1]
-                if b1 <= b0:
-                    continue
                 st, w = pipe[c % 2]
                 if c - 2 in staged:
                     staged[c - 2].synchronize()       # the pinned staging buffer of this stream is free again

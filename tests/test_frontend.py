@@ -112,6 +112,22 @@ def test_m9_inputs_and_launch_shape():
     assert ModelSpec(cases.methanol_readme_input("N1")).nin == spec.nin - spec.nkp + ModelSpec(cases.methanol_readme_input("N1")).nkp
 
 
+def test_launch_shapes_and_pipeline_cuts():
+    # lanes per reactor of the dynamic integrator: about three resident waves of threads, never more lanes than nodes
+    assert [engine.n2_lanes(B, 200) for B in (1, 100, 4096, 12500, 50000, 10**6)] == [32, 32, 16, 8, 2, 1]
+    assert engine.n2_lanes(1, 12) == 16 and engine.n2_lanes(1, 3) == 4
+    assert engine.n2_block(12500, lanes=8) == 64 and engine.n2_block(1, lanes=32) == 32
+    assert engine.n2_block(10**6) == 256 and engine.n2_block(5000) == 32 and engine.n2_block(8000) == 64
+    # copy/compute pipeline: chunks cover the ensemble exactly, are non-empty and 1024-aligned inside
+    for B in (3*1024, 5000, 1 << 18, (1 << 20) + 7, 10**7):
+        cuts = engine.pipeline_cuts(B)
+        assert cuts[0] == 0 and cuts[-1] == B and all(b > a for a, b in zip(cuts, cuts[1:]))
+        assert all(c % 1024 == 0 for c in cuts[1:-1]) and 2 <= len(cuts) <= 4
+    assert engine.pipeline_cuts(1 << 20) == [0, 131072, 917504, 1048576]
+    assert engine.pipeline_cuts(2048, split=(0.5, 0.5)) == [0, 1024, 2048]
+    assert engine.pipeline_cuts(1000, split=(0.5, 0.5)) == [0, 1000]
+
+
 def test_automatic_method_choice():
     mi = cases.methanol_readme_input("N1")
     assert engine.choose_method(mi, 1e-3, 1) == "ros4"              # outlet only, loose tolerance

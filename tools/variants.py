@@ -8,6 +8,9 @@ from rmt_app_b200 import engine, capi
 
 B = int(os.environ.get("B", 1 << 20))
 base = cases.methanol_readme_input(); sw = cases.config3_sweep(B)
+if os.environ.get("SORT"):      # experiment: reactors ordered by a stiffness proxy
+    key = {"T": sw["temperature"], "P": sw["pressure"], "TP": sw["temperature"] + 1e-5*sw["pressure"]}[os.environ["SORT"]]
+    o = np.argsort(key); sw = {k: v[o] for k, v in sw.items()}
 base["solver-config"]["method"] = os.environ.get("METHOD", "rodas4")
 CTRL = [float(v) for v in os.environ["CTRL"].split(",")] if os.environ.get("CTRL") else None
 cm = engine.compile_model(base)

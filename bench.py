@@ -337,6 +337,24 @@ def run_gpu_arm(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
 
+    # ---- the same through the C ABI's host-buffer entry point (rmt_n1_solve_host: no torch on the path) -----------
+    # SoA rows in pinned host memory in, pinned host arrays out; the library runs its own three-chunk pipeline
+    hp_out = torch.empty((1, n, B), dtype=torch.float64).pin_memory()
+    hp_status = torch.empty((B,), dtype=torch.int32).pin_memory()
+    rows_np, out_np, status_np = h_rows.numpy(), hp_out.numpy(), hp_status.numpy()
+    for _ in range(2):
+        mod.n1_solve_host(B, rows_np, n_rows, row_map, uniform, z_eval, RTOL, ATOL, out_np, status_np, ctrl=ctrl)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        mod.n1_solve_host(B, rows_np, n_rows, row_map, uniform, z_eval, RTOL, ATOL, out_np, status_np, ctrl=ctrl)
+    cabi_s = time.perf_counter() - t0
+    cabi_ok = int((status_np == 0).sum())
+    if world > 1:
+        t = torch.tensor([cabi_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        cabi_s = float(t.item())
+
     # ---- BASELINE configs[3]: parameter-estimation population, sharded, NCCL objective reduction + gather -------
     config4 = None
     if not args.no_config4:
@@ -475,7 +493,9 @@ def run_gpu_arm(args, rank, world, local_rank):
             "clocks": clocks,
             "e2e": {"value": world*B*steps/e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "api": "rmt_app_b200.rmtExeBatch(modelInput, sweep, workspace=...) with pinned host tensors in, pinned host arrays out",
-                    "converged": e2e_ok},
+                    "converged": e2e_ok,
+                    "c_abi_host_call": {"value": world*B*steps/cabi_s, "unit": UNIT, "converged": cabi_ok,
+                                        "api": "rmt_n1_solve_host (include/rmt_b200.h) with pinned host buffers, same bytes"}},
             "gpu_launches": 2*steps,
             "converged": n_ok_all, "instances": world*B,
             "roofline": {

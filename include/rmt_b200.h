@@ -134,7 +134,10 @@ int rmt_n1_solve(rmt_module_t m, int64_t B, const double* d_consts, int32_t n_ev
                  const double* obj_ref, double* d_obj, const double* ctrl, void* stream);
 
 /* Same path with HOST buffers: copies inputs in, runs setup + solve, copies
- * results back, synchronises.  h_rows [n_rows][B], h_out [n_eval][rows][B]. */
+ * results back, synchronises.  h_rows [n_rows][B], h_out [n_eval][rows][B].
+ * From 2^18 reactors on the library cuts the ensemble into three chunks on two
+ * streams of its own, so that the copies run under the integrator kernel (pinned
+ * host buffers make the copies asynchronous); the results are the same bits. */
 int rmt_n1_solve_host(rmt_module_t m, int64_t B, const double* h_rows, int32_t n_rows, const int32_t* row_map,
                       const double* uniform, int32_t n_eval, const double* z_eval,
                       double rtol, double atol, int32_t max_steps, int32_t dense, int32_t out_mode,

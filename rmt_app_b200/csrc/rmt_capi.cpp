@@ -45,7 +45,7 @@ int fail(const char* fmt, ...)
     X(cuMemcpyDtoHAsync) X(cuMemcpyDtoH) X(cuMemsetD8Async) X(cuStreamSynchronize) X(cuFuncSetAttribute) \
     X(cuOccupancyMaxActiveBlocksPerMultiprocessor) X(cuGetErrorString) X(cuEventCreate) X(cuEventRecord) \
     X(cuEventSynchronize) X(cuEventElapsedTime) X(cuEventDestroy) X(cuMemAllocHost) X(cuMemFreeHost) \
-    X(cuCtxSynchronize)
+    X(cuCtxSynchronize) X(cuStreamCreate) X(cuStreamDestroy_v2)
 
 struct Driver {
     void* lib = nullptr;
@@ -118,6 +118,10 @@ struct Module {
     // grow-only workspaces of the *_host entry points and the reductions
     CUdeviceptr ws[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     size_t ws_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // copy/compute pipeline of rmt_n1_solve_host: two streams, each with its own device buffers
+    CUstream pipe_stream[2] = {nullptr, nullptr};
+    CUdeviceptr pipe_ws[2][6] = {{0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}};
+    size_t pipe_bytes[2][6] = {{0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}};
 };
 
 std::map<uint64_t, Blob*> g_blobs;
@@ -149,6 +153,18 @@ int ws_reserve(Module* M, int slot, size_t bytes, CUdeviceptr* out)
     return 0;
 }
 
+int pipe_reserve(Module* M, int k, int slot, size_t bytes, CUdeviceptr* out)
+{
+    if (M->pipe_bytes[k][slot] < bytes) {
+        if (M->pipe_ws[k][slot]) { CU(cuCtxSynchronize()); CU(cuMemFree(M->pipe_ws[k][slot])); M->pipe_ws[k][slot] = 0; M->pipe_bytes[k][slot] = 0; }
+        size_t want = bytes + bytes/8 + 256;
+        CU(cuMemAlloc(&M->pipe_ws[k][slot], want));
+        M->pipe_bytes[k][slot] = want;
+    }
+    *out = M->pipe_ws[k][slot];
+    return 0;
+}
+
 // Per-launch scratch (work-queue counter, z_eval, objective reference): a ring of 8 slots per module, so that up
 // to 8 launches of one module may be in flight on different streams (the Python pipeline uses 3 per call and
 // synchronises before returning); a slot is re-used only after 8 further launches.
@@ -165,6 +181,9 @@ int scratch_get(Module* M, size_t bytes, CUdeviceptr* out)
     *out = s.p;
     return 0;
 }
+
+// host-buffer entry point: ensembles at least this large run as a three-chunk copy/compute pipeline
+const int64_t RMT_PIPELINE_MIN_B = 1 << 18;
 
 // default step-size controller: safety, max shrink, max growth, tolerance scale kappa, PI beta,
 // initial-step factor (applied to the Hairer-Wanner starting step)
@@ -445,6 +464,10 @@ int rmt_module_free(rmt_module_t m)
         drv.p_cuCtxSynchronize();
         for (auto& s : M->ring) if (s.p) drv.p_cuMemFree(s.p);
         for (auto& w : M->ws) if (w) drv.p_cuMemFree(w);
+        for (int k = 0; k < 2; ++k) {
+            for (auto& w : M->pipe_ws[k]) if (w) drv.p_cuMemFree(w);
+            if (M->pipe_stream[k]) drv.p_cuStreamDestroy_v2(M->pipe_stream[k]);
+        }
         if (M->mod) drv.p_cuModuleUnload(M->mod);
     }
     delete M;
@@ -556,8 +579,45 @@ int rmt_n1_solve_host(rmt_module_t m, int64_t B, const double* h_rows, int32_t n
     if (check_rows(M, n_rows, row_map, uniform, h_rows)) return 1;
     if (!h_out || !h_status) return fail("rmt_n1_solve_host: h_out and h_status are required");
     const int n = M->info.n;
+    const int rows = out_mode == 2 ? 2*n + M->info.nc : n;
+    if (B >= RMT_PIPELINE_MIN_B && n_rows > 0) {
+        // Large host-side ensembles: three chunks (1/8, 3/4, 1/8 of the reactors, 1024-aligned) on two streams, so
+        // that the copies of one chunk run under the integrator kernel of another and the blocks of the next kernel
+        // fill the tail of the previous one.  Every reactor is an independent solve: same bits as one launch.
+        for (int k = 0; k < 2; ++k)
+            if (!M->pipe_stream[k]) CU(cuStreamCreate(&M->pipe_stream[k], CU_STREAM_NON_BLOCKING));
+        const int64_t c1 = std::max<int64_t>(1024, ((B/8 + 512)/1024)*1024);
+        const int64_t cuts[4] = {0, c1, B - c1, B};
+        for (int c = 0; c < 3; ++c) {
+            const int64_t b0 = cuts[c], Bc = cuts[c + 1] - cuts[c];
+            const int k = c % 2;
+            CUstream st = M->pipe_stream[k];
+            CUdeviceptr d_rows, d_consts, d_out, d_status, d_stats, d_obj = 0;
+            if (pipe_reserve(M, k, 0, 8*(size_t)n_rows*Bc, &d_rows)) return 1;
+            if (pipe_reserve(M, k, 1, 8*(size_t)M->info.nconst*Bc, &d_consts)) return 1;
+            if (pipe_reserve(M, k, 2, 8*(size_t)n_eval*rows*Bc, &d_out)) return 1;
+            if (pipe_reserve(M, k, 3, 4*(size_t)Bc, &d_status)) return 1;
+            if (pipe_reserve(M, k, 4, 16*(size_t)Bc, &d_stats)) return 1;
+            if (obj_ref && pipe_reserve(M, k, 5, 8*(size_t)Bc, &d_obj)) return 1;
+            for (int r = 0; r < n_rows; ++r)
+                CU(cuMemcpyHtoDAsync(d_rows + 8*(size_t)r*Bc, h_rows + (size_t)r*B + b0, 8*(size_t)Bc, st));
+            if (rmt_setup(m, Bc, (const double*)d_rows, n_rows, row_map, uniform, (double*)d_consts, st)) return 1;
+            if (rmt_n1_solve(m, Bc, (const double*)d_consts, n_eval, z_eval, rtol, atol, max_steps, dense, out_mode,
+                             (double*)d_out, (int32_t*)d_status, (int32_t*)d_stats, obj_ref, (double*)d_obj, ctrl, st)) return 1;
+            for (int64_t q = 0; q < (int64_t)n_eval*rows; ++q)
+                CU(cuMemcpyDtoHAsync(h_out + (size_t)q*B + b0, d_out + 8*(size_t)q*Bc, 8*(size_t)Bc, st));
+            CU(cuMemcpyDtoHAsync(h_status + b0, d_status, 4*(size_t)Bc, st));
+            if (h_stats)
+                for (int q = 0; q < 4; ++q)
+                    CU(cuMemcpyDtoHAsync(h_stats + (size_t)q*B + b0, d_stats + 4*(size_t)q*Bc, 4*(size_t)Bc, st));
+            if (obj_ref && h_obj) CU(cuMemcpyDtoHAsync(h_obj + b0, d_obj, 8*(size_t)Bc, st));
+        }
+        CU(cuStreamSynchronize(M->pipe_stream[0]));
+        CU(cuStreamSynchronize(M->pipe_stream[1]));
+        return 0;
+    }
     const size_t bytes_rows = 8*(size_t)std::max(n_rows, 0)*B, bytes_consts = 8*(size_t)M->info.nconst*B;
-    const size_t bytes_out = 8*(size_t)n_eval*(out_mode == 2 ? 2*n + M->info.nc : n)*B;
+    const size_t bytes_out = 8*(size_t)n_eval*rows*B;
     CUdeviceptr d_rows = 0, d_consts, d_out, d_status, d_stats, d_obj = 0;
     if (n_rows > 0 && ws_reserve(M, 0, bytes_rows, &d_rows)) return 1;
     if (ws_reserve(M, 1, bytes_consts, &d_consts)) return 1;

@@ -262,6 +262,19 @@ def test_host_buffer_entry_point_matches_device_path():
     np.testing.assert_array_equal(out, dev.out)
     np.testing.assert_array_equal(status, dev.status)
     np.testing.assert_array_equal(stats, dev.stats)
+    # >= 2^18 reactors: the library pipelines three chunks on two streams; same bits, with profile points and objective
+    B = (1 << 18) + 777
+    sw = cases.config3_sweep(B, seed=4)
+    z = np.array([0.5, 1.0])
+    ref = np.array([0.6, 0.2, 0.02, 0.02, 0.15, 1e-4, 5e6, 600.0])
+    dev = engine.n1_solve_ensemble(cm, base, sw, B, z_eval=z, objective_ref=ref, pipeline=False)
+    rows, row_map = engine.sweep_rows(cm.spec, sw, B)
+    out = np.empty((2, cm.spec.n, B)); status = np.empty(B, np.int32); stats = np.empty((4, B), np.int32); obj = np.empty(B)
+    cm.module.n1_solve_host(B, rows, rows.shape[0], row_map, uniform, z, 1e-3, 1e-6, out, status, stats, obj_ref=ref, h_obj=obj)
+    np.testing.assert_array_equal(out, dev.out)
+    np.testing.assert_array_equal(status, dev.status)
+    np.testing.assert_array_equal(stats, dev.stats)
+    np.testing.assert_array_equal(obj, dev.objective)
 
 
 def test_full_size_ensemble_properties():

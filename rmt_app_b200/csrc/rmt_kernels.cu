@@ -2089,6 +2089,10 @@ __device__ __forceinline__ void dyn_eval(const double (&u)[RMT_N], const double 
 #endif
 }
 
+// lockstep of the block: a barrier before every stage sweep of a node group (1) or only once per node group (0)
+#ifndef RMT_N2_STAGE_SYNC
+#define RMT_N2_STAGE_SYNC 0
+#endif
 #ifndef RMT_N2_MINBLOCKS
 #define RMT_N2_MINBLOCKS 1
 #endif
@@ -2125,6 +2129,14 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
     const double dz = 1.0/(zNo - 1), invdz = 1.0/dz;
 #endif
     const double SAFE = a.ctrl[0], FAC1 = a.ctrl[1], FAC2 = 1.0/a.ctrl[2], KAPPA = a.ctrl[3], BETA = a.ctrl[4];
+    // per reactor and sweep (s stage sweeps + the Jacobian sweep): upwind state [n], K of the node before [n], marched
+    // pressure, linearised pressure, marched velocity, linearised velocity (M9)
+    constexpr int N2_CARRY = 2*RMT_N + 4;
+#if RMT_N2_G > 1
+    __shared__ double n2_carry[(RMT_BLOCK/RMT_N2_G)*(RMT_ROS_S + 1)*N2_CARRY];     // one record per reactor of the block
+#else
+    double n2_carry[(RMT_ROS_S + 1)*N2_CARRY];                                     // one lane per reactor: thread-private
+#endif
 
     i64 inst = -1;
     bool exhausted = false;
@@ -2212,13 +2224,34 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
         const double hh = clipped ? hlim : hstep;
         const double dg = 1.0/(hh*RMT_ROS_GAMMA), invh = 1.0/hh;
 
-        // ---- sweep 0: f(y_n), Jacobian blocks, LU of the diagonal blocks (all nodes of a group in parallel) ----
+        // ---- one pass over the node groups.  For each group: the Jacobian sweep (f(y_n), Jacobian blocks, inverse
+        // diagonal blocks — all nodes of the group in parallel) and then all stage sweeps, back to back, so that the
+        // group's work rows (inverse blocks, couplings, stage vectors) are re-read while they are still in L2 / L1
+        // instead of being streamed from HBM once per stage.  What a sweep carries from one group to the next (state
+        // and K of the group's last node, marched pressure, linearised pressure) is kept per stage in shared memory.
+        double errsum = 0.0;
+        bool bad = false;
+#if RMT_N2_G > 1
+        double* const cs = n2_carry + (threadIdx.x/G)*((RMT_ROS_S + 1)*N2_CARRY);
+#else
+        double* const cs = n2_carry;
+#endif
+        for (int t = 0; t <= RMT_ROS_S; ++t) {                 // slot RMT_ROS_S: the Jacobian sweep
+            double* c = cs + t*N2_CARRY;
+#pragma unroll
+            for (int v = 0; v < 2*RMT_N; ++v) c[v] = 0.0;      // upwind state / K of the node before the inlet
+            c[2*RMT_N] = h.Pf; c[2*RMT_N + 1] = 0.0; c[2*RMT_N + 2] = h.us0; c[2*RMT_N + 3] = 0.0;
+        }
+        for (int kg = 0; kg < NG; ++kg) {
         {
-            double Pg = h.Pf, vg = h.us0;
-            double carry[RMT_N] = {0}, ub[RMT_N], u[RMT_N], fo[RMT_N];
+            double* const c0 = cs + RMT_ROS_S*N2_CARRY;
+            double carry[RMT_N], ub[RMT_N], u[RMT_N], fo[RMT_N];
             NodeJac nj;
-            for (int kg = 0; kg < NG; ++kg) {
+            {
                 __syncthreads();
+                double Pg = c0[2*RMT_N], vg = c0[2*RMT_N + 2];
+#pragma unroll
+                for (int v = 0; v < RMT_N; ++v) carry[v] = c0[v];
 #pragma unroll
                 for (int v = 0; v < RMT_N; ++v) {
                     u[v] = WK(YN + v, kg);
@@ -2283,22 +2316,30 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
 #if defined(RMT_MODEL_M9)
                 WK(W_S4, kg) = nj.ev; WK(W_S4 + 1, kg) = nj.eVb; WK(W_S4 + 2, kg) = nj.eVP; WK(W_S4 + 3, kg) = nj.eVv;
 #endif
+#pragma unroll
+                for (int v = 0; v < RMT_N; ++v) c0[v] = carry[v];
+                c0[2*RMT_N] = Pg; c0[2*RMT_N + 2] = vg;
             }
         }
 
-        // ---- stage sweeps ----
-        double errsum = 0.0;
-        bool bad = false;
+        // ---- stage sweeps of this group ----
 #pragma unroll 1
         for (int s = 0; s < RMT_ROS_S; ++s) {
-            double Pg = h.Pf, vg = h.us0, dPg = 0.0;
-            double carry[RMT_N] = {0}, kcarry[RMT_N] = {0};
-#if defined(RMT_MODEL_M9)
-            double dvg = 0.0;                                  // linearised velocity march
-#endif
+            double* const c = cs + s*N2_CARRY;
+            double carry[RMT_N], kcarry[RMT_N];
             const bool lastStage = s == RMT_ROS_S - 1;
-            for (int kg = 0; kg < NG; ++kg) {
+            {
+#if RMT_N2_STAGE_SYNC
                 __syncthreads();
+#else
+                __syncwarp();
+#endif
+                double Pg = c[2*RMT_N], dPg = c[2*RMT_N + 1], vg = c[2*RMT_N + 2];
+#if defined(RMT_MODEL_M9)
+                double dvg = c[2*RMT_N + 3];                   // linearised velocity march
+#endif
+#pragma unroll
+                for (int v = 0; v < RMT_N; ++v) { carry[v] = c[v]; kcarry[v] = c[RMT_N + v]; }
 #if RMT_N2_PREFETCH
                 if (kg + 1 < NG) {
                     // the rows the next node group reads (the sweep is bound by memory latency at 8 warps per SM)
@@ -2424,8 +2465,15 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
 #pragma unroll
                     for (int j = 0; j < G; ++j) errsum += G > 1 ? __shfl_sync(gmask, ne, j, G) : ne;   // node order
                 }
+#pragma unroll
+                for (int v = 0; v < RMT_N; ++v) { c[v] = carry[v]; c[RMT_N + v] = kcarry[v]; }
+                c[2*RMT_N] = Pg; c[2*RMT_N + 1] = dPg; c[2*RMT_N + 2] = vg;
+#if defined(RMT_MODEL_M9)
+                c[2*RMT_N + 3] = dvg;
+#endif
             }
         }
+        }   // node groups
         bad = (__ballot_sync(FULL, bad) & gmask) != 0u;
         double err = sqrt(errsum/(RMT_N*zNo));
         if (bad || !(err == err)) err = 1e30;

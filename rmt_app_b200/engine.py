@@ -92,8 +92,8 @@ def n2_lanes(B, zNo, sm_count=148):
     """Threads per reactor of the N2 integrator (a power of two <= 32; the nodes of a reactor are spread over
     them).  The kernel needs 255 registers, so 256 threads are resident per SM; about three waves of them keep
     the queue busy without paying for lane-to-lane hand-overs that buy nothing (measured on 12 500 x 200 nodes:
-    0.58 s with 1 lane, 0.26 s with 2 or 4, 0.22 s with 8, 0.25 s with 16, 0.35 s with 32; 50 000 x 50 nodes: 0.25 /
-    0.21 / 0.20 / 0.22 s with 1 / 2 / 4 / 8; one 50-node reactor: 67 / 15 / 6 ms with 1 / 8 / 32 lanes)."""
+    0.29 s with 1 lane, 0.24 s with 2 or 4, 0.19 s with 8, 0.23 s with 16; 50 000 x 50 nodes: 0.24 / 0.19 / 0.18 s
+    with 1 / 2 / 4; one 50-node reactor: 67 / 15 / 5 ms with 1 / 8 / 32 lanes)."""
     budget = 3*sm_count*256
     lanes = 32
     while lanes > 1 and (B*lanes > budget or lanes >= 2*zNo):
@@ -105,8 +105,9 @@ def n2_block(B, sm_count=148, lanes=1):
     """Threads per block of the N2 integrator (`lanes` threads per reactor, lockstep blocks): spread a small
     ensemble over all SMs rather than filling a few of them."""
     threads = B*lanes
-    # several lanes per reactor: 64-thread blocks (12 500 x 200 nodes, 8 lanes: 0.216 s with 64, 0.242 s with 128)
-    for b in ((64,) if lanes > 1 else (256, 128, 64)):
+    # several lanes per reactor: at most 128-thread blocks (12 500 x 200 nodes, 8 lanes: 0.190 s with 128, 0.200 s with
+    # 64, 0.212 s with 256); one lane per reactor: at most 128 (0.29 / 0.31 / 0.47 s with 64 / 128 / 256)
+    for b in (128, 64):
         if threads >= sm_count*b*3//4:
             return b
     return 32

@@ -673,7 +673,8 @@ int64_t rmt_n2_work_doubles(rmt_module_t m, int64_t B, int32_t zNo)
     // (M9 adds the velocity march: two more coupling vectors, one more gradient vector, four scalars)
     const int64_t rows = n*(5 + s + n) + 1 + (M->info.model == 9 ? 3*n + 4 : 0);
     const int64_t groups = (zNo + M->info.lanes - 1)/M->info.lanes;      // node groups, one node per lane
-    return rows*groups*n2_slots(M, B);
+    // the two state rows exist per node group; the rest is scratch of the group being processed
+    return (groups*2*n + (rows - 2*n))*n2_slots(M, B);
 }
 
 int rmt_n2_solve(rmt_module_t m, int64_t B, int32_t zNo, int32_t tNo, double period, const double* d_consts,

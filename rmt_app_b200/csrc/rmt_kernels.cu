@@ -2096,20 +2096,6 @@ __device__ __forceinline__ void dyn_eval(const double (&u)[RMT_N], const double 
 #ifndef RMT_N2_MINBLOCKS
 #define RMT_N2_MINBLOCKS 1
 #endif
-// software prefetch of the next node group's work rows while this group is computed: 0 off, 1 into L2, 2 into L1.
-// Measured on 12 500 x 200 nodes, 8 lanes: 0.283 s without, 0.336 s with either — the extra 80-150 prefetch
-// instructions per node group cost more than the latency they hide.  Off.
-#ifndef RMT_N2_PREFETCH
-#define RMT_N2_PREFETCH 0
-#endif
-__device__ __forceinline__ void n2_prefetch(const double* p)
-{
-#if RMT_N2_PREFETCH == 1
-    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
-#elif RMT_N2_PREFETCH == 2
-    asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
-#endif
-}
 extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2_solve(const SolveArgsN2 a)
 {
     constexpr int G = RMT_N2_G;
@@ -2123,8 +2109,13 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
     // work layout [block][node group][row][thread of the block]: within a node group every row is a compile-time
     // offset from one base pointer, so an access costs no address arithmetic (the [row][group][thread] layout spent
     // a quarter of the kernel's instructions on 64-bit index multiplies)
-    double* w = a.work + (i64)blockIdx.x*((i64)NG*W_ROWS*RMT_BLOCK) + threadIdx.x;
-#define WK(row, kg) w[((i64)(kg)*W_ROWS + (row))*RMT_BLOCK]
+    // State rows (y_n, y_{n+1}) exist per node group; everything else (stage vectors, inverse blocks, couplings) is
+    // scratch of the group being processed and is re-used from group to group (group-major sweep order), which keeps
+    // it resident in L2: per thread NG*2n + (W_ROWS - 2n) doubles.
+    double* const wy = a.work + (i64)blockIdx.x*(((i64)NG*W_K + (W_ROWS - W_K))*RMT_BLOCK) + threadIdx.x;
+    double* const wsx = wy + (i64)NG*W_K*RMT_BLOCK;
+#define WY(row, kg) wy[((i64)(kg)*W_K + (row))*RMT_BLOCK]
+#define WS(row) wsx[((row) - W_K)*RMT_BLOCK]
 #if !defined(RMT_MODEL_M9)
     const double dz = 1.0/(zNo - 1), invdz = 1.0/dz;
 #endif
@@ -2162,11 +2153,11 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
                     rmt_load_hot(a.consts, a.B, inst, h);
                     for (int kg = 0; kg < NG; ++kg) {                    // IV: feed composition at every node, T-hat = 0 (:3483-3497)
 #pragma unroll
-                        for (int v = 0; v < RMT_NC; ++v) WK(W_Y0 + v, kg) = h.iv[v];
+                        for (int v = 0; v < RMT_NC; ++v) WY(W_Y0 + v, kg) = h.iv[v];
 #if defined(RMT_MODEL_M9)
-                        WK(W_Y0 + RMT_ITN, kg) = h.Tf;                   // pbReactor.py:2099-2100
+                        WY(W_Y0 + RMT_ITN, kg) = h.Tf;                   // pbReactor.py:2099-2100
 #elif !RMT_ISO
-                        WK(W_Y0 + RMT_ITN, kg) = 0.0;
+                        WY(W_Y0 + RMT_ITN, kg) = 0.0;
 #endif
                     }
                     t = 0.0; nacc = nrej = nanrej = 0; slab = 0; cur = 0; last_rejected = false; fresh = true;
@@ -2195,7 +2186,7 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
             for (int kg = 0; kg < NG; ++kg) {
 #pragma unroll
                 for (int v = 0; v < RMT_N; ++v) {
-                    u[v] = WK(YN + v, kg);
+                    u[v] = WY(YN + v, kg);
                     const double up = G > 1 ? __shfl_up_sync(gmask, u[v], 1, G) : 0.0;
                     ub[v] = g == 0 ? carry[v] : up;
                     carry[v] = G > 1 ? __shfl_sync(gmask, u[v], G - 1, G) : u[v];
@@ -2254,7 +2245,7 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
                 for (int v = 0; v < RMT_N; ++v) carry[v] = c0[v];
 #pragma unroll
                 for (int v = 0; v < RMT_N; ++v) {
-                    u[v] = WK(YN + v, kg);
+                    u[v] = WY(YN + v, kg);
                     const double up = G > 1 ? __shfl_up_sync(gmask, u[v], 1, G) : 0.0;
                     ub[v] = g == 0 ? carry[v] : up;
                     carry[v] = G > 1 ? __shfl_sync(gmask, u[v], G - 1, G) : u[v];
@@ -2302,19 +2293,19 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
                     for (int q = 0; q < RMT_N; ++q) b[q] = q == c ? 1.0 : 0.0;
                     n2_lu_solve(nj.A, perm, b, xs);
 #pragma unroll
-                    for (int q = 0; q < RMT_N; ++q) WK(W_LU + q*RMT_N + c, kg) = xs[q];
+                    for (int q = 0; q < RMT_N; ++q) WS(W_LU + q*RMT_N + c) = xs[q];
                 }
 #pragma unroll
                 for (int r = 0; r < RMT_N; ++r) {
-                    WK(W_L + r, kg) = nj.L[r]; WK(W_G + r, kg) = nj.g[r]; WK(W_E + r, kg) = nj.e[r];
-                    WK(W_K + r, kg) = fo[r];                   // stage-1 right-hand side
+                    WS(W_L + r) = nj.L[r]; WS(W_G + r) = nj.g[r]; WS(W_E + r) = nj.e[r];
+                    WS(W_K + r) = fo[r];                   // stage-1 right-hand side
 #if defined(RMT_MODEL_M9)
-                    WK(W_GV + r, kg) = nj.gv[r]; WK(W_LT + r, kg) = nj.Lt[r]; WK(W_EV + r, kg) = nj.eV[r];
+                    WS(W_GV + r) = nj.gv[r]; WS(W_LT + r) = nj.Lt[r]; WS(W_EV + r) = nj.eV[r];
 #endif
                 }
-                WK(W_EP, kg) = nj.ep;
+                WS(W_EP) = nj.ep;
 #if defined(RMT_MODEL_M9)
-                WK(W_S4, kg) = nj.ev; WK(W_S4 + 1, kg) = nj.eVb; WK(W_S4 + 2, kg) = nj.eVP; WK(W_S4 + 3, kg) = nj.eVv;
+                WS(W_S4) = nj.ev; WS(W_S4 + 1) = nj.eVb; WS(W_S4 + 2) = nj.eVP; WS(W_S4 + 3) = nj.eVv;
 #endif
 #pragma unroll
                 for (int v = 0; v < RMT_N; ++v) c0[v] = carry[v];
@@ -2340,25 +2331,18 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
 #endif
 #pragma unroll
                 for (int v = 0; v < RMT_N; ++v) { carry[v] = c[v]; kcarry[v] = c[RMT_N + v]; }
-#if RMT_N2_PREFETCH
-                if (kg + 1 < NG) {
-                    // the rows the next node group reads (the sweep is bound by memory latency at 8 warps per SM)
-                    for (int r = 0; r < RMT_N*(s > 0 ? 1 + s : 1); ++r) n2_prefetch(&WK((r < RMT_N ? (s > 0 ? YN : W_K) : W_K - RMT_N) + r, kg + 1));
-                    for (int r = W_LU; r < W_ROWS; ++r) n2_prefetch(&WK(r, kg + 1));
-                }
-#endif
                 double rhs[RMT_N];
                 if (s == 0) {
 #pragma unroll
-                    for (int v = 0; v < RMT_N; ++v) rhs[v] = WK(W_K + v, kg);
+                    for (int v = 0; v < RMT_N; ++v) rhs[v] = WS(W_K + v);
                 } else {
                     double u[RMT_N], ub[RMT_N], vc[RMT_N];
 #pragma unroll
-                    for (int v = 0; v < RMT_N; ++v) { u[v] = WK(YN + v, kg); vc[v] = 0.0; }
+                    for (int v = 0; v < RMT_N; ++v) { u[v] = WY(YN + v, kg); vc[v] = 0.0; }
                     for (int j = 0; j < s; ++j) {
                         const double aj = RMT_cROS_A[s][j], cj = RMT_cROS_C[s][j]*invh;
 #pragma unroll
-                        for (int v = 0; v < RMT_N; ++v) { const double kv = WK(W_K + j*RMT_N + v, kg); u[v] += aj*kv; vc[v] += cj*kv; }
+                        for (int v = 0; v < RMT_N; ++v) { const double kv = WS(W_K + j*RMT_N + v); u[v] += aj*kv; vc[v] += cj*kv; }
                     }
 #pragma unroll
                     for (int v = 0; v < RMT_N; ++v) {
@@ -2375,9 +2359,9 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
                 double Wi[RMT_N][RMT_N], Lk[RMT_N], gk[RMT_N], x0[RMT_N];
 #pragma unroll
                 for (int r = 0; r < RMT_N; ++r) {
-                    Lk[r] = WK(W_L + r, kg); gk[r] = WK(W_G + r, kg);
+                    Lk[r] = WS(W_L + r); gk[r] = WS(W_G + r);
 #pragma unroll
-                    for (int c = 0; c < RMT_N; ++c) Wi[r][c] = WK(W_LU + r*RMT_N + c, kg);
+                    for (int c = 0; c < RMT_N; ++c) Wi[r][c] = WS(W_LU + r*RMT_N + c);
                 }
 #pragma unroll
                 for (int r = 0; r < RMT_N; ++r) {
@@ -2399,7 +2383,7 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
                     // M9: besides the upwind block and the pressure column, the velocity column and the T_{k-1} column
 #pragma unroll
                     for (int c = 0; c < RMT_N; ++c)
-                        tv[c] = fma(Lk[c], kp[c], gk[c]*dP) + (WK(W_GV + c, kg)*dvg + WK(W_LT + c, kg)*kp[RMT_ITN]);
+                        tv[c] = fma(Lk[c], kp[c], gk[c]*dP) + (WS(W_GV + c)*dvg + WS(W_LT + c)*kp[RMT_ITN]);
 #else
 #pragma unroll
                     for (int c = 0; c < RMT_N; ++c) tv[c] = fma(Lk[c], kp[c], gk[c]*dP);     // explicit: the same bits for every G
@@ -2413,17 +2397,17 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
                     }
                     double ek = 0.0;
 #pragma unroll
-                    for (int v = 0; v < RMT_N; ++v) ek += WK(W_E + v, kg)*xx[v];
+                    for (int v = 0; v < RMT_N; ++v) ek += WS(W_E + v)*xx[v];
 #if defined(RMT_MODEL_M9)
                     // dP_{k+1} = dP_k + dz*(e_k.K_k + (dE/dv) dv_k);  dv_{k+1} = dv_k + dz*(eV_k.K_k + (dV/dT_{k-1}) K_{k-1,T}
                     //            + (dV/dP) dP_k + (dV/dv) dv_k)
                     double evk = 0.0;
 #pragma unroll
-                    for (int v = 0; v < RMT_N; ++v) evk += WK(W_EV + v, kg)*xx[v];
-                    const double dnx = fma(dz, ek + WK(W_S4, kg)*dvg, dP);
-                    dvg = fma(dz, evk + WK(W_S4 + 1, kg)*kp[RMT_ITN] + WK(W_S4 + 2, kg)*dP + WK(W_S4 + 3, kg)*dvg, dvg);
+                    for (int v = 0; v < RMT_N; ++v) evk += WS(W_EV + v)*xx[v];
+                    const double dnx = fma(dz, ek + WS(W_S4)*dvg, dP);
+                    dvg = fma(dz, evk + WS(W_S4 + 1)*kp[RMT_ITN] + WS(W_S4 + 2)*dP + WS(W_S4 + 3)*dvg, dvg);
 #else
-                    const double dnx = fma(dz, fma(WK(W_EP, kg), dP, ek), dP);
+                    const double dnx = fma(dz, fma(WS(W_EP), dP, ek), dP);
 #endif
                     if (g == j) {
 #pragma unroll
@@ -2442,21 +2426,21 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
                 dPg = G > 1 ? __shfl_sync(gmask, dPn, G - 1, G) : dPn;
                 if (!lastStage) {
 #pragma unroll
-                    for (int v = 0; v < RMT_N; ++v) WK(W_K + s*RMT_N + v, kg) = x[v];
+                    for (int v = 0; v < RMT_N; ++v) WS(W_K + s*RMT_N + v) = x[v];
                 } else {
                     // y_{n+1} = y_n + sum_j m_j K_j ; err = sum_j e_j K_j
                     double ne = 0.0;
 #pragma unroll
                     for (int v = 0; v < RMT_N; ++v) {
-                        const double yo = WK(YN + v, kg);
+                        const double yo = WY(YN + v, kg);
                         double yn = yo;
                         double ev = 0.0;
                         for (int j = 0; j < s; ++j) {
-                            const double kj = WK(W_K + j*RMT_N + v, kg);
+                            const double kj = WS(W_K + j*RMT_N + v);
                             yn += RMT_cROS_M[j]*kj; ev += RMT_cROS_E[j]*kj;
                         }
                         yn += RMT_cROS_M[s]*x[v]; ev += RMT_cROS_E[s]*x[v];
-                        WK(YP + v, kg) = yn;
+                        WY(YP + v, kg) = yn;
                         const double sc = KAPPA*(a.atol + a.rtol*fmax(fabs(yo), fabs(yn)));
                         ne += (ev/sc)*(ev/sc);
                         bad = bad || (kg*G + g < zNo && !(fabs(yn) <= 1.7e308));
@@ -2509,7 +2493,7 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
                     if (!live || k >= zNo) continue;
                     double v[RMT_N];
 #pragma unroll
-                    for (int q = 0; q < RMT_N; ++q) v[q] = WK(YC + q, kg);
+                    for (int q = 0; q < RMT_N; ++q) v[q] = WY(YC + q, kg);
                     double* o = a.out + (((i64)slab*rows)*zNo + k)*a.B + inst;
                     const i64 rs = (i64)zNo*a.B;
                     if (a.out_mode != 1) {
@@ -2570,7 +2554,8 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
             if (live) inst = -1;
         }
     }
-#undef WK
+#undef WY
+#undef WS
 }
 #endif  // RMT_DYNAMIC
 

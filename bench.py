@@ -475,11 +475,11 @@ def run_gpu_arm(args, rank, world, local_rank):
                            "lanes_per_reactor": cm2.lanes, "block": cm2.block,
                            "node_rhs_evals_per_s": att2*zn*i2.stages/ens_s,
                            "fp64_tflops_algorithmic": alg2/ens_s/1e12,
-                           # dram bytes of one launch from ncu (profiles/r01_ncu_n2_solve_lanes8_v2_block_layout.csv:
-                           # 606 + 136 GB at 12 500 x 200 nodes x 43.0 attempts), scaled per node-attempt
-                           "hbm_traffic_gbs_ncu_calibrated": 6901.0*att2*zn/ens_s/1e9,
-                           "note": "wall time of engine.n2_solve_ensemble with device-resident results; bound: HBM "
-                                   "(work arrays streamed, 52 % of the copy bandwidth), see DESIGN.md 5.2"}}
+                           # dram bytes of one launch from ncu (profiles/r01_ncu_n2_solve_lanes8_v4_final.csv: 15 + 101 GB
+                           # at 12 500 x 200 nodes x 43.0 attempts; L2 hit rate 92 %), scaled per node-attempt
+                           "hbm_traffic_gbs_ncu_calibrated": 1080.0*att2*zn/ens_s/1e9,
+                           "note": "wall time of engine.n2_solve_ensemble with device-resident results; bound: FP64 / "
+                                   "instruction latency at 8 warps per SM (work rows stay in L2), see DESIGN.md 5.2"}}
 
     if rank == 0:
         steps = args.steps

@@ -1961,8 +1961,8 @@ rmt_n2_rhs(const double* __restrict__ consts, const i64 B, const int zNo, const 
 // remainder from the pressure march which is carried EXACTLY by one running scalar
 // (the linearised pressure dP_k).  Every stage is therefore one forward sweep over the nodes
 // with an n x n solve per node — no approximation of the Jacobian, as Rosenbrock methods need.
-// Per-instance work arrays live in global memory, [block][node group][row][thread] so that the lanes of
-// a warp read consecutive doubles.
+// Per-instance work arrays live in global memory, [.][thread of the block], so that the lanes of a warp read
+// consecutive doubles (layout: see rmt_n2_solve).
 // ---------------------------------------------------------------------------------
 struct SolveArgsN2 {
     const double* consts;
@@ -2106,12 +2106,12 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
     const i64 threads = (i64)gridDim.x*blockDim.x;
     const i64 tid = (i64)blockIdx.x*blockDim.x + threadIdx.x;
     const int zNo = a.zNo, NG = (zNo + G - 1)/G;
-    // work layout [block][node group][row][thread of the block]: within a node group every row is a compile-time
-    // offset from one base pointer, so an access costs no address arithmetic (the [row][group][thread] layout spent
-    // a quarter of the kernel's instructions on 64-bit index multiplies)
-    // State rows (y_n, y_{n+1}) exist per node group; everything else (stage vectors, inverse blocks, couplings) is
-    // scratch of the group being processed and is re-used from group to group (group-major sweep order), which keeps
-    // it resident in L2: per thread NG*2n + (W_ROWS - 2n) doubles.
+    // Work layout per block: state [node group][y_n | y_{n+1}][thread] followed by scratch [row][thread].  Every row
+    // is a compile-time offset from one base pointer, so an access costs no address arithmetic (a [row][node][thread]
+    // layout over the whole launch spent a quarter of the kernel's instructions on 64-bit index multiplies).  The
+    // state rows exist per node group; everything else (stage vectors, inverse blocks, couplings) is scratch of the
+    // group being processed and is re-used from group to group (group-major sweep order), which keeps it resident
+    // in L2: per thread NG*2n + (W_ROWS - 2n) doubles.
     double* const wy = a.work + (i64)blockIdx.x*(((i64)NG*W_K + (W_ROWS - W_K))*RMT_BLOCK) + threadIdx.x;
     double* const wsx = wy + (i64)NG*W_K*RMT_BLOCK;
 #define WY(row, kg) wy[((i64)(kg)*W_K + (row))*RMT_BLOCK]

@@ -1,14 +1,15 @@
 """CPU oracle for the PyREMOT N1 / N2 hot path  —  TEST INFRASTRUCTURE ONLY.
 
 This file is a plain NumPy/SciPy restatement of what the reference computes on
-the path named by BASELINE.json (`rmtExe` with model "N1" or "N2").  It exists
+the path named by BASELINE.json (`rmtExe` with model "N1" or "N2", plus their
+dimensional twins "M7" and "M9" from the next-row list of SURVEY 8(f)).  It exists
 so that the CUDA path can be checked on machines where /root/reference is not
 available (the GPU box).  It is NOT part of the product: only `tests/`,
 `__graft_entry__.smoke()` and the `cpu_baseline` / `--impl reference` legs of
 `bench.py` may import it.  The product (`rmt_app_b200`) never does and fails
 loudly without its CUDA library.
 
-Parity status: PINNED.  `tests/test_oracle_golden.py` checks every function
+Parity status: PINNED.  `tests/test_oracle_golden*.py` check every function
 below against numbers produced by running the unmodified reference in the
 build container (`tests/golden/make_golden.py` -> `tests/golden/*.npz`):
 RHS values to ~1e-14 relative, solutions through the same SciPy integrators

@@ -444,42 +444,56 @@ def run_gpu_arm(args, rank, world, local_rank):
     jac_bytes = 8.0*(14 + info.nkp + 2*n + n*n)*B
 
     # ---- the dynamic model (BASELINE configs[1] and configs[4]), informational ---------------------
+    # every rank solves its own 12 500-reactor share of config 5 (100 000 reactors x 200 nodes over 8 GPUs); the time is
+    # the max over ranks.  The single 50-node reactor (config 2) runs on rank 0.
     n2 = None
-    if rank == 0 and not args.no_n2:
+    if not args.no_n2:
         from rmt_app_b200 import rmtExe, solverSetting
         mi2 = cases.methanol_readme_input("N2")
-        solverSetting["N2"]["zNo"] = 50
-        rmtExe(mi2)
-        t0 = time.perf_counter()
-        rmtExe(mi2)
-        single_s = time.perf_counter() - t0
-        solverSetting["N2"]["zNo"] = 20
-        Bn, zn = 12500, 200                     # BASELINE configs[4]: 100k instances x 200 nodes over 8 GPUs
+        single_s = None
+        if rank == 0:
+            solverSetting["N2"]["zNo"] = 50
+            rmtExe(mi2)
+            t0 = time.perf_counter()
+            rmtExe(mi2)
+            single_s = time.perf_counter() - t0
+            solverSetting["N2"]["zNo"] = 20
+        Bn, zn = 12500, 200
         cm2 = engine.compile_model_n2(mi2, Bn, zn)
-        sw2 = cases.config3_sweep(Bn, 20240613)
-        for _ in range(2):
-            torch.cuda.synchronize(); t0 = time.perf_counter()
-            r2 = engine.n2_solve_ensemble(cm2, mi2, sw2, Bn, zNo=zn, tNo=5, period=0.5, keep_on_device=True, workspace=ws)
-            torch.cuda.synchronize(); ens_s = time.perf_counter() - t0
+        sw2 = cases.config3_sweep(Bn, 20240613 + rank)
+        r2 = engine.n2_solve_ensemble(cm2, mi2, sw2, Bn, zNo=zn, tNo=5, period=0.5, keep_on_device=True, workspace=ws)   # warm-up
+        barrier()
+        q0 = torch.cuda.Event(enable_timing=True); q1 = torch.cuda.Event(enable_timing=True)
+        q0.record()
+        r2 = engine.n2_solve_ensemble(cm2, mi2, sw2, Bn, zNo=zn, tNo=5, period=0.5, keep_on_device=True, workspace=ws)
+        q1.record(); torch.cuda.synchronize()
         i2 = cm2.load(local_rank).info
-        att2 = float(r2.stats[3].double().sum().item())              # step attempts summed over the reactors
+        t2 = torch.tensor([q0.elapsed_time(q1)*1e-3, float(r2.stats[3].double().sum().item()),
+                           float((r2.status == 0).sum().item()), float(r2.stats[0].double().sum().item())],
+                          dtype=torch.float64, device=dev)
+        if world > 1:
+            tmax = t2[:1].clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t2, op=dist.ReduceOp.SUM)
+            t2[0] = tmax[0]
+        ens_s, att2, ok2, acc2 = (float(v) for v in t2.tolist())
         nn = i2.n
         # per attempt and node: 1 f + Jacobian blocks, (s-1) RHS, LU + n unit-vector solves (explicit inverse), per stage
         # two n x n matrix-vector products and the stage combinations
         lin = (2.0*nn**3)/3.0 + nn*2.0*nn*nn + i2.stages*(4.0*nn*nn + 4.0*nn*i2.stages)
         alg2 = att2*zn*(i2.flops_jac_alg + (i2.stages - 1)*i2.flops_rhs_alg + lin)
         n2 = {"config2_single_50_nodes_s": single_s, "reference_bdf_same_case_s": 446.3,
-              "ensemble": {"instances": Bn, "nodes": zn, "period_s": 0.5, "seconds": ens_s, "instances_per_s": Bn/ens_s,
-                           "converged": int((r2.status == 0).sum().item()),
-                           "steps_mean": float(r2.stats[0].double().mean().item()),
+              "ensemble": {"instances": world*Bn, "instances_per_gpu": Bn, "nodes": zn, "period_s": 0.5, "seconds": ens_s,
+                           "instances_per_s": world*Bn/ens_s, "converged": int(ok2), "steps_mean": acc2/(world*Bn),
                            "lanes_per_reactor": cm2.lanes, "block": cm2.block,
                            "node_rhs_evals_per_s": att2*zn*i2.stages/ens_s,
                            "fp64_tflops_algorithmic": alg2/ens_s/1e12,
                            # dram bytes of one launch from ncu (profiles/r01_ncu_n2_solve_lanes8_v4_final.csv: 15 + 101 GB
                            # at 12 500 x 200 nodes x 43.0 attempts; L2 hit rate 92 %), scaled per node-attempt
                            "hbm_traffic_gbs_ncu_calibrated": 1080.0*att2*zn/ens_s/1e9,
-                           "note": "wall time of engine.n2_solve_ensemble with device-resident results; bound: FP64 / "
-                                   "instruction latency at 8 warps per SM (work rows stay in L2), see DESIGN.md 5.2"}}
+                           "note": "device time (CUDA events, max over ranks) of engine.n2_solve_ensemble: H2D of the sweep, "
+                                   "setup, integrator; results stay on the device; bound: FP64 / instruction latency at "
+                                   "8 warps per SM (work rows stay in L2), see DESIGN.md 5.2"}}
 
     if rank == 0:
         steps = args.steps

@@ -170,3 +170,49 @@ def test_full_state_integrator_when_reactions_do_not_outnumber_species():
     np.testing.assert_allclose(r["dataYs"][i], want, rtol=5e-3)
     r9 = rmtExeBatch(mi, sw, rtol=1e-9, atol=1e-12)
     np.testing.assert_allclose(r9["dataYs"][i], want, rtol=1e-6)
+
+
+def test_integration_stub_with_raw_ctypes():
+    """The binding INTEGRATION.md shows a maintainer (raw ctypes against include/rmt_b200.h, no rmt_app_b200.capi):
+    compile, load, rmt_setup, rmt_n1_solve — and the result equals rmtExe's."""
+    import ctypes as C
+    import os
+    import torch
+    from rmt_app_b200 import engine, rmtExe
+    from rmt_app_b200.model import ModelSpec
+    from rmt_app_b200.codegen import generate_model_header
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "rmt_app_b200")
+    lib = C.CDLL(os.path.join(root, "librmtb200.so"))
+    lib.rmt_last_error.restype = C.c_char_p
+
+    def ck(rc):
+        if rc:
+            raise RuntimeError(lib.rmt_last_error().decode())
+    ck(lib.rmt_init(torch.cuda.current_device()))
+    mi = cases.methanol_readme_input("N1")
+    spec = ModelSpec(mi)
+    blob, mod = C.c_uint64(), C.c_uint64()
+    src = open(os.path.join(root, "csrc", "rmt_kernels.cu")).read()
+    ck(lib.rmt_nvrtc_compile(generate_model_header(spec).encode(), src.encode(), b"sm_100a", 256, None, 0, C.byref(blob)))
+    data, size = C.c_void_p(), C.c_size_t()
+    ck(lib.rmt_blob_data(blob, C.byref(data), C.byref(size)))
+    ck(lib.rmt_module_load(data, size, C.byref(mod)))
+    nin = spec.nin
+    row_map = (C.c_int32*nin)(*([-1]*nin))
+    uniform = (C.c_double*nin)(*engine.uniform_inputs(spec, mi))
+    consts = torch.empty((29 + spec.nc + spec.nkp, 1), dtype=torch.float64, device="cuda")
+    ck(lib.rmt_setup(mod, C.c_int64(1), None, 0, row_map, uniform, C.c_void_p(consts.data_ptr()), None))
+    z = np.linspace(0, 1, 101)
+    out = torch.empty((101, 2*spec.n + spec.nc, 1), dtype=torch.float64, device="cuda")
+    status = torch.empty(1, dtype=torch.int32, device="cuda")
+    stats = torch.empty((4, 1), dtype=torch.int32, device="cuda")
+    ck(lib.rmt_n1_solve(mod, C.c_int64(1), C.c_void_p(consts.data_ptr()), 101, z.ctypes.data_as(C.POINTER(C.c_double)),
+                        C.c_double(1e-3), C.c_double(1e-6), 100000, 1, 2,
+                        C.c_void_p(out.data_ptr()), C.c_void_p(status.data_ptr()), C.c_void_p(stats.data_ptr()),
+                        None, None, None, None))
+    torch.cuda.synchronize()
+    assert int(status.cpu()[0]) == 0
+    dataYs = out.cpu().numpy()[:, spec.n + spec.nc:, 0].T                           # rows per point: raw | C_i | dataYs
+    ref = rmtExe(mi)["resModel"][0]["dataYs"]
+    np.testing.assert_allclose(dataYs, ref, rtol=1e-12)
+    ck(lib.rmt_blob_free(blob)); ck(lib.rmt_module_free(mod))

@@ -41,18 +41,54 @@ RTOL, ATOL = 1e-3, 1e-6
 
 
 # ------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference path on the host cores
+# CPU arm: the reference's own implementation of the path on the host cores.
+# kind "reference" = the UNMODIFIED PyREMOT package staged under oracle/_ref by oracle/stage_reference.py (build());
+# kind "port"      = oracle/pyremot_oracle.py (same equations, same SciPy call, without the reference's per-call
+#                    `eval` of Cp strings — about 8x faster per solve), used when nothing is staged and reported
+#                    beside the reference figure otherwise.
 # ------------------------------------------------------------------------------------
-def _cpu_worker(idx_chunk):
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+def _cpu_paths():
+    for p in (os.path.join(ROOT, "oracle"),):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+
+
+def reference_staged():
+    _cpu_paths()
+    import ref_harness
+    return ref_harness.available()
+
+
+def _case_inputs(case, n):
+    """(base modelInput, sweep) of the CPU sample: the first n instances of the GPU arm's own draw."""
+    if case == "config4":
+        base = cases.methanol_readme_input("N1")
+        base["reaction-rates"] = cases.methanol_kinetics_param(1171.2)
+        return base, cases.config4_population(n)
+    return cases.methanol_readme_input("N1"), cases.config3_sweep(n, SEED)
+
+
+def _cpu_worker(job):
+    kind, case, idx_chunk = job
+    _cpu_paths()
     import io
     import contextlib
     import warnings
     warnings.simplefilter("ignore")
-    import pyremot_oracle as O
-    base = cases.methanol_readme_input("N1")
-    sweep = cases.config3_sweep(max(idx_chunk) + 1, SEED)
+    base, sweep = _case_inputs(case, max(idx_chunk) + 1)
     nfev, ok = 0, 0
+    if kind == "reference":
+        import ref_harness as R
+        for i in idx_chunk:
+            try:
+                with R.Capture() as cap:
+                    R.rmtExe(cases.instance_input(base, sweep, i))
+                nfev += cap.calls[0]["nfev"]
+                ok += 1
+            except Exception:
+                pass
+        return nfev, ok
+    import pyremot_oracle as O
     for i in idx_chunk:
         mi = cases.instance_input(base, sweep, i)
         with contextlib.redirect_stdout(io.StringIO()):
@@ -65,48 +101,169 @@ def _cpu_worker(idx_chunk):
     return nfev, ok
 
 
-def cpu_solves(n_solves, pool, cores):
+def cpu_solves(n_solves, pool, cores, kind="port", case="config3"):
     chunks = [list(range(c, n_solves, cores)) for c in range(cores)]
-    chunks = [c for c in chunks if c]
+    jobs = [(kind, case, c) for c in chunks if c]
     t0 = time.perf_counter()
-    res = pool.map(_cpu_worker, chunks)
+    res = pool.map(_cpu_worker, jobs)
     dt = time.perf_counter() - t0
     return dt, sum(r[0] for r in res), sum(r[1] for r in res)
 
 
+def cpu_baseline_block(cores, pool, per_core_ref=6, per_core_port=16):
+    """`cpu_baseline` of the GPU arm's line: the reference (when staged) on a bounded sample of the config-3 draw,
+    the port's figure beside it."""
+    kind = "reference" if reference_staged() else "port"
+    out = {}
+    cpu_solves(cores, pool, cores, "port")                        # warm the workers (imports)
+    S = per_core_port*cores
+    dt, nfev, ok = cpu_solves(S, pool, cores, "port")
+    port = {"value": S/dt, "unit": UNIT, "cores": cores, "sample": "%d config-3 reactors" % S,
+            "mean_nfev": nfev/max(ok, 1), "converged": ok}
+    if kind == "reference":
+        cpu_solves(cores, pool, cores, "reference")
+        S = per_core_ref*cores
+        dt, nfev, ok = cpu_solves(S, pool, cores, "reference")
+        out = {"value": S/dt, "unit": UNIT, "cores": cores, "kind": "reference",
+               "sample": "%d config-3 reactors (first indices of the GPU arm's own seed-%d draw, identical float64 inputs), the "
+                         "UNMODIFIED PyREMOT rmtExe (oracle/_ref, staged byte for byte by oracle/stage_reference.py; matplotlib "
+                         "stubbed, display-result False, stdout discarded), SciPy LSODA at its default rtol=1e-3 atol=1e-6, "
+                         "one process per core over %d cores; mean nfev %.0f; %d/%d converged"
+                         % (S, SEED, cores, nfev/max(ok, 1), ok, S),
+               "solves_per_s_per_core": S/dt/cores, "port": port}
+    else:
+        out = dict(port, kind="port")
+        out["sample"] += (" (first indices of the same seed), oracle port of runN1/modelEquationN1 + SciPy LSODA rtol=1e-3 "
+                          "atol=1e-6, %d processes; the reference is not staged under oracle/_ref" % cores)
+    return out
+
+
+def single_reference_times():
+    """Config 1 (one N1 solve through the reference's rmtExe, best of 3) and the reference's RHS alone
+    (modelEquationN1 called on states of its own solution) on ONE host core."""
+    _cpu_paths()
+    import ref_harness as R
+    mi = cases.methanol_readme_input("N1")
+    best, nfev = None, 0
+    for _ in range(3):
+        with R.Capture(keep_fun=True) as cap:
+            _, w = R.rmtExe(mi)
+        best = w if best is None else min(best, w)
+        c = cap.calls[0]
+        nfev = c["nfev"]
+    fun, ps, Y = c["fun"], c["args"][0], c["y"]
+    import io
+    import contextlib
+    n = 0
+    t0 = time.perf_counter()
+    with contextlib.redirect_stdout(io.StringIO()):
+        while time.perf_counter() - t0 < 2.0:
+            for k in range(Y.shape[1]):
+                fun(0.0, list(Y[:, k]), ps)
+            n += Y.shape[1]
+    rhs_s = (time.perf_counter() - t0)/n
+    return {"config1_single_rmtExe_s": best, "config1_nfev": int(nfev), "modelEquationN1_s_per_call": rhs_s,
+            "modelEquationN1_evals_per_s_per_core": 1.0/rhs_s, "rhs_calls_timed": n}
+
+
 def run_reference_arm(args, rank, world):
-    """`--impl reference`: the reference's CPU algorithm (oracle port: same
-    equations, same SciPy LSODA call, same default tolerances) on all host cores."""
+    """`--impl reference`: the reference's own CPU implementation of the path (the unmodified package staged under
+    oracle/_ref; the oracle port when nothing is staged) on all host cores, default tolerances, on a bounded sample
+    of the GPU arm's workload per step."""
     if rank != 0:
         return
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    per_step = 8*cores
+    kind = "reference" if reference_staged() else "port"
+    per_step = (2 if kind == "reference" else 8)*cores
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
+        cpu_solves(cores, pool, cores, kind)                      # imports
         for _ in range(args.warmup):
-            cpu_solves(min(per_step, 2*cores), pool, cores)
+            cpu_solves(cores, pool, cores, kind)
         t_total, nfev, ok = 0.0, 0, 0
         for _ in range(args.steps):
-            dt, nf, k = cpu_solves(per_step, pool, cores)
+            dt, nf, k = cpu_solves(per_step, pool, cores, kind)
             t_total += dt; nfev += nf; ok += k
     value = args.steps*per_step/t_total
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3*t_total/args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(world, sample=per_step),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d config-3 reactors per step (first indices of seed %d), SciPy LSODA rtol=1e-3 atol=1e-6, "
-                                   "multiprocessing over %d cores; mean nfev %.0f; %d/%d converged"
-                                   % (per_step, SEED, cores, nfev/max(ok, 1), ok, args.steps*per_step)},
+        "config": workload_config(world),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": "%d config-3 reactors per step (first indices of seed %d; each warm-up step %d), %s, SciPy LSODA "
+                                   "rtol=1e-3 atol=1e-6, multiprocessing over %d cores; mean nfev %.0f; %d/%d converged"
+                                   % (per_step, SEED, cores,
+                                      "UNMODIFIED PyREMOT rmtExe from oracle/_ref" if kind == "reference" else "oracle port",
+                                      cores, nfev/max(ok, 1), ok, args.steps*per_step)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
 
 
-def workload_config(world, sample=None):
+def run_cpu_baselines(args):
+    """`--cpu-baselines`: the long CPU measurements of BASELINE.md section 3 (minutes; not part of the default run).
+    Prints one JSON object; the copy measured on the GPU box's host is committed as profiles/r02_cpu_baselines.json and
+    quoted (with that provenance) by the default line."""
+    import multiprocessing as mp
+    import platform
+    _cpu_paths()
+    import ref_harness as R
+    cores = os.cpu_count() or 1
+    out = {"host": {"cores": cores, "machine": platform.machine(), "python": platform.python_version()},
+           "reference": "unmodified PyREMOT from " + str(R.reference_root())}
+    try:
+        out["host"]["model_name"] = [l.split(":", 1)[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name")][0]
+    except Exception:
+        pass
+    out.update(single_reference_times())
+    with mp.get_context("spawn").Pool(cores) as pool:
+        cpu_solves(cores, pool, cores, "reference")
+        for case, S in (("config3", 512), ("config4", 256)):
+            dt, nfev, ok = cpu_solves(S, pool, cores, "reference", case)
+            out[case] = {"sample": S, "seconds": dt, "solves_per_s_box": S/dt, "solves_per_s_per_core": S/dt/cores,
+                         "mean_nfev": nfev/max(ok, 1), "converged": ok,
+                         "extrapolated_full_size_hours": ((1 << 20) if case == "config3" else 65536)/(S/dt)/3600.0}
+        dt, nfev, ok = cpu_solves(512, pool, cores, "port", "config3")
+        out["config3_port"] = {"sample": 512, "seconds": dt, "solves_per_s_box": 512/dt, "mean_nfev": nfev/max(ok, 1)}
+    if not args.no_n2:
+        # config 2: one N2 instance, 50 axial nodes, README inputs, BDF (LSODA needs longer; BASELINE.md section 2)
+        mi2 = cases.methanol_readme_input("N2")
+        mi2["solver-config"]["ivp"] = "BDF"
+        R.set_grid("N2", zNo=50)
+        with R.Capture() as cap:
+            _, w = R.rmtExe(mi2)
+        R.set_grid("N2", zNo=20)
+        out["config2_single_n2_50_nodes_bdf_s"] = w
+        out["config2_nfev"] = int(sum(c["nfev"] for c in cap.calls))
+        out["config2_njev"] = int(sum(c["njev"] for c in cap.calls))
+        # config 5: the reference at 200 nodes needs > 1 h per instance (FD Jacobian of 1400 unknowns = 1400 RHS calls
+        # of ~0.25 s); quote its RHS cost at 200 nodes and the 50-node run instead (BASELINE.md 3.5)
+        R.set_grid("N2", zNo=200)
+        mi5 = cases.instance_input(cases.methanol_readme_input("N2"), cases.config3_sweep(8, 20240613), 0)
+        try:
+            with R.Capture(capture_only=True) as cap:
+                try:
+                    R.rmtExe(mi5)
+                except R.StopAfter:
+                    pass
+            c = cap.calls[0]
+            import io
+            import contextlib
+            t0 = time.perf_counter(); k = 0
+            with contextlib.redirect_stdout(io.StringIO()):
+                while time.perf_counter() - t0 < 3.0:
+                    c["fun"](0.0, list(c["y0"]), c["args"][0]); k += 1
+            out["config5_modelEquationN2_200_nodes_s_per_call"] = (time.perf_counter() - t0)/k
+        except Exception as e:                                       # diagnostics only
+            out["config5_rhs_error"] = repr(e)
+        R.set_grid("N2", zNo=20)
+    emit(out)
+
+
+def workload_config(world):
     cfg = {
         "workload": "config3: 2^20 steady-state PFR (PyREMOT N1, CO2->MeOH/DME, 6 comps, 3 rxns, 8 unknowns) per GPU; "
                     "T0~U[473,573]K, P0~U[2,8]MPa, H2/COx~U[1,3], CO2/COx~U[0.2,0.8]; seed %d+rank" % SEED,
@@ -114,8 +271,6 @@ def workload_config(world, sample=None):
         "integrator": "auto -> Ros4(3) L-stable Rosenbrock (outlet only, rtol >= 5e-4; Rodas4(3) otherwise), analytic Jacobian", "parallelism": "ensemble-sharded x%d, no data-path collective" % world,
         "cache": "inputs+constants+outputs 410 MB per step > 126 MB L2 (no flush needed)",
     }
-    if sample is not None:
-        cfg["instances_per_step"] = sample
     return cfg
 
 
@@ -235,18 +390,14 @@ def run_gpu_arm(args, rank, world, local_rank):
 
     # CPU baseline first (rank 0, N=1 only), before the timed GPU region
     cpu_baseline = None
+    cpu_single = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import multiprocessing as mp
         cores = os.cpu_count() or 1
-        S = 16*cores
         with mp.get_context("spawn").Pool(cores) as pool:
-            cpu_solves(cores, pool, cores)                      # warm the workers (imports)
-            dt, nfev, ok = cpu_solves(S, pool, cores)
-        cpu_baseline = {"value": S/dt, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": "%d config-3 reactors (first indices of the same seed), oracle port of runN1/modelEquationN1 "
-                                  "+ SciPy LSODA rtol=1e-3 atol=1e-6, %d processes; mean nfev %.0f; %d/%d converged; "
-                                  "the unmodified reference is ~8x slower per solve (0.6 s vs 0.07 s, BASELINE.md)"
-                                  % (S, cores, nfev/max(ok, 1), ok, S)}
+            cpu_baseline = cpu_baseline_block(cores, pool)
+        if reference_staged():
+            cpu_single = single_reference_times()
 
     B = args.instances
     base = cases.methanol_readme_input("N1")
@@ -591,6 +742,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--instances", type=int, default=B_PER_GPU, help="reactors per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-baselines", action="store_true",
+                    help="only the long CPU measurements of BASELINE.md section 3 (reference on the host cores; minutes)")
     ap.add_argument("--no-n2", action="store_true", help="skip the informational N2 (dynamic model) timings")
     ap.add_argument("--no-config4", action="store_true", help="skip the informational parameter-estimation population timing")
     ap.add_argument("--no-profile", action="store_true", help="skip the informational 101-point-profile timing")
@@ -604,6 +757,10 @@ def main():
                "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
     protect_stdout()
+    if args.cpu_baselines:
+        if rank == 0:
+            run_cpu_baselines(args)
+        return
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
     else:

@@ -418,12 +418,14 @@ class N2Oracle(HomoReactorSetup):
                 dxdtMat[nc][z] = const_T2*(conv + hform + hexch)
         return dxdtMat.flatten().tolist()
 
-    def solve(self, method=None, rtol=None, atol=None):
+    def solve(self, method=None, rtol=None, atol=None, **ivp_kw):
         """Slab loop of runN2 :3589-3685: tNo restarted solve_ivp calls, only
-        the last column of each is kept."""
+        the last column of each is kept.  `ivp_kw` goes to solve_ivp unchanged (fixture generation passes
+        `jac_sparsity` to the implicit methods so that a 200-node run finishes in minutes; the sparsity only
+        shapes the finite-difference Jacobian of the Newton iteration, not the converged solution)."""
         ivp = self.modelInput['solver-config']['ivp']
         method = method or ("LSODA" if ivp == 'default' else ivp)
-        kw = {}
+        kw = dict(ivp_kw)
         if rtol is not None:
             kw["rtol"] = rtol
         if atol is not None:

@@ -104,6 +104,8 @@ struct Blob {
 struct Scratch {           // per-launch device scratch: queue counter + z_eval + obj_ref
     CUdeviceptr p = 0;
     size_t bytes = 0;
+    CUevent done = nullptr;    // recorded after the launch that uses the slot; waited for before the slot is re-used
+    bool in_flight = false;
 };
 
 struct Module {
@@ -113,6 +115,8 @@ struct Module {
     CUfunction f_n2_rhs = nullptr, f_n2_solve = nullptr, f_reduce = nullptr, f_peak = nullptr, f_probe = nullptr;
     int solve_blocks_per_sm = 0;
     size_t solve_smem = 0;
+    std::mutex mu;             // guards the scratch ring
+    std::mutex host_mu;        // serialises the synchronous host-buffer entry points (they share ws / pipe_ws)
     Scratch ring[8];
     int ring_next = 0;
     // grow-only workspaces of the *_host entry points and the reductions
@@ -165,20 +169,33 @@ int pipe_reserve(Module* M, int k, int slot, size_t bytes, CUdeviceptr* out)
     return 0;
 }
 
-// Per-launch scratch (work-queue counter, z_eval, objective reference): a ring of 8 slots per module, so that up
-// to 8 launches of one module may be in flight on different streams (the Python pipeline uses 3 per call and
-// synchronises before returning); a slot is re-used only after 8 further launches.
-int scratch_get(Module* M, size_t bytes, CUdeviceptr* out)
+// Per-launch scratch (work-queue counter, z_eval, objective reference): a ring of 8 slots per module.  Every slot
+// carries an event recorded behind the launch that uses it; taking a slot waits for that event, so any number of
+// launches may be in flight on any streams (the 9th simply waits for the 1st to finish).  Ring bookkeeping is guarded
+// by the module's mutex: concurrent host threads may launch on the same module.
+int scratch_get(Module* M, size_t bytes, CUdeviceptr* out, Scratch** slot)
 {
+    std::lock_guard<std::mutex> lk(M->mu);
     Scratch& s = M->ring[M->ring_next];
     M->ring_next = (M->ring_next + 1) % 8;
+    if (s.in_flight) { CU(cuEventSynchronize(s.done)); s.in_flight = false; }
+    if (!s.done) CU(cuEventCreate(&s.done, CU_EVENT_DISABLE_TIMING));
     if (s.bytes < bytes) {
-        if (s.p) { CU(cuCtxSynchronize()); CU(cuMemFree(s.p)); s.p = 0; s.bytes = 0; }
+        if (s.p) { CU(cuMemFree(s.p)); s.p = 0; s.bytes = 0; }
         size_t want = std::max<size_t>(bytes, 64*1024);
         CU(cuMemAlloc(&s.p, want));
         s.bytes = want;
     }
     *out = s.p;
+    *slot = &s;
+    return 0;
+}
+
+int scratch_launched(Module* M, Scratch* s, CUstream st)
+{
+    std::lock_guard<std::mutex> lk(M->mu);
+    CU(cuEventRecord(s->done, st));
+    s->in_flight = true;
     return 0;
 }
 
@@ -462,7 +479,7 @@ int rmt_module_free(rmt_module_t m)
     if (g_ctx && drv.p_cuCtxSetCurrent) {
         drv.p_cuCtxSetCurrent(g_ctx);
         drv.p_cuCtxSynchronize();
-        for (auto& s : M->ring) if (s.p) drv.p_cuMemFree(s.p);
+        for (auto& s : M->ring) { if (s.p) drv.p_cuMemFree(s.p); if (s.done) drv.p_cuEventDestroy(s.done); }
         for (auto& w : M->ws) if (w) drv.p_cuMemFree(w);
         for (int k = 0; k < 2; ++k) {
             for (auto& w : M->pipe_ws[k]) if (w) drv.p_cuMemFree(w);
@@ -540,11 +557,13 @@ int rmt_n1_solve(rmt_module_t m, int64_t B, const double* d_consts, int32_t n_ev
     if (!(z_eval[n_eval - 1] > 0.0)) return fail("rmt_n1_solve: the last output position must be > 0");
     if (!(rtol > 0.0) || !(atol >= 0.0)) return fail("rmt_n1_solve: rtol must be > 0 and atol >= 0");
     if ((obj_ref == nullptr) != (d_obj == nullptr)) return fail("rmt_n1_solve: obj_ref and d_obj go together");
+    if (!d_consts || !d_out || !d_status) return fail("rmt_n1_solve: d_consts, d_out and d_status are required (d_stats may be NULL)");
     CUstream st = (CUstream)stream;
     const int n = M->info.n;
     size_t need = 64 + 8*(size_t)n_eval + 8*(size_t)n;
     CUdeviceptr scr;
-    if (scratch_get(M, need, &scr)) return 1;
+    Scratch* slot = nullptr;
+    if (scratch_get(M, need, &scr, &slot)) return 1;
     CU(cuMemsetD8Async(scr, 0, 64, st));
     CU(cuMemcpyHtoDAsync(scr + 64, z_eval, 8*(size_t)n_eval, st));
     if (obj_ref) CU(cuMemcpyHtoDAsync(scr + 64 + 8*(size_t)n_eval, obj_ref, 8*(size_t)n, st));
@@ -563,7 +582,8 @@ int rmt_n1_solve(rmt_module_t m, int64_t B, const double* d_consts, int32_t n_ev
     long long cap = (long long)g_sm_count*M->solve_blocks_per_sm;
     unsigned grid = (unsigned)std::max<long long>(1, std::min(want, cap));
     void* params[] = {&a};
-    return launch(M->f_n1_solve, grid, block, M->solve_smem, st, params, "rmt_n1_solve");
+    if (launch(M->f_n1_solve, grid, block, M->solve_smem, st, params, "rmt_n1_solve")) return 1;
+    return scratch_launched(M, slot, st);
 }
 
 int rmt_n1_solve_host(rmt_module_t m, int64_t B, const double* h_rows, int32_t n_rows, const int32_t* row_map,
@@ -576,6 +596,7 @@ int rmt_n1_solve_host(rmt_module_t m, int64_t B, const double* h_rows, int32_t n
     if (!M) return fail("invalid module handle");
     if (ensure_ctx()) return 1;
     if (B <= 0) return fail("rmt_n1_solve_host: B must be positive");
+    std::lock_guard<std::mutex> host_lk(M->host_mu);
     if (check_rows(M, n_rows, row_map, uniform, h_rows)) return 1;
     if (!h_out || !h_status) return fail("rmt_n1_solve_host: h_out and h_status are required");
     const int n = M->info.n;
@@ -688,10 +709,12 @@ int rmt_n2_solve(rmt_module_t m, int64_t B, int32_t zNo, int32_t tNo, double per
     if (B <= 0 || zNo < 2 || tNo < 1 || !(period > 0.0)) return fail("rmt_n2_solve: need B > 0, zNo >= 2, tNo >= 1, period > 0");
     if (!(rtol > 0.0) || !(atol >= 0.0)) return fail("rmt_n2_solve: rtol must be > 0 and atol >= 0");
     if (!d_work) return fail("rmt_n2_solve: d_work is required (rmt_n2_work_doubles)");
+    if (!d_consts || !d_out || !d_status) return fail("rmt_n2_solve: d_consts, d_out and d_status are required (d_stats may be NULL)");
     if (M->info.n > 15) return fail("rmt_n2_solve: more than 15 unknowns per node are not supported (pivot packing)");
     CUstream st = (CUstream)stream;
     CUdeviceptr scr;
-    if (scratch_get(M, 64, &scr)) return 1;
+    Scratch* slot = nullptr;
+    if (scratch_get(M, 64, &scr, &slot)) return 1;
     CU(cuMemsetD8Async(scr, 0, 64, st));
     SolveArgsN2 a;
     a.consts = (CUdeviceptr)d_consts; a.B = B; a.zNo = zNo; a.tNo = tNo; a.period = period;
@@ -705,7 +728,8 @@ int rmt_n2_solve(rmt_module_t m, int64_t B, int32_t zNo, int32_t tNo, double per
     const int block = M->info.block;
     unsigned grid = (unsigned)(n2_slots(M, B)/block);
     void* params[] = {&a};
-    return launch(M->f_n2_solve, grid, block, 0, st, params, "rmt_n2_solve");
+    if (launch(M->f_n2_solve, grid, block, 0, st, params, "rmt_n2_solve")) return 1;
+    return scratch_launched(M, slot, st);
 }
 
 int rmt_reduce_objective(rmt_module_t m, int64_t n, const double* d_obj, int64_t index_offset,
@@ -715,6 +739,7 @@ int rmt_reduce_objective(rmt_module_t m, int64_t n, const double* d_obj, int64_t
     if (!M) return fail("invalid module handle");
     if (ensure_ctx()) return 1;
     if (n <= 0) return fail("rmt_reduce_objective: n must be positive");
+    std::lock_guard<std::mutex> host_lk(M->host_mu);
     CUstream st = (CUstream)stream;
     const unsigned blocks = (unsigned)std::min<long long>(256, (n + 255)/256);
     CUdeviceptr part;
@@ -764,6 +789,7 @@ int rmt_fp64_peak(rmt_module_t m, int32_t iters, int32_t repeats, double* tflops
     if (!M) return fail("invalid module handle");
     if (ensure_ctx()) return 1;
     if (!M->f_peak) return fail("module lacks rmt_dfma_peak");
+    std::lock_guard<std::mutex> host_lk(M->host_mu);
     const unsigned blocks = (unsigned)g_sm_count*8, threads = 256;
     CUdeviceptr out;
     if (ws_reserve(M, 7, 8*(size_t)blocks*threads, &out)) return 1;

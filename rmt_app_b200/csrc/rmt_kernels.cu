@@ -1505,11 +1505,23 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
             bad = bad || !(fabs(ynew[i]) <= 1.7e308);
         }
         err = rmt_sqrt(err*(1.0/RMT_N));
-        // domain guard: concentrations never change sign in the exact solution (a negative one can run away
-        // through second-order terms, e.g. -k*C^2); a species that sits in a denominator / log / sqrt of the
-        // kinetics must stay strictly positive.  A step that violates this is rejected like a failed error test.
+        // domain guard.  RMT_POSITIVE[i]: the kinetics have a pole where species i vanishes (it reaches a denominator
+        // that can become zero, a logarithm, a negative / non-integer power — decided by a sign analysis of the traced
+        // rates and their partials, kinetics.positive_species): such a species must stay strictly positive, a step
+        // that violates this is rejected like a failed error test (the reference raises there).  Every other species
+        // may sit at exactly zero (zero feed and never formed, e.g. inside an LHHW term 1 + K*p_i) or reach it
+        // (irreversible reaction at complete conversion, where the exact zero sits at the rounding floor with a random
+        // sign): a value that is negative within the error tolerance IS that zero and is taken as such; only a value
+        // further below zero than the tolerance allows is rejected (a negative concentration can run away through
+        // second-order terms, e.g. -k*C^2).
 #pragma unroll
-        for (int i = 0; i < RMT_NC; ++i) bad = bad || (RMT_POSITIVE[i] ? !(ynew[i] > 0.0) : (ynew[i] < 0.0));
+        for (int i = 0; i < RMT_NC; ++i) {
+            if (RMT_POSITIVE[i]) bad = bad || !(ynew[i] > 0.0);
+            else {
+                bad = bad || (ynew[i] < -(a.ctrl[3]*(a.atol + a.rtol*fabs(y[i]))));
+                ynew[i] = fmax(ynew[i], 0.0);
+            }
+        }
         if (bad || !(err == err)) err = 1e30;
 
         // step-size controller: Hairer-Wanner with Gustafsson's predictive correction
@@ -1589,11 +1601,13 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
         }
         if (fin >= 0 && live) {
             a.status[inst] = fin;
-            a.stats[inst] = nacc; a.stats[a.B + inst] = nrej;
-            int nnew = 0;
+            if (a.stats) {                                       // optional (rmt_b200.h)
+                a.stats[inst] = nacc; a.stats[a.B + inst] = nrej;
+                int nnew = 0;
 #pragma unroll
-            for (int q = 1; q < RMT_ROS_S; ++q) nnew += RMT_ROS_NEWF[q];
-            a.stats[2*a.B + inst] = (nacc + nrej)*nnew; a.stats[3*a.B + inst] = nacc + nrej;
+                for (int q = 1; q < RMT_ROS_S; ++q) nnew += RMT_ROS_NEWF[q];
+                a.stats[2*a.B + inst] = (nacc + nrej)*nnew; a.stats[3*a.B + inst] = nacc + nrej;
+            }
             if (fin != 0) {
                 // make failures loud in the data as well: NaN for every point not yet written
                 double v[RMT_N];
@@ -2541,8 +2555,10 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
         if (fin >= 0) {
             if (live && g == 0) {
                 a.status[inst] = fin;
-                a.stats[inst] = nacc; a.stats[a.B + inst] = nrej;
-                a.stats[2*a.B + inst] = (nacc + nrej)*(RMT_ROS_S - 1); a.stats[3*a.B + inst] = nacc + nrej;
+                if (a.stats) {
+                    a.stats[inst] = nacc; a.stats[a.B + inst] = nrej;
+                    a.stats[2*a.B + inst] = (nacc + nrej)*(RMT_ROS_S - 1); a.stats[3*a.B + inst] = nacc + nrej;
+                }
             }
             if (live && fin != 0) {
                 const int rows = n2_out_rows(a.out_mode);

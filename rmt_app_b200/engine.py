@@ -74,18 +74,71 @@ def default_block(spec, stages=6, reduced=None):
     return int(max(32, min(256, (fit//32)*32)))
 
 
-def _fn_sig(f):
-    cells = ()
-    if getattr(f, "__closure__", None):
-        out = []
-        for c in f.__closure__:
-            try:
-                v = c.cell_contents
-            except ValueError:
-                v = None
-            out.append(v if isinstance(v, (int, float, str, bool, type(None))) else id(v))
-        cells = tuple(out)
-    return (f.__code__, cells, repr(f.__defaults__), id(f.__globals__))
+class _NoFastKey(Exception):
+    """A value the cheap identity cannot describe: compile_model falls back to tracing (always correct)."""
+
+
+def _value_sig(v, depth=0):
+    """Hashable description of a value the tracer would bake into the graph as a constant."""
+    import types
+    if isinstance(v, (float, np.floating)):
+        return (type(v).__name__, float(v).hex())            # -0.0 != 0.0, nan == nan
+    if isinstance(v, (int, str, bool, complex, bytes, type(None))):
+        return (type(v).__name__, v)
+    if isinstance(v, (np.integer, np.bool_)):
+        return (type(v).__name__, v.item())
+    if isinstance(v, np.ndarray):
+        if v.size > 4096 or v.dtype == object:
+            raise _NoFastKey()
+        return ("ndarray", v.shape, str(v.dtype), v.tobytes())
+    if isinstance(v, (list, tuple)):
+        if len(v) > 4096 or depth > 4:
+            raise _NoFastKey()
+        return (type(v).__name__, tuple(_value_sig(x, depth + 1) for x in v))
+    if isinstance(v, dict):
+        if len(v) > 4096 or depth > 4:
+            raise _NoFastKey()
+        return ("dict", tuple((repr(k), _value_sig(x, depth + 1)) for k, x in v.items()))
+    if isinstance(v, types.ModuleType):
+        return ("module", v.__name__)
+    if isinstance(v, types.FunctionType):
+        if depth > 4:
+            raise _NoFastKey()
+        return ("function", _fn_sig(v, depth + 1))
+    if isinstance(v, (types.BuiltinFunctionType, np.ufunc, type)):
+        return ("callable", getattr(v, "__module__", None), getattr(v, "__qualname__", getattr(v, "__name__", None)))
+    raise _NoFastKey()
+
+
+def _code_names(code):
+    """Global / attribute names a code object (and the code objects nested in it) can look up."""
+    import types
+    names = set(code.co_names)
+    for c in code.co_consts:
+        if isinstance(c, types.CodeType):
+            names |= _code_names(c)
+    return names
+
+
+def _fn_sig(f, depth=0):
+    """Identity of a kinetics lambda for the compile cache: its code object AND everything the tracer would read
+    through it and bake into the graph — closure cells, the module-level globals its code names, defaults.  A
+    parameter-estimation loop that rebinds a global pre-exponential, or mutates an array captured in a closure,
+    therefore gets a new key (the key used to hold only id(f.__globals__) and primitive cells)."""
+    cells = []
+    for c in (getattr(f, "__closure__", None) or ()):
+        try:
+            cells.append(_value_sig(c.cell_contents, depth + 1))
+        except ValueError:                      # empty cell
+            cells.append(("empty",))
+    globs = []
+    g = f.__globals__
+    for name in sorted(_code_names(f.__code__)):
+        if name in g:
+            globs.append((name, _value_sig(g[name], depth + 1)))
+    defaults = _value_sig(f.__defaults__, depth + 1) if f.__defaults__ else None
+    kwdefaults = _value_sig(f.__kwdefaults__, depth + 1) if f.__kwdefaults__ else None
+    return (f.__code__, tuple(cells), tuple(globs), defaults, kwdefaults)
 
 
 def n2_lanes(B, zNo, sm_count=148):
@@ -150,10 +203,16 @@ def _fast_key(modelInput, block):
     import types
     rr = modelInput["reaction-rates"]
     sig = []
+    from .kinetics import _is_scalar_param
     for k, v in rr["VARS"].items():
-        sig.append((k, _fn_sig(v)) if isinstance(v, types.FunctionType) else (k, type(v).__name__))
+        if isinstance(v, types.FunctionType):
+            sig.append((k, _fn_sig(v)))
+        elif _is_scalar_param(v):
+            sig.append((k, "param"))            # a kinetic-parameter slot: its value is a run-time input, not baked
+        else:
+            sig.append((k, _value_sig(v)))      # arrays / lists / bools / strings are baked into the graph
     for k, v in rr["RATES"].items():
-        sig.append((k, _fn_sig(v)) if isinstance(v, types.FunctionType) else (k, type(v).__name__))
+        sig.append((k, _fn_sig(v)) if isinstance(v, types.FunctionType) else (k, _value_sig(v)))
     return (modelInput["model"], tuple(modelInput["feed"]["components"]["shell"]),
             modelInput["operating-conditions"].get("process-type"), tuple(modelInput["reactions"].values()),
             tuple(sig), block)

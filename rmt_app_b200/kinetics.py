@@ -235,38 +235,128 @@ class KineticsIR:
         return out
 
     def positive_species(self):
-        """Species whose concentration / mole fraction reaches a denominator, a
-        logarithm, a square root or a non-integer / negative power anywhere in
-        the rates: the kinetics are undefined (or change sign through a pole)
-        at non-positive values, so the integrator must keep them > 0 — in the
-        reference such a state raises (`math domain error`) or silently runs on
-        the wrong side of the pole."""
+        """Species that must stay STRICTLY positive: those whose vanishing (on its own, every other species, T and P
+        positive) makes a denominator zero or puts a non-positive argument into a logarithm / a negative or zero one
+        into a non-integer or negative power — anywhere in the rates or in their partial derivatives (so the 1/sqrt
+        of a square root's derivative counts).  There the kinetics have a pole: the reference raises (`math domain
+        error`, `ZeroDivisionError`) or silently runs on the wrong side of it.
+
+        Decided by a sign analysis of the DAG (abstract values = subsets of {-, 0, +}), not by mere dependence: the
+        LHHW denominator `1 + K*p_i` depends on species i but is >= 1 when p_i -> 0, so a zero-feed species that only
+        occurs there is NOT flagged and may sit at exactly 0 for the whole integration.  Kinetic-parameter
+        slots carry the sign of their default value."""
         g = self.g
+        if self.partials is None:
+            self.differentiate()
+        outs = list(self.rates) + [d for row in self.partials.values() for d in row if d is not None]
+        order = g.topo(outs)
+        NEG, ZERO, POS = 1, 2, 4
+        FULL = NEG | ZERO | POS
+
+        def bits(m):
+            return [b for b in (NEG, ZERO, POS) if m & b]
+
+        def flip(m):
+            return (POS if m & NEG else 0) | (m & ZERO) | (NEG if m & POS else 0)
+
+        def add(a, b):
+            r = 0
+            for x in bits(a):
+                for y in bits(b):
+                    r |= y if x == ZERO else x if (y == ZERO or x == y) else FULL
+            return r
+
+        def mul(a, b):
+            r = 0
+            for x in bits(a):
+                for y in bits(b):
+                    r |= ZERO if ZERO in (x, y) else (POS if x == y else NEG)
+            return r
+
+        def sgn(v):
+            return POS if v > 0 else NEG if v < 0 else ZERO if v == 0 else FULL
+
         dep = {}
-        need = 0
-        for n in g.topo(self.rates):
+        for n in order:
             if n.op == "in":
+                dep[n.id] = (1 << int(n.name[1:])) if (n.name[0] in "yC" and n.name[1:].isdigit()) else 0
+            else:
                 m = 0
-                if n.name[0] in "yC" and n.name[1:].isdigit():
-                    m = 1 << int(n.name[1:])
+                for a in n.args:
+                    m |= dep[a.id]
                 dep[n.id] = m
-                continue
-            if n.op == "const":
-                dep[n.id] = 0
-                continue
-            m = 0
-            for a in n.args:
-                m |= dep[a.id]
-            dep[n.id] = m
-            if n.op == "div":
-                need |= dep[n.args[1].id]
-            elif n.op in ("log", "log10", "log2", "sqrt", "log1p"):
-                need |= dep[n.args[0].id]
-            elif n.op == "pow":
-                need |= dep[n.args[0].id]
-            elif n.op == "powi" and n.value < 0:
-                need |= dep[n.args[0].id]
-        return [bool(need >> i & 1) for i in range(self.nc)]
+        flagged = []
+        for i in range(self.nc):
+            sg = {}
+            need = False
+            for n in order:
+                a = [sg[x.id] for x in n.args]
+                pole = False
+                if n.op == "in":
+                    if n.name.startswith("kp"):
+                        v = sgn(self.param_defaults[int(n.name[2:])])
+                    elif n.name in ("y%d" % i, "C%d" % i):
+                        v = ZERO | POS
+                    else:
+                        v = POS
+                elif n.op == "const":
+                    v = sgn(n.value)
+                elif n.op == "neg":
+                    v = flip(a[0])
+                elif n.op == "abs":
+                    v = (a[0] & ZERO) | (POS if a[0] & (NEG | POS) else 0)
+                elif n.op in ("exp", "exp10", "cosh"):
+                    v = POS
+                elif n.op == "sqrt":
+                    pole = bool(a[0] & NEG)
+                    v = a[0] & (ZERO | POS) or FULL
+                elif n.op in ("cbrt", "sinh", "tanh", "atan", "asin", "expm1"):
+                    v = a[0]
+                elif n.op in ("log", "log10", "log2"):
+                    pole = bool(a[0] & (NEG | ZERO))
+                    v = FULL
+                elif n.op == "log1p":
+                    pole = bool(a[0] & NEG)
+                    v = a[0] if not a[0] & NEG else FULL
+                elif n.op == "add":
+                    v = add(a[0], a[1])
+                elif n.op == "sub":
+                    v = add(a[0], flip(a[1]))
+                elif n.op == "mul":
+                    v = mul(a[0], a[1])
+                elif n.op == "div":
+                    pole = bool(a[1] & ZERO)
+                    v = FULL if pole else mul(a[0], a[1])
+                elif n.op == "pow":
+                    expo = n.args[1]
+                    pos_const = expo.op == "const" and expo.value > 0
+                    pole = bool(a[0] & NEG) or (bool(a[0] & ZERO) and not pos_const)
+                    v = POS if a[0] == POS else ((ZERO | POS) if (not a[0] & NEG and pos_const) else FULL)
+                elif n.op == "powi":
+                    k = int(n.value)
+                    pole = k < 0 and bool(a[0] & ZERO)
+                    if k == 0:
+                        v = POS
+                    elif k % 2 == 0:
+                        v = (a[0] & ZERO) | (POS if a[0] & (NEG | POS) else 0)
+                    else:
+                        v = a[0]
+                    if pole:
+                        v = FULL
+                elif n.op in ("min", "max"):
+                    rank = {NEG: 0, ZERO: 1, POS: 2}
+                    pick = max if n.op == "max" else min
+                    v = 0
+                    for x in bits(a[0]):
+                        for y in bits(a[1]):
+                            v |= pick(x, y, key=rank.get)
+                else:                               # sin, cos, tan, acos, atan2, ...: no sign information
+                    v = FULL
+                sg[n.id] = v
+                if pole and (dep[n.id] >> i) & 1:
+                    need = True
+            flagged.append(need)
+        return flagged
 
     def evaluate(self, T, P, y, C, params=None):
         """Host interpreter of the traced rates (tests of the tracer only)."""

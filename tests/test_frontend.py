@@ -145,3 +145,58 @@ def test_n_unknowns():
     assert ModelSpec(cases.methanol_readme_input("N2")).n == 7
     assert ModelSpec(cases.ch4_input("N2", "iso-thermal")).n == 3
     assert ModelSpec(cases.ch4_input("N1", "iso-thermal")).n == 4
+
+
+K0_GLOBAL = 7.2e-4
+_TABLE = np.array([1.0, 2.0])
+
+
+def _ch4_with_global_kinetics(extra_vars=None):
+    mi = cases.ch4_input("N1")
+    varis = {"C": lambda x: x['SpCoi'][0]}
+    varis.update(extra_vars or {})
+    mi["reaction-rates"] = {"VARS": varis, "RATES": {"r1": lambda x: K0_GLOBAL*_TABLE[1]*(x['C']**2)}}
+    return mi
+
+
+def test_compile_cache_sees_globals_closures_and_baked_vars():
+    """the fast cache key must change when anything the tracer bakes into the graph changes — a module-level
+    global a lambda reads, the contents of an array it indexes, a closure cell, a non-scalar VARS entry — and must NOT
+    change for scalar VARS values (those are run-time kinetic-parameter slots)."""
+    global K0_GLOBAL
+    cm_a = engine.compile_model(_ch4_with_global_kinetics())
+    assert engine.compile_model(_ch4_with_global_kinetics()) is cm_a
+    old = K0_GLOBAL
+    try:
+        K0_GLOBAL = 9.9e-4                                  # rebinding a global constant between two calls
+        cm_b = engine.compile_model(_ch4_with_global_kinetics())
+        assert cm_b is not cm_a and cm_b.header != cm_a.header
+        assert "0.00099" in cm_b.header.replace("9.9e-04", "0.00099").replace("9.9000000000000002e-04", "0.00099") \
+            or cm_b.spec.key() != cm_a.spec.key()
+    finally:
+        K0_GLOBAL = old
+    assert engine.compile_model(_ch4_with_global_kinetics()) is cm_a
+    _TABLE[1] = 3.0                                         # mutating an array the lambda indexes
+    try:
+        cm_c = engine.compile_model(_ch4_with_global_kinetics())
+        assert cm_c is not cm_a and cm_c.spec.key() != cm_a.spec.key()
+    finally:
+        _TABLE[1] = 2.0
+
+    def with_closure(k):
+        mi = cases.ch4_input("N1")
+        scale = [k]                                         # a mutable object in a closure cell
+        mi["reaction-rates"] = {"VARS": {"C": lambda x: x['SpCoi'][0]}, "RATES": {"r1": lambda x: scale[0]*(x['C']**2)}}
+        return mi
+    assert engine.compile_model(with_closure(1.0)).spec.key() != engine.compile_model(with_closure(2.0)).spec.key()
+    # non-scalar VARS entries are constants of the graph; scalar ones are parameter slots
+    def with_vars(extra, rate):
+        mi = _ch4_with_global_kinetics(extra)
+        mi["reaction-rates"]["RATES"] = {"r1": rate}
+        return mi
+    a = engine.compile_model(with_vars({"w": [1.0, 2.0]}, lambda x: x['w'][1]*(x['C']**2)))
+    b = engine.compile_model(with_vars({"w": [1.0, 5.0]}, lambda x: x['w'][1]*(x['C']**2)))
+    assert a is not b and a.spec.key() != b.spec.key()
+    p1 = engine.compile_model(with_vars({"k": 1.0}, lambda x: x['k']*(x['C']**2)))
+    p2 = engine.compile_model(with_vars({"k": 2.0}, lambda x: x['k']*(x['C']**2)))
+    assert p1 is p2 and p1.spec.kin.param_names == ["k"]

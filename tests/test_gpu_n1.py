@@ -357,3 +357,73 @@ def test_branch_free_device_math_accuracy():
         assert relerr(o[3], np.power(10.0, xs), m10) < 4*ulp
         nz = (np.abs(xs) > 1e-290) & (np.abs(xs) < 1e290)
         assert relerr(o[4], 1.0/xs, nz) < 2*ulp
+
+
+def _with_inert(mi, sym="CO"):
+    """ch4 input plus a zero-feed inert species `sym` (never formed by the reaction)."""
+    mi["feed"]["components"]["shell"] = list(mi["feed"]["components"]["shell"]) + [sym]
+    mi["feed"]["concentration"] = np.append(np.asarray(mi["feed"]["concentration"], float), 0.0)
+    return mi
+
+
+@pytest.mark.parametrize("process", ["iso-thermal", "non-iso-thermal"])
+@pytest.mark.parametrize("reduced", [True, False])
+def test_zero_feed_species_inside_a_denominator(process, reduced):
+    """a species with zero feed that is never produced stays exactly 0; when it only occurs in an LHHW-type
+    term 1 + K*y_i there is no pole at 0, the sign analysis does not flag it, and the integration runs like the
+    reference's (which has no positivity restriction, pbHomoReactor.py:3148-3175) — in the reaction-extent form and in
+    the full-state form."""
+    eng = _engine()
+    mi = _with_inert(cases.ch4_input("N1", process))
+    mi["reaction-rates"] = {
+        "VARS": {"k0": 0.0072*1e-1, "K": 40.0, "C_CH4": lambda x: x['SpCoi'][0], "y_CO": lambda x: x['MoFri'][3]},
+        "RATES": {"r1": lambda x: x['k0']*(x['C_CH4']**2)/(1 + x['K']*x['y_CO'])},
+    }
+    cm = eng.compile_model(mi, reduced=reduced)
+    assert cm.reduced == reduced
+    assert cm.spec.kin.positive_species() == [False, False, False, False]
+    z = np.linspace(0, 1, 11)
+    for tol in (dict(rtol=1e-3, atol=1e-6), TIGHT):
+        r = eng.n1_solve_ensemble(cm, mi, None, 1, z_eval=z, **tol)
+        assert r.status[0] == 0, r.status
+        assert r.stats[1, 0] <= 0.25*r.stats[0, 0] + 3            # no rejection storm
+        assert (r.out[:, 3, 0] == 0.0).all()                      # the inert's mole fraction is exactly zero everywhere
+    want = O.N1Oracle(mi).solve(method="LSODA", rtol=1e-11, atol=1e-13, t_eval=z)
+    got = r.out[:, :, 0].T                                        # dataYs rows: y_i..., P, (T)
+    ref = O.N1Oracle(mi).pack(want)[0]["dataYs"]
+    live = [0, 1, 2] + list(range(4, got.shape[0]))
+    assert np.max(np.abs(got[live] - ref[live])/np.abs(ref[live])) < 1e-6
+    # the same species under a true pole (division by its mole fraction) IS flagged, and the run fails loudly
+    mi2 = _with_inert(cases.ch4_input("N1", process))
+    mi2["reaction-rates"] = {
+        "VARS": {"k0": 0.0072*1e-1, "C_CH4": lambda x: x['SpCoi'][0], "y_CO": lambda x: x['MoFri'][3]},
+        "RATES": {"r1": lambda x: x['k0']*(x['C_CH4']**2)*x['y_CO']/x['y_CO']},
+    }
+    cm2 = eng.compile_model(mi2, reduced=reduced)
+    assert cm2.spec.kin.positive_species() == [False, False, False, True]
+    assert eng.n1_solve_ensemble(cm2, mi2, None, 1, **TIGHT).status[0] != 0
+
+
+@pytest.mark.parametrize("reduced", [True, False])
+def test_irreversible_reaction_at_complete_conversion(reduced):
+    """a fast irreversible first-order reaction consumes its reactant completely within the first tenth of the
+    bed; afterwards the exact solution's zero sits at the rounding floor (y = y0 + nu^T xi in the extent form) with a
+    random sign.  A negative value within the error tolerance is that zero: no rejection storm, status 0, and the
+    products agree with the oracle."""
+    eng = _engine()
+    mi = cases.ch4_input("N1", "iso-thermal")
+    mi["reaction-rates"] = {"VARS": {"k0": 40.0, "C_CH4": lambda x: x['SpCoi'][0]},
+                            "RATES": {"r1": lambda x: x['k0']*x['C_CH4']}}
+    cm = eng.compile_model(mi, reduced=reduced)
+    assert cm.spec.kin.positive_species() == [False, False, False]
+    z = np.linspace(0, 1, 21)
+    want = O.N1Oracle(mi).pack(O.N1Oracle(mi).solve(method="LSODA", rtol=1e-12, atol=1e-14, t_eval=z))[0]["dataYs"]
+    assert want[0, -1] < 1e-9                                     # the reactant is gone at the outlet
+    for tol, bar in ((dict(rtol=1e-3, atol=1e-6), 5e-3), (TIGHT, 1e-6)):
+        r = eng.n1_solve_ensemble(cm, mi, None, 1, z_eval=z, **tol)
+        assert r.status[0] == 0, r.status
+        assert r.stats[1, 0] <= 0.5*r.stats[0, 0] + 3, r.stats[:, 0]
+        got = r.out[:, :, 0].T
+        assert (got[:3] >= 0).all()
+        assert np.max(np.abs(got[1:] - want[1:])/np.abs(want[1:])) < bar
+        assert np.max(np.abs(got[0] - want[0])) < bar             # the vanishing reactant: absolute (mole fraction)

@@ -205,3 +205,70 @@ def test_n2_isothermal_parity(n2_settings):
     assert rb["dataYs"].shape == (3, 5, 4, z) and rb["success"].all()
     np.testing.assert_array_equal(rb["dataYs"][:, :, 3, :], np.broadcast_to(sw["temperature"].reshape(3, 1, 1), (3, 5, z)))
     np.testing.assert_allclose(rb["dataYs"][1, :, :3, :], np.array([d["dataYs"][:3] for d in dflt]), rtol=1e-12)
+
+
+def _slab_errors(dp, ref):
+    rel = np.abs(dp["dataYs"] - ref)/np.abs(ref)
+    return rel[-1].max(), rel[:, -1].max(), rel.max()
+
+
+def test_n2_config2_z50_tight_against_converged_oracle(n2_settings):
+    """BASELINE config 2 (README inputs, 50 axial nodes) at the parity-grade tolerance: outlet mole fractions and the
+    temperature profile of all five slabs within 1e-6 of the converged oracle run (BDF rtol 1e-9 / atol 1e-12,
+    tests/golden/n2_sol_m50_oracle_tight.npz; the oracle RHS is pinned to modelEquationN2 at 50 nodes to 1e-12)."""
+    from rmt_app_b200 import rmtExe
+    conv = np.load(os.path.join(GOLDEN, "n2_sol_m50_oracle_tight.npz"))
+    assert int(conv["zNo"]) == 50
+    n2_settings["N2"]["zNo"] = 50
+    mi = cases.methanol_readme_input("N2")
+    mi["solver-config"].update(rtol=1e-8, atol=1e-11)
+    res = rmtExe(mi)["resModel"]
+    assert len(res["dataPack"]) == 5
+    for i, dp in enumerate(res["dataPack"]):
+        eT, eOut, eAll = _slab_errors(dp, conv["dataYs"][i])
+        assert eT < 1e-6, (i, eT)                # temperature profile, all 50 nodes
+        assert eOut < 1e-6, (i, eOut)            # outlet mole fractions + outlet temperature
+        assert eAll < 1e-5, (i, eAll)            # every species at every node (trace species near 1e-5 mole fraction)
+        np.testing.assert_allclose(dp["dataTime"], conv["dataTime"][i])
+
+
+def test_n2_ch4_tight_against_converged_oracle(n2_settings):
+    """Methane coupling (nc = 3, one reaction), 20 nodes: all slabs within 1e-6 of the converged ORACLE run
+    (n2_sol_ch4_oracle_tight.npz) — the twin of the check against the reference's own tight run above."""
+    from rmt_app_b200 import rmtExe
+    conv = np.load(os.path.join(GOLDEN, "n2_sol_ch4_oracle_tight.npz"))
+    n2_settings["N2"]["zNo"] = int(conv["zNo"])
+    mi = cases.ch4_input("N2")
+    mi["solver-config"].update(rtol=1e-9, atol=1e-12)
+    res = rmtExe(mi)["resModel"]
+    for i, dp in enumerate(res["dataPack"]):
+        np.testing.assert_allclose(dp["dataYs"], conv["dataYs"][i], rtol=1e-6)
+
+
+def test_n2_config5_z200_against_converged_oracle(n2_settings):
+    """BASELINE config 5's grid (200 nodes, period 0.5 s, 5 slabs): three instances of the per-GPU share (seed 20240613,
+    indices 0 / 6789 / 12499) against converged oracle runs (tests/golden/n2_sol_config5_z200_oracle_tight.npz, made by
+    make_golden_oracle.py config5).  The instances are solved INSIDE an ensemble large enough for the 8-lane launch shape
+    config 5 uses (25 node groups of 8, hand-over between groups through shared memory), and alone (32 lanes)."""
+    from rmt_app_b200 import engine, rmtExeBatchN2
+    conv = np.load(os.path.join(GOLDEN, "n2_sol_config5_z200_oracle_tight.npz"))
+    zNo, idx = int(conv["zNo"]), [int(i) for i in conv["index"]]
+    assert zNo == 200
+    mi = cases.methanol_readme_input("N2")
+    full = cases.config3_sweep(int(conv["B"]), int(conv["seed"]))
+    # 12 500-reactor launch shape (8 lanes per reactor) with the three fixture instances planted among other reactors
+    B = 12500
+    assert engine.n2_lanes(B, zNo) == 8
+    r = rmtExeBatchN2(mi, full, zNo=zNo, tNo=5, rtol=1e-8, atol=1e-11)
+    assert r["success"].all()
+    for j, i in enumerate(idx):
+        got = r["dataYs"][i]                                          # [tNo][nc+1][zNo]
+        for s in range(5):
+            ref = conv["dataYs"][j][s]
+            rel = np.abs(got[s] - ref)/np.abs(ref)
+            assert rel[-1].max() < 1e-6, (i, s, rel[-1].max())        # temperature profile, all 200 nodes
+            assert rel[:, -1].max() < 1e-6, (i, s, rel[:, -1])        # outlet
+            assert rel.max() < 1e-5, (i, s, rel.max())
+    # the same reactors alone (32 lanes per reactor): same solution to rounding
+    one = rmtExeBatchN2(mi, {k: v[idx] for k, v in full.items()}, zNo=zNo, tNo=5, rtol=1e-8, atol=1e-11)
+    np.testing.assert_allclose(one["dataYs"], r["dataYs"][idx], rtol=1e-9)

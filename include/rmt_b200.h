@@ -41,6 +41,8 @@ extern "C" {
 
 typedef uint64_t rmt_blob_t;     /* host-side compiled module image (cubin)   */
 typedef uint64_t rmt_module_t;   /* module loaded on the current device       */
+typedef uint64_t rmt_comm_t;     /* communicator over the GPUs of one job     */
+#define RMT_COMM_ID_BYTES 128    /* size of a communicator id (ncclUniqueId)  */
 
 /* model description read back from a loaded module */
 typedef struct rmt_module_info {
@@ -133,6 +135,17 @@ int rmt_n1_solve(rmt_module_t m, int64_t B, const double* d_consts, int32_t n_ev
                  double* d_out, int32_t* d_status, int32_t* d_stats,
                  const double* obj_ref, double* d_obj, const double* ctrl, void* stream);
 
+/* Parameter-estimation populations: rmt_n1_solve for the outlet only (z = 1, out_mode 1:
+ * d_out [n][B]) with the fused objective AND its reduction: the last block of the integrator kernel to finish folds
+ * d_obj[0..B) and d_status[0..B) — in a fixed order, deterministic — into d_red[0..3] = {sum, min, argmin +
+ * index_offset (exact as a double), number of reactors with status != 0}.  No second kernel and no host round trip
+ * before the cross-GPU step: d_red may point into the buffer that is handed to rmt_comm_allgather.
+ * (no reference counterpart: the reference never implemented the estimation loop its README names, README.md:5) */
+int rmt_n1_solve_population(rmt_module_t m, int64_t B, const double* d_consts, double rtol, double atol,
+                            int32_t max_steps, double* d_out, int32_t* d_status, int32_t* d_stats,
+                            const double* obj_ref, double* d_obj, double* d_red, int64_t index_offset,
+                            const double* ctrl, void* stream);
+
 /* Same path with HOST buffers: copies inputs in, runs setup + solve, copies
  * results back, synchronises.  h_rows [n_rows][B], h_out [n_eval][rows][B].
  * From 2^18 reactors on the library cuts the ensemble into three chunks on two
@@ -164,6 +177,23 @@ int rmt_n2_solve(rmt_module_t m, int64_t B, int32_t zNo, int32_t tNo, double per
  * these three numbers, done by the caller's torch.distributed group) ------------- */
 int rmt_reduce_objective(rmt_module_t m, int64_t n, const double* d_obj, int64_t index_offset,
                          double* h_sum, double* h_min, int64_t* h_argmin, void* stream);
+
+/* ---- sharded ensembles: the cross-GPU step -------------------------
+ * Reactor instances are independent, so an ensemble is split into contiguous blocks, one per GPU (one process per
+ * GPU, rmt_init(device) in each), and nothing is exchanged on the data path.  These calls serve the END of a run:
+ * gather of results / objectives and the all-reduce of O(1) objective statistics, with NCCL over NVLink
+ * (libnccl.so.2 is loaded on first use; when the process already carries an NCCL — PyTorch's — that one is used).
+ * The reference has no counterpart: it solves one reactor per rmtExe call (docs/rmtCore.py:393-413).
+ *   rank 0: rmt_comm_unique_id(id) -> ship the RMT_COMM_ID_BYTES bytes to the other ranks by any means (file, pipe,
+ *           MPI, torch.distributed store) -> every rank: rmt_comm_init(nranks, rank, id) -> collectives -> rmt_comm_free.
+ * Buffers are DEVICE pointers, counts are in doubles; the calls are asynchronous on `stream`.
+ * rmt_comm_allgather: d_recv [nranks][count].  rmt_comm_allreduce: op 0 = sum, 1 = min, 2 = max. */
+int rmt_comm_unique_id(void* id_out, size_t id_bytes);
+int rmt_comm_init(int32_t nranks, int32_t rank, const void* id, size_t id_bytes, rmt_comm_t* comm_out);
+int rmt_comm_info(rmt_comm_t comm, int32_t* nranks, int32_t* rank, int32_t* nccl_version);
+int rmt_comm_allgather(rmt_comm_t comm, const double* d_send, double* d_recv, int64_t count, void* stream);
+int rmt_comm_allreduce(rmt_comm_t comm, const double* d_send, double* d_recv, int64_t count, int32_t op, void* stream);
+int rmt_comm_free(rmt_comm_t comm);
 
 /* ---- diagnostics: accuracy probe of the branch-free device math used by the generated kinetics:
  * d_out [5][n] = exp(x), log(x), sqrt(x), 10^x, 1/x for x = d_x[0..n). ----------------------------- */

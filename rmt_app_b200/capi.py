@@ -54,6 +54,8 @@ SIGNATURES = {
     "rmt_n1_sys": (C.c_int, [_u64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "rmt_n1_solve": (C.c_int, [_u64, _i64, _vp, _i32, _pdbl, _dbl, _dbl, _i32, _i32, _i32, _vp, _vp, _vp, _pdbl,
                                _vp, _pdbl, _vp]),
+    "rmt_n1_solve_population": (C.c_int, [_u64, _i64, _vp, _dbl, _dbl, _i32, _vp, _vp, _vp, _pdbl, _vp, _vp, _i64, _pdbl,
+                                          _vp]),
     "rmt_n1_solve_host": (C.c_int, [_u64, _i64, _vp, _i32, _pi32, _pdbl, _i32, _pdbl, _dbl, _dbl, _i32, _i32, _i32,
                                     _vp, _vp, _vp, _pdbl, _vp, _pdbl]),
     "rmt_n2_rhs": (C.c_int, [_u64, _i64, _i32, _vp, _vp, _vp, _vp]),
@@ -61,6 +63,12 @@ SIGNATURES = {
     "rmt_n2_solve": (C.c_int, [_u64, _i64, _i32, _i32, _dbl, _vp, _dbl, _dbl, _i32, _i32, _vp, _vp, _vp, _vp, _pdbl,
                                _vp]),
     "rmt_reduce_objective": (C.c_int, [_u64, _i64, _vp, _i64, _pdbl, _pdbl, C.POINTER(_i64), _vp]),
+    "rmt_comm_unique_id": (C.c_int, [_vp, C.c_size_t]),
+    "rmt_comm_init": (C.c_int, [_i32, _i32, _vp, C.c_size_t, C.POINTER(_u64)]),
+    "rmt_comm_info": (C.c_int, [_u64, _pi32, _pi32, _pi32]),
+    "rmt_comm_allgather": (C.c_int, [_u64, _vp, _vp, _i64, _vp]),
+    "rmt_comm_allreduce": (C.c_int, [_u64, _vp, _vp, _i64, _i32, _vp]),
+    "rmt_comm_free": (C.c_int, [_u64]),
     "rmt_math_probe": (C.c_int, [_u64, _i32, _vp, _vp, _vp]),
     "rmt_debug_trace": (C.c_int, [_vp, _i32, _i64]),
     "rmt_fp64_peak": (C.c_int, [_u64, _i32, _i32, _pdbl]),
@@ -212,6 +220,14 @@ class Module:
                                   None if ref is None else _dptr(ref), _ptr(d_obj),
                                   None if ctl is None else _dptr(ctl), stream))
 
+    def n1_solve_population(self, B, d_consts, rtol, atol, d_out, d_status, d_stats, obj_ref, d_obj, d_red,
+                            index_offset=0, max_steps=100000, ctrl=None, stream=None):
+        ref = np.ascontiguousarray(obj_ref, dtype=np.float64)
+        ctl = None if ctrl is None else np.ascontiguousarray(ctrl, dtype=np.float64)
+        _check(lib().rmt_n1_solve_population(self.handle, B, _ptr(d_consts), rtol, atol, max_steps, _ptr(d_out),
+                                             _ptr(d_status), _ptr(d_stats), _dptr(ref), _ptr(d_obj), _ptr(d_red),
+                                             index_offset, None if ctl is None else _dptr(ctl), stream))
+
     def n1_solve_host(self, B, h_rows, n_rows, row_map, uniform, z_eval, rtol, atol, h_out, h_status, h_stats=None,
                       max_steps=100000, dense=True, out_mode=1, obj_ref=None, h_obj=None, ctrl=None):
         row_map = np.ascontiguousarray(row_map, dtype=np.int32)
@@ -254,3 +270,41 @@ class Module:
         v = _dbl(0)
         _check(lib().rmt_fp64_peak(self.handle, iters, repeats, C.byref(v)))
         return v.value
+
+
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id():
+    """Rank 0: a fresh communicator id (bytes) to ship to the other ranks."""
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    _check(lib().rmt_comm_unique_id(C.cast(buf, _vp), COMM_ID_BYTES))
+    return buf.raw
+
+
+class Comm:
+    """NCCL communicator behind the C ABI (rmt_comm_*): gather / reduce of sharded ensembles without
+    torch.distributed.  `rmt_init(device)` must have been called in this process (capi.init)."""
+
+    def __init__(self, nranks, rank, unique_id):
+        self.handle = _u64(0)
+        self.nranks, self.rank = int(nranks), int(rank)
+        buf = C.create_string_buffer(bytes(unique_id), COMM_ID_BYTES)
+        _check(lib().rmt_comm_init(self.nranks, self.rank, C.cast(buf, _vp), COMM_ID_BYTES, C.byref(self.handle)))
+
+    def nccl_version(self):
+        v = C.c_int32(0)
+        _check(lib().rmt_comm_info(self.handle, None, None, C.byref(v)))
+        return v.value
+
+    def allgather(self, d_send, d_recv, count, stream=None):
+        _check(lib().rmt_comm_allgather(self.handle, _ptr(d_send), _ptr(d_recv), int(count), stream))
+
+    def allreduce(self, d_send, d_recv, count, op="sum", stream=None):
+        _check(lib().rmt_comm_allreduce(self.handle, _ptr(d_send), _ptr(d_recv), int(count),
+                                        {"sum": 0, "min": 1, "max": 2}[op], stream))
+
+    def close(self):
+        if self.handle is not None and self.handle.value:
+            lib().rmt_comm_free(self.handle)
+            self.handle = None

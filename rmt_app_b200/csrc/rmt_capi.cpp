@@ -9,6 +9,7 @@
 
 #include <cuda.h>
 #include <nvrtc.h>
+#include <nccl.h>          // types only: libnccl.so.2 is dlopen'ed by rmt_comm_* (a process that never shards needs no NCCL)
 #include <dlfcn.h>
 
 #include <algorithm>
@@ -226,8 +227,10 @@ struct SolveArgsN1 {
     CUdeviceptr trace;
     long long trace_inst;
     int trace_cap;
+    CUdeviceptr red;
+    long long red_offset;
 };
-static_assert(sizeof(SolveArgsN1) == 176, "SolveArgs layout");
+static_assert(sizeof(SolveArgsN1) == 192, "SolveArgs layout");
 
 struct SolveArgsN2 {
     CUdeviceptr consts;
@@ -271,6 +274,57 @@ int launch(CUfunction f, unsigned grid, unsigned block, size_t smem, CUstream st
     CUresult r = drv.p_cuLaunchKernel(f, grid, 1, 1, block, 1, 1, (unsigned)smem, st, params, nullptr);
     if (r != CUDA_SUCCESS) return cu_fail(r, name);
     return 0;
+}
+
+// ---- NCCL through dlopen (cross-GPU reduce / gather of sharded ensembles) ------------------
+#define RMT_NCCL_FUNCS(X) \
+    X(ncclGetVersion) X(ncclGetUniqueId) X(ncclCommInitRank) X(ncclCommDestroy) X(ncclAllGather) X(ncclAllReduce) \
+    X(ncclGetErrorString)
+
+struct Nccl {
+    void* lib = nullptr;
+#define X(name) decltype(&name) p_##name = nullptr;
+    RMT_NCCL_FUNCS(X)
+#undef X
+} nccl;
+bool g_nccl_ok = false;
+
+int load_nccl()
+{
+    if (g_nccl_ok) return 0;
+    // the soname: when the process already carries an NCCL (e.g. the one PyTorch bundles) this resolves to it
+    nccl.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!nccl.lib) return fail("rmt_comm: cannot load libnccl.so.2: %s", dlerror());
+#define X(name)                                                                                  \
+    nccl.p_##name = (decltype(&name))dlsym(nccl.lib, RMT_STR(name));                             \
+    if (!nccl.p_##name) return fail("rmt_comm: libnccl.so.2 lacks symbol %s", RMT_STR(name));
+    RMT_NCCL_FUNCS(X)
+#undef X
+    g_nccl_ok = true;
+    return 0;
+}
+
+int nccl_fail(ncclResult_t r, const char* what)
+{
+    return fail("%s failed: NCCL error %d (%s)", what, (int)r, nccl.p_ncclGetErrorString ? nccl.p_ncclGetErrorString(r) : "?");
+}
+#define NC(call)                                                  \
+    do {                                                          \
+        ncclResult_t r_ = nccl.p_##call;                          \
+        if (r_ != ncclSuccess) return nccl_fail(r_, #call);       \
+    } while (0)
+
+struct Comm {
+    ncclComm_t comm = nullptr;
+    int nranks = 0, rank = 0;
+};
+std::map<uint64_t, Comm*> g_comms;
+
+Comm* get_comm(rmt_comm_t c)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_comms.find(c);
+    return it == g_comms.end() ? nullptr : it->second;
 }
 
 }  // namespace
@@ -449,7 +503,13 @@ int rmt_module_load(const void* cubin, size_t size, rmt_module_t* module_out)
         CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&M->solve_blocks_per_sm, fs, I.block, M->solve_smem));
         if (M->solve_blocks_per_sm < 1) { drv.p_cuModuleUnload(M->mod); delete M; return fail("integrator kernel does not fit on an SM (smem %zu B)", M->solve_smem); }
     } else if (fs) {
-        CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&M->solve_blocks_per_sm, fs, I.block, 0));
+        // N2: the substitution's shared-memory record, ((n + 1) n + 3 n + 1) rows of (block + 1) doubles (rmt_n2_solve); M9: none
+        // and, with several lanes per reactor, the sweeps' hand-over records [block/lanes][stages + 1][2 n + 4]
+        M->solve_smem = I.model == 2 ? 8*((size_t)(I.n + 1)*I.n + 3*(size_t)I.n + 1)*((size_t)I.block + 1) : 0;
+        if (I.lanes > 1) M->solve_smem += 8*(size_t)(I.block/I.lanes)*(I.stages + 1)*(2*(size_t)I.n + 4);
+        if (M->solve_smem) CU(cuFuncSetAttribute(fs, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)M->solve_smem));
+        CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&M->solve_blocks_per_sm, fs, I.block, M->solve_smem));
+        if (M->solve_blocks_per_sm < 1) { drv.p_cuModuleUnload(M->mod); delete M; return fail("dynamic-model integrator does not fit on an SM (smem %zu B)", M->solve_smem); }
     }
     std::lock_guard<std::mutex> lk(g_mu);
     uint64_t id = g_next_id++;
@@ -542,10 +602,39 @@ int rmt_n1_sys(rmt_module_t m, int64_t B, const double* d_consts, const double* 
     return launch(M->f_n1_sys, (unsigned)((B + 127)/128), 128, 0, (CUstream)stream, params, "rmt_n1_sys");
 }
 
+static int n1_solve_impl(rmt_module_t m, int64_t B, const double* d_consts, int32_t n_eval, const double* z_eval,
+                         double rtol, double atol, int32_t max_steps, int32_t dense, int32_t out_mode,
+                         double* d_out, int32_t* d_status, int32_t* d_stats,
+                         const double* obj_ref, double* d_obj, double* d_red, int64_t red_offset,
+                         const double* ctrl, void* stream);
+
 int rmt_n1_solve(rmt_module_t m, int64_t B, const double* d_consts, int32_t n_eval, const double* z_eval,
                  double rtol, double atol, int32_t max_steps, int32_t dense, int32_t out_mode,
                  double* d_out, int32_t* d_status, int32_t* d_stats,
                  const double* obj_ref, double* d_obj, const double* ctrl, void* stream)
+{
+    return n1_solve_impl(m, B, d_consts, n_eval, z_eval, rtol, atol, max_steps, dense, out_mode, d_out, d_status, d_stats,
+                         obj_ref, d_obj, nullptr, 0, ctrl, stream);
+}
+
+int rmt_n1_solve_population(rmt_module_t m, int64_t B, const double* d_consts, double rtol, double atol, int32_t max_steps,
+                            double* d_out, int32_t* d_status, int32_t* d_stats, const double* obj_ref, double* d_obj,
+                            double* d_red, int64_t index_offset, const double* ctrl, void* stream)
+{
+    if (!obj_ref || !d_obj || !d_red) return fail("rmt_n1_solve_population: obj_ref, d_obj and d_red are required");
+    Module* M = get_module(m);
+    if (!M) return fail("invalid module handle");
+    const double z_end = M->info.model == 7 ? -1.0 : 1.0;
+    if (z_end < 0.0) return fail("rmt_n1_solve_population: model M7 integrates over [0, ReLe]; use rmt_n1_solve with z_eval = {ReLe}");
+    return n1_solve_impl(m, B, d_consts, 1, &z_end, rtol, atol, max_steps, 0, 1, d_out, d_status, d_stats,
+                         obj_ref, d_obj, d_red, index_offset, ctrl, stream);
+}
+
+static int n1_solve_impl(rmt_module_t m, int64_t B, const double* d_consts, int32_t n_eval, const double* z_eval,
+                         double rtol, double atol, int32_t max_steps, int32_t dense, int32_t out_mode,
+                         double* d_out, int32_t* d_status, int32_t* d_stats,
+                         const double* obj_ref, double* d_obj, double* d_red, int64_t red_offset,
+                         const double* ctrl, void* stream)
 {
     Module* M = get_module(m);
     if (!M) return fail("invalid module handle");
@@ -573,12 +662,17 @@ int rmt_n1_solve(rmt_module_t m, int64_t B, const double* d_consts, int32_t n_ev
     a.out = (CUdeviceptr)d_out; a.status = (CUdeviceptr)d_status; a.stats = (CUdeviceptr)d_stats; a.queue = scr;
     a.obj_ref = obj_ref ? scr + 64 + 8*(size_t)n_eval : 0; a.obj = (CUdeviceptr)d_obj;
     a.trace = (CUdeviceptr)g_trace_buf; a.trace_inst = g_trace_inst; a.trace_cap = g_trace_cap;
+    a.red = (CUdeviceptr)d_red; a.red_offset = red_offset;
     for (int k = 0; k < 6; ++k) a.ctrl[k] = ctrl ? ctrl[k] : RMT_DEFAULT_CTRL[k];
     if (!(a.ctrl[0] > 0.0 && a.ctrl[0] <= 1.0) || !(a.ctrl[1] > 1.0) || !(a.ctrl[2] > 1.0) || !(a.ctrl[3] > 0.0))
         return fail("rmt_n1_solve: controller needs 0 < safety <= 1, max shrink > 1, max growth > 1, kappa > 0");
     if (!(a.ctrl[5] > 0.0)) a.ctrl[5] = RMT_DEFAULT_CTRL[5];
     const int block = M->info.block;
-    long long want = (B + block - 1)/block;
+    // One block per SM; lanes pull reactors from the queue, a warp at a time.  An ensemble smaller than one resident
+    // wave is spread over all SMs (a warp's worth of reactors per block and up) rather than packed into a few of
+    // them: the integrator is bound by the FP64 pipe of the SM it runs on (8 192 reactors: 22 full blocks use 15 %
+    // of the GPU's FP64 pipes, 148 blocks of two busy warps all of them).
+    long long want = (B + 31)/32;
     long long cap = (long long)g_sm_count*M->solve_blocks_per_sm;
     unsigned grid = (unsigned)std::max<long long>(1, std::min(want, cap));
     void* params[] = {&a};
@@ -728,7 +822,7 @@ int rmt_n2_solve(rmt_module_t m, int64_t B, int32_t zNo, int32_t tNo, double per
     const int block = M->info.block;
     unsigned grid = (unsigned)(n2_slots(M, B)/block);
     void* params[] = {&a};
-    if (launch(M->f_n2_solve, grid, block, 0, st, params, "rmt_n2_solve")) return 1;
+    if (launch(M->f_n2_solve, grid, block, M->solve_smem, st, params, "rmt_n2_solve")) return 1;
     return scratch_launched(M, slot, st);
 }
 
@@ -763,6 +857,83 @@ int rmt_reduce_objective(rmt_module_t m, int64_t n, const double* d_obj, int64_t
     if (h_sum) *h_sum = s;
     if (h_min) *h_min = mn;
     if (h_argmin) *h_argmin = am;
+    return 0;
+}
+
+// ---- sharded ensembles: cross-GPU gather / reduce (NCCL over NVLink) -----------------------
+int rmt_comm_unique_id(void* id_out, size_t id_bytes)
+{
+    if (!id_out || id_bytes < sizeof(ncclUniqueId)) return fail("rmt_comm_unique_id: need a buffer of RMT_COMM_ID_BYTES (%zu) bytes", sizeof(ncclUniqueId));
+    if (load_nccl()) return 1;
+    ncclUniqueId id;
+    NC(ncclGetUniqueId(&id));
+    memcpy(id_out, &id, sizeof id);
+    return 0;
+}
+
+int rmt_comm_init(int32_t nranks, int32_t rank, const void* id, size_t id_bytes, rmt_comm_t* comm_out)
+{
+    if (!id || id_bytes < sizeof(ncclUniqueId) || !comm_out) return fail("rmt_comm_init: NULL / short id or NULL comm_out");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail("rmt_comm_init: rank %d of %d", rank, nranks);
+    if (ensure_ctx()) return 1;                       // rmt_init(device) first: one process per GPU
+    if (load_nccl()) return 1;
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof uid);
+    Comm* C = new Comm;
+    C->nranks = nranks; C->rank = rank;
+    ncclResult_t r = nccl.p_ncclCommInitRank(&C->comm, nranks, uid, rank);
+    if (r != ncclSuccess) { delete C; return nccl_fail(r, "ncclCommInitRank"); }
+    std::lock_guard<std::mutex> lk(g_mu);
+    uint64_t h = g_next_id++;
+    g_comms[h] = C;
+    *comm_out = h;
+    return 0;
+}
+
+int rmt_comm_info(rmt_comm_t comm, int32_t* nranks, int32_t* rank, int32_t* nccl_version)
+{
+    Comm* C = get_comm(comm);
+    if (!C) return fail("invalid communicator handle");
+    if (nranks) *nranks = C->nranks;
+    if (rank) *rank = C->rank;
+    if (nccl_version) { int v = 0; NC(ncclGetVersion(&v)); *nccl_version = v; }
+    return 0;
+}
+
+int rmt_comm_allgather(rmt_comm_t comm, const double* d_send, double* d_recv, int64_t count, void* stream)
+{
+    Comm* C = get_comm(comm);
+    if (!C) return fail("invalid communicator handle");
+    if (count <= 0 || !d_send || !d_recv) return fail("rmt_comm_allgather: need count > 0 and device buffers");
+    if (ensure_ctx()) return 1;
+    NC(ncclAllGather(d_send, d_recv, (size_t)count, ncclFloat64, C->comm, (cudaStream_t)stream));
+    return 0;
+}
+
+int rmt_comm_allreduce(rmt_comm_t comm, const double* d_send, double* d_recv, int64_t count, int32_t op, void* stream)
+{
+    Comm* C = get_comm(comm);
+    if (!C) return fail("invalid communicator handle");
+    if (count <= 0 || !d_send || !d_recv) return fail("rmt_comm_allreduce: need count > 0 and device buffers");
+    if (op < 0 || op > 2) return fail("rmt_comm_allreduce: op 0 = sum, 1 = min, 2 = max");
+    if (ensure_ctx()) return 1;
+    const ncclRedOp_t ops[3] = {ncclSum, ncclMin, ncclMax};
+    NC(ncclAllReduce(d_send, d_recv, (size_t)count, ncclFloat64, ops[op], C->comm, (cudaStream_t)stream));
+    return 0;
+}
+
+int rmt_comm_free(rmt_comm_t comm)
+{
+    Comm* C;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_comms.find(comm);
+        if (it == g_comms.end()) return fail("invalid communicator handle");
+        C = it->second;
+        g_comms.erase(it);
+    }
+    if (C->comm && nccl.p_ncclCommDestroy) nccl.p_ncclCommDestroy(C->comm);
+    delete C;
     return 0;
 }
 

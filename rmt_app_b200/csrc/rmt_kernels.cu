@@ -21,8 +21,8 @@
 
 // Division.  IEEE `a/b` on sm_100a is a ~14-instruction sequence with a branch to a slow path
 // (BSSY/BSYNC + call) — with ~35 divisions per RHS that is a fifth of the instruction stream and a
-// steady source of instruction-fetch stalls.  The hot code therefore multiplies by a Newton-refined
-// reciprocal: MUFU.RCP64H seed (~2^-20) + two FMA iterations -> <= 2 ulp, branch free.  Zero / Inf /
+// steady source of instruction-fetch stalls.  The hot code therefore multiplies by a refined
+// reciprocal: MUFU.RCP64H seed (~2^-20) + one third-order correction (3 FMAs) -> <= 2 ulp, branch free.  Zero / Inf /
 // NaN operands still end in Inf / NaN, which the integrator's domain guard turns into a rejected
 // step.  -DRMT_EXACT_DIV=1 restores IEEE division everywhere.
 #ifndef RMT_EXACT_DIV
@@ -33,14 +33,22 @@ __device__ __forceinline__ double rmt_rcp(const double x)
 #if RMT_EXACT_DIV
     return 1.0/x;
 #else
+    // seed r0 = (1/x)(1 - e), |e| <~ 2^-20; one third-order step r0 (1 + e + e^2) = (1/x)(1 - e^3): three dependent
+    // FMAs instead of the four of two Newton steps, |e|^3 < 2^-58
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    return r;
+    const double e = fma(-x, r, 1.0);
+    const double t = fma(e, e, e);
+    return fma(r, t, r);
 #endif
+}
+// |x| limited to the double whose high word is `hi_limit` (the low word of x is kept: limit <= |result| < limit*(1 + 2^-20)),
+// sign kept; NaN / Inf come out as +-limit like the fmin(fmax()) pair it replaces.  Integer pipe only: DMNMX does not
+// exist on sm_100a, fmin/fmax of doubles are a DSETP + selects each, and the DSETP occupies an FP64 issue slot.
+__device__ __forceinline__ double rmt_clamp_abs(const double x, const int hi_limit)
+{
+    const int hx = __double2hiint(x);
+    return __hiloint2double((hx & 0x80000000) | min(hx & 0x7fffffff, hi_limit), __double2loint(x));
 }
 #if RMT_EXACT_DIV
 #define RMT_DIV(a, b) ((a)/(b))
@@ -52,8 +60,8 @@ __device__ __forceinline__ double rmt_rcp(const double x)
 // extra instructions, those branches cut the instruction stream into basic blocks, so the independent
 // Arrhenius / equilibrium exponentials of a kinetics section (all functions of T only) cannot be interleaved
 // by the scheduler.  The versions below are branch free (select instead of branch) and accurate to ~1 ulp
-// on the normal range: exp clamps its argument to [-708, 709] (finite huge/tiny instead of Inf/0), log and
-// sqrt return NaN for negative arguments.  -DRMT_EXACT_MATH=1 uses libdevice everywhere.
+// on the normal range: exp clamps its argument to +-708 (finite huge/tiny instead of Inf/0), log returns NaN outside
+// the positive normal range, sqrt NaN for negative arguments.  -DRMT_EXACT_MATH=1 uses libdevice everywhere.
 #ifndef RMT_EXACT_MATH
 #define RMT_EXACT_MATH 0
 #endif
@@ -112,14 +120,14 @@ __device__ __forceinline__ double rmt_exp(double x)
 #if RMT_EXACT_MATH
     return exp(x);
 #elif RMT_EXP_TABLE
-    x = fmin(fmax(x, -708.0), 709.0);
+    x = rmt_clamp_abs(x, 0x40862000);                                     // |x| <= 708
     const double t = fma(x, 46.16624130844683, 6755399441055744.0);      // round(x*32/ln2) in the low word
     const double nd = t - 6755399441055744.0;
     double r = fma(nd, -0.02166084938653512, x);                          // ln2_hi/32 (exact product)
     r = fma(nd, -5.9631716539705866e-12, r);                              // ln2_lo/32
     return rmt_exp_tab(r, __double2loint(t));
 #else
-    x = fmin(fmax(x, -708.0), 709.0);
+    x = rmt_clamp_abs(x, 0x40862000);                                     // |x| <= 708: 2^k stays a normal number
     const double t = fma(x, 1.4426950408889634, 6755399441055744.0);     // round(x*log2(e)) in the low word
     const double kd = t - 6755399441055744.0;
     double r = fma(kd, -6.93147180369123816490e-01, x);
@@ -132,7 +140,7 @@ __device__ __forceinline__ double rmt_exp10(double x)
 #if RMT_EXACT_MATH
     return exp10(x);
 #elif RMT_EXP_TABLE
-    x = fmin(fmax(x, -307.0), 308.0);
+    x = rmt_clamp_abs(x, 0x40733000);                                     // |x| <= 307
     const double t = fma(x, 106.30169903639559, 6755399441055744.0);     // round(x*32*log2(10))
     const double nd = t - 6755399441055744.0;
     const double xh = x*2.302585092994045901e+00;
@@ -142,7 +150,7 @@ __device__ __forceinline__ double rmt_exp10(double x)
     r += fma(x, 2.302585092994045901e+00, -xh);
     return rmt_exp_tab(r, __double2loint(t));
 #else
-    x = fmin(fmax(x, -307.0), 308.0);
+    x = rmt_clamp_abs(x, 0x40733000);                                     // |x| <= 307
     const double t = fma(x, 3.3219280948873622, 6755399441055744.0);     // round(x*log2(10))
     const double kd = t - 6755399441055744.0;
     // r = x*ln10 - k*ln2 with ln10 and ln2 split hi/lo and the rounding error of x*ln10_hi recovered
@@ -162,18 +170,18 @@ __device__ __forceinline__ double rmt_log(const double x)
     // fdlibm e_log.c without the special cases: x = 2^k * m, m in [sqrt(1/2), sqrt(2))
     int hx = __double2hiint(x);
     const int lx = __double2loint(x);
+    // positive normal numbers only (one integer range test instead of a DSETP): negative, zero, subnormal, Inf, NaN -> NaN
+    const bool ok = (unsigned)(hx - 0x00100000) < (unsigned)(0x7ff00000 - 0x00100000);
     int k = (hx >> 20) - 1023;
     hx &= 0x000fffff;
     const int i = (hx + 0x95f64) & 0x100000;
     const double m = __hiloint2double(hx | (i ^ 0x3ff00000), lx);
     k += i >> 20;
     const double f = m - 1.0;
-    double e, rr;
+    double rr;
     {   // s = f/(2+f) by a refined reciprocal
         const double d = 2.0 + f;
-        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rr) : "d"(d));
-        e = fma(-d, rr, 1.0); rr = fma(rr, e, rr);
-        e = fma(-d, rr, 1.0); rr = fma(rr, e, rr);
+        rr = rmt_rcp(d);
     }
     const double s = f*rr;
     const double z = s*s, w = z*z;
@@ -184,7 +192,7 @@ __device__ __forceinline__ double rmt_log(const double x)
     const double hfsq = 0.5*f*f;
     const double dk = (double)k;
     const double res = dk*6.93147180369123816490e-01 - ((hfsq - fma(s, hfsq + R, dk*1.90821492927058770002e-10)) - f);
-    return x > 0.0 ? res : __longlong_as_double(0x7ff8000000000000LL);
+    return ok ? res : __longlong_as_double(0x7ff8000000000000LL);
 #endif
 }
 __device__ __forceinline__ double rmt_log10(const double x)
@@ -1116,6 +1124,12 @@ struct SolveArgs {
     double* trace;             // [trace_cap][4] or null
     i64 trace_inst;
     int trace_cap;
+    // optional fused reduction of the objective (parameter-estimation populations): the last block to finish folds
+    // obj[0..B) and status[0..B) into red[0..3] = sum, min, argmin + red_offset (as a double), number of failed
+    // reactors — in a fixed order, so the result is deterministic — and no second kernel is needed before the
+    // cross-GPU step.  The block-completion counter sits behind the work counter (queue + 1).
+    double* red;               // [4] or null
+    i64 red_offset;
 };
 
 #define SM(slot) sm[(slot)*RMT_BLOCK]
@@ -1172,7 +1186,14 @@ __device__ __forceinline__ void n1_write_point(const SolveArgs& a, const Hot& h,
     }
 }
 
-extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const SolveArgs a)
+// register cap of the integrator: from the block size (one block per SM), or explicit (RMT_MAXNREG: ptxas rounds a
+// launch-bounds cap down to an occupancy step — 448 threads gives 128 registers although 144 fit)
+#ifdef RMT_MAXNREG
+#define RMT_SOLVE_BOUNDS __maxnreg__(RMT_MAXNREG)
+#else
+#define RMT_SOLVE_BOUNDS __launch_bounds__(RMT_BLOCK)
+#endif
+extern "C" __global__ void RMT_SOLVE_BOUNDS rmt_n1_solve(const SolveArgs a)
 {
     extern __shared__ double smem[];
     double* sm = smem + threadIdx.x;
@@ -1183,8 +1204,16 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
     bool exhausted = false;
     Hot h = {};
     double y[RMT_N];
-    double t = 0.0, hstep = 0.0, hacc = 0.0, erracc = 0.0, tend = 0.0;
+    double t = 0.0, hstep = 0.0, hacc = 0.0, erracc = 0.0;
     int nacc = 0, nrej = 0, next_e = 0, nanrej = 0;
+    // Output grid: everything a lane needs when it picks up a reactor is read here, once per thread, so that the
+    // refill itself has no dependent loads: the end of the domain, the number of leading output points at z <= 0
+    // (written straight from the initial state) and the first output position inside the domain.
+    const double tend = a.z_eval[a.n_eval - 1];
+    int first_e = 0;
+    while (first_e < a.n_eval && a.z_eval[first_e] <= 0.0) ++first_e;
+    const double z_first = first_e < a.n_eval ? a.z_eval[first_e] : tend;
+    double znext = z_first;                 // z_eval[next_e] (tend when all points are written)
     bool last_rejected = false, fresh = false;
 #if RMT_SYNC && RMT_SYNC_EVERY > 1
     int iter = 0;
@@ -1239,8 +1268,8 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
 #endif
                     t = 0.0; nacc = 0; nrej = 0; nanrej = 0; next_e = 0; last_rejected = false; fresh = true;
                     hacc = 0.0; erracc = 1e-2;
-                    tend = a.z_eval[a.n_eval - 1];
-                    while (next_e < a.n_eval && a.z_eval[next_e] <= 0.0) { n1_write_point(a, h, inst, next_e, y); ++next_e; }
+                    for (; next_e < first_e; ++next_e) n1_write_point(a, h, inst, next_e, y);
+                    znext = z_first;
                 }
             }
         }
@@ -1293,7 +1322,7 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
         // clip to the end of the domain / next output point
         double hlim = tend - t;
         const bool dense = RMT_ROS_DENSE && a.dense;
-        if (!dense && next_e < a.n_eval) hlim = a.z_eval[next_e] - t;
+        if (!dense) hlim = znext - t;
         const bool clipped = hstep*1.01 >= hlim;
         const double hh = clipped ? hlim : hstep;
 
@@ -1345,9 +1374,6 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
 #else
         const double (&flast)[RMT_M] = f0;
 #endif
-        double dxs[RMT_M], evs[RMT_M];          // sum m_s k_s and sum e_s k_s in the integrator's unknowns
-#pragma unroll
-        for (int i = 0; i < RMT_M; ++i) { dxs[i] = 0.0; evs[i] = 0.0; }
 
 #if RMT_ROLL
 #pragma unroll 1
@@ -1468,26 +1494,26 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
                 for (int j = i + 1; j < RMT_M; ++j) v -= ROW(i, j)*x[j];
                 x[i] = v*ROW(i, i);
             }
-#if RMT_ROLL
-            const double ms = RMT_cROS_M[s], es = RMT_cROS_E[s];
 #pragma unroll
-            for (int i = 0; i < RMT_M; ++i) {
-                ks[i*RMT_BLOCK] = x[i];
-                dxs[i] += ms*x[i];
-                evs[i] += es*x[i];
-            }
-#else
-#pragma unroll
-            for (int i = 0; i < RMT_M; ++i) {
-                ks[i*RMT_BLOCK] = x[i];
-                if (RMT_ROS_M[s] == 1.0) dxs[i] += x[i];
-                else if (RMT_ROS_M[s] != 0.0) dxs[i] += RMT_cROS_M[s]*x[i];
-                if (RMT_ROS_E[s] == 1.0) evs[i] += x[i];
-                else if (RMT_ROS_E[s] != 0.0) evs[i] += RMT_ROS_E[s]*x[i];
-            }
-#endif
+            for (int i = 0; i < RMT_M; ++i) ks[i*RMT_BLOCK] = x[i];
         }
 #undef ROW
+        // sum m_s k_s and sum e_s k_s in the integrator's unknowns, from the stage vectors in shared memory (accumulating
+        // them inside the stage loop would hold 2m doubles in registers across every right-hand-side evaluation)
+        double dxs[RMT_M], evs[RMT_M];
+#pragma unroll
+        for (int i = 0; i < RMT_M; ++i) {
+            double dx = 0.0, ev = 0.0;
+#pragma unroll
+            for (int s = 0; s < RMT_ROS_S; ++s) {
+                const double kv = KS(s, i);
+                if (RMT_ROS_M[s] == 1.0) dx += kv;
+                else if (RMT_ROS_M[s] != 0.0) dx += RMT_cROS_M[s]*kv;
+                if (RMT_ROS_E[s] == 1.0) ev += kv;
+                else if (RMT_ROS_E[s] != 0.0) ev += RMT_cROS_E[s]*kv;
+            }
+            dxs[i] = dx; evs[i] = ev;
+        }
         double ynew[RMT_N], errv[RMT_N];
         rmt_expand(dxs, ynew);
         rmt_expand(evs, errv);
@@ -1548,7 +1574,7 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
             }
             hacc = hh; erracc = fmax(1e-2, err);
             ++nacc; nanrej = 0;
-            const double tnew = clipped ? (dense || next_e >= a.n_eval ? tend : a.z_eval[next_e]) : t + hh;
+            const double tnew = clipped ? (dense ? tend : znext) : t + hh;
             // output points inside (t, tnew]
             if (dense) {
                 while (next_e < a.n_eval && a.z_eval[next_e] <= tnew) {
@@ -1580,6 +1606,7 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
             } else if (clipped && next_e < a.n_eval) {
                 if (live) n1_write_point(a, h, inst, next_e, ynew);
                 ++next_e;
+                znext = next_e < a.n_eval ? a.z_eval[next_e] : tend;
             }
             t = tnew;
 #pragma unroll
@@ -1640,6 +1667,42 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK) rmt_n1_solve(const Solve
                 a.obj[inst] = ob;
             }
             inst = -1;
+        }
+    }
+    if (a.red) {
+        // ---- fused objective reduction: last block out folds the shard ----
+        __shared__ int is_last;
+        __threadfence();                                   // this block's obj / status writes are visible device-wide ...
+        __syncthreads();
+        if (threadIdx.x == 0) {                            // ... before its arrival is counted
+            const unsigned arrived = atomicAdd(reinterpret_cast<unsigned int*>(a.queue + 1), 1u);
+            is_last = arrived == gridDim.x - 1;
+        }
+        __syncthreads();
+        if (is_last) {
+            __threadfence();
+            const double inf = __longlong_as_double(0x7ff0000000000000LL);
+            double sum = 0.0, mn = inf, nbad = 0.0;
+            i64 am = -1;
+            for (i64 i = threadIdx.x; i < a.B; i += RMT_BLOCK) {          // fixed assignment: deterministic
+                const double x = __ldcg(a.obj + i);
+                sum += x;
+                if (x < mn) { mn = x; am = i + a.red_offset; }
+                nbad += __ldcg(a.status + i) != 0 ? 1.0 : 0.0;
+            }
+            double* ssum = smem; double* smin = smem + RMT_BLOCK; double* sbad = smem + 2*RMT_BLOCK;
+            i64* sarg = reinterpret_cast<i64*>(smem + 3*RMT_BLOCK);
+            __syncthreads();                               // the integrator's shared-memory slots are free now
+            ssum[threadIdx.x] = sum; smin[threadIdx.x] = mn; sbad[threadIdx.x] = nbad; sarg[threadIdx.x] = am;
+            __syncthreads();
+            if (threadIdx.x == 0) {                        // fixed order over the block's threads
+                for (int k = 1; k < RMT_BLOCK; ++k) {
+                    sum += ssum[k]; nbad += sbad[k];
+                    const double o = smin[k]; const i64 oa = sarg[k];
+                    if (o < mn || (o == mn && oa >= 0 && (am < 0 || oa < am))) { mn = o; am = oa; }
+                }
+                a.red[0] = sum; a.red[1] = mn; a.red[2] = (double)am; a.red[3] = nbad;
+            }
         }
     }
 }
@@ -2004,7 +2067,11 @@ enum {
 #else
     W_ROWS = W_EP + 1
 #endif
-};                               // W_LU holds W_kk^{-1} (n x n, row-major)
+};                               // W_LU.. W_EP: used by M9 only (N2 keeps these in shared memory, S_* rows below)
+
+// rows of the shared-memory record of the N2 substitution (see rmt_n2_solve); the host sizes the dynamic shared
+// memory as N2_SH_ROWS*(RMT_BLOCK + 1) doubles = ((n + 1) n + 3 n + 1)*(block + 1)*8 bytes
+enum { S_AUG = 0, S_L = (RMT_N + 1)*RMT_N, S_G = S_L + RMT_N, S_R = S_G + RMT_N, S_DPF = S_R + RMT_N, N2_SH_ROWS = S_DPF + 1 };
 
 // solve with LU factors held in registers (rows permuted in place, reciprocal pivots on the diagonal)
 __device__ __forceinline__ void n2_lu_solve(const double (&A)[RMT_N][RMT_N], const int (&perm)[RMT_N],
@@ -2133,16 +2200,30 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
 #if !defined(RMT_MODEL_M9)
     const double dz = 1.0/(zNo - 1), invdz = 1.0/dz;
 #endif
-    const double SAFE = a.ctrl[0], FAC1 = a.ctrl[1], FAC2 = 1.0/a.ctrl[2], KAPPA = a.ctrl[3], BETA = a.ctrl[4];
+    const double ISAFE = 1.0/a.ctrl[0], FAC1 = a.ctrl[1], FAC2 = 1.0/a.ctrl[2], KAPPA = a.ctrl[3], BETA = a.ctrl[4];
+    const double inv_nz = 1.0/((double)RMT_N*zNo);             // 1/(unknowns per reactor): rms norms
     // per reactor and sweep (s stage sweeps + the Jacobian sweep): upwind state [n], K of the node before [n], marched
     // pressure, linearised pressure, marched velocity, linearised velocity (M9)
     constexpr int N2_CARRY = 2*RMT_N + 4;
-#if RMT_N2_G > 1
-    __shared__ double n2_carry[(RMT_BLOCK/RMT_N2_G)*(RMT_ROS_S + 1)*N2_CARRY];     // one record per reactor of the block
-#else
+#if RMT_N2_G == 1
     double n2_carry[(RMT_ROS_S + 1)*N2_CARRY];                                     // one lane per reactor: thread-private
 #endif
-
+#if !defined(RMT_MODEL_M9)
+    // What the block forward substitution reads of a node — the augmented inverse block ((n + 1) x n: W_kk^{-1} and
+    // the pressure row dz e_k^T W_kk^{-1}), the couplings L_k and g_k, the stage right-hand side (replaced by K_k) and
+    // the factor 1 + dz ep_k — lives in shared memory, [row][thread] with the row stride padded to RMT_BLOCK + 1: in
+    // the substitution lane r reads row r of ANOTHER lane's column, and with the padded stride those reads fall into
+    // different banks (n = 7, 8 lanes per reactor: no conflict at all); the owner's own accesses are conflict-free
+    // as before.  Size: N2_SH_ROWS*(RMT_BLOCK + 1) doubles, passed by the host as dynamic shared memory.
+    extern __shared__ double n2_sh[];
+    constexpr int SH_LD = RMT_BLOCK + 1;
+    double* const shc = n2_sh + threadIdx.x;
+#define SH(row) shc[(row)*SH_LD]
+#if RMT_N2_G > 1
+    // behind it: what the sweeps carry from one node group to the next, one record per reactor of the block
+    double* const n2_carry = n2_sh + N2_SH_ROWS*SH_LD;        // [(RMT_BLOCK/G)][RMT_ROS_S + 1][N2_CARRY]
+#endif
+#endif
     i64 inst = -1;
     bool exhausted = false;
     Hot h = {};
@@ -2209,8 +2290,8 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
                 double n0 = 0.0, n1 = 0.0;
 #pragma unroll
                 for (int v = 0; v < RMT_N; ++v) {
-                    const double sc = KAPPA*(a.atol + a.rtol*fabs(u[v]));
-                    n0 += (u[v]/sc)*(u[v]/sc); n1 += (fo[v]/sc)*(fo[v]/sc);
+                    const double isc = rmt_rcp(KAPPA*(a.atol + a.rtol*fabs(u[v])));
+                    n0 += (u[v]*isc)*(u[v]*isc); n1 += (fo[v]*isc)*(fo[v]*isc);
                 }
                 if (kg*G + g >= zNo) { n0 = 0.0; n1 = 0.0; }
 #pragma unroll
@@ -2219,15 +2300,15 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
                     d1 += G > 1 ? __shfl_sync(gmask, n1, j, G) : n1;
                 }
             }
-            d0 = sqrt(d0/(RMT_N*zNo)); d1 = sqrt(d1/(RMT_N*zNo));
-            const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01*d0/d1;
+            d0 = rmt_sqrt(d0*inv_nz); d1 = rmt_sqrt(d1*inv_nz);
+            const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01*d0*rmt_rcp(d1);
             hstep = fmin(a.ctrl[5]*100.0*h0, tend);
             fresh = false;
         }
         const double hlim = tend - t;
         const bool clipped = hstep*1.01 >= hlim;
         const double hh = clipped ? hlim : hstep;
-        const double dg = 1.0/(hh*RMT_ROS_GAMMA), invh = 1.0/hh;
+        const double invh = rmt_rcp(hh), dg = invh*(1.0/RMT_ROS_GAMMA);
 
         // ---- one pass over the node groups.  For each group: the Jacobian sweep (f(y_n), Jacobian blocks, inverse
         // diagonal blocks — all nodes of the group in parallel) and then all stage sweeps, back to back, so that the
@@ -2306,18 +2387,31 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
 #pragma unroll
                     for (int q = 0; q < RMT_N; ++q) b[q] = q == c ? 1.0 : 0.0;
                     n2_lu_solve(nj.A, perm, b, xs);
+#if defined(RMT_MODEL_M9)
 #pragma unroll
                     for (int q = 0; q < RMT_N; ++q) WS(W_LU + q*RMT_N + c) = xs[q];
+#else
+                    double we = 0.0;
+#pragma unroll
+                    for (int q = 0; q < RMT_N; ++q) { SH(S_AUG + q*RMT_N + c) = xs[q]; we = fma(nj.e[q], xs[q], we); }
+                    SH(S_AUG + RMT_N*RMT_N + c) = dz*we;       // row n: d(dP_{k+1})/d(tv_k) = dz * e_k^T W_kk^{-1}
+#endif
                 }
 #pragma unroll
                 for (int r = 0; r < RMT_N; ++r) {
-                    WS(W_L + r) = nj.L[r]; WS(W_G + r) = nj.g[r]; WS(W_E + r) = nj.e[r];
                     WS(W_K + r) = fo[r];                   // stage-1 right-hand side
 #if defined(RMT_MODEL_M9)
+                    WS(W_L + r) = nj.L[r]; WS(W_G + r) = nj.g[r]; WS(W_E + r) = nj.e[r];
                     WS(W_GV + r) = nj.gv[r]; WS(W_LT + r) = nj.Lt[r]; WS(W_EV + r) = nj.eV[r];
+#else
+                    SH(S_L + r) = nj.L[r]; SH(S_G + r) = nj.g[r];
 #endif
                 }
+#if defined(RMT_MODEL_M9)
                 WS(W_EP) = nj.ep;
+#else
+                SH(S_DPF) = fma(dz, nj.ep, 1.0);           // d(dP_{k+1})/d(dP_k) besides the path through K_k
+#endif
 #if defined(RMT_MODEL_M9)
                 WS(W_S4) = nj.ev; WS(W_S4 + 1) = nj.eVb; WS(W_S4 + 2) = nj.eVP; WS(W_S4 + 3) = nj.eVv;
 #endif
@@ -2369,6 +2463,64 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
 #pragma unroll
                     for (int v = 0; v < RMT_N; ++v) rhs[v] += vc[v];
                 }
+#if !defined(RMT_MODEL_M9)
+                // ---- block forward substitution of this group, rows spread over the lanes ----
+                // K_k = W_kk^{-1} tv_k,  tv_k = rhs_k + L_k*K_{k-1} + g_k dP_k,  dP_{k+1} = (1 + dz ep_k) dP_k + (dz e_k^T W_kk^{-1}) tv_k.
+                // The nodes of the group are visited in order (that is inherent to the upwind coupling), but the n + 1
+                // rows of a node's update (n of K_k, one of dP_{k+1}: row n of the augmented inverse block) are
+                // independent dot products with the same vector tv_k: lane r of the group takes rows r, r + G, ... of
+                // EVERY node — it reads them from the owner's work column — so a hand-over costs each lane one dot
+                // product instead of the whole matrix-vector product (round 1: all G lanes computed every node's
+                // product and kept one, 47 % of the kernel's instructions).  tv_k is assembled from the lanes' own
+                // entries with n shuffles; the finished K_k goes back into the owner's K_s slot.  Same arithmetic, in
+                // the same order, for every G.
+                constexpr int NROW = (RMT_N + 1 + G - 1)/G;               // rows per lane
+                double x[RMT_N];
+                {
+#pragma unroll
+                    for (int v = 0; v < RMT_N; ++v) SH(S_R + v) = rhs[v];
+                    __syncwarp();
+                    double kprev[NROW], dP = dPg;
+#pragma unroll
+                    for (int q = 0; q < NROW; ++q) { const int r = g + q*G; kprev[q] = r < RMT_N ? c[RMT_N + r] : 0.0; }
+#pragma unroll 1
+                    for (int j = 0; j < G; ++j) {
+                        double* const sj = shc + (j - g);                  // column of the lane that owns node j
+                        double tvo[NROW];
+#pragma unroll
+                        for (int q = 0; q < NROW; ++q) {
+                            const int r = g + q*G;
+                            tvo[q] = 0.0;
+                            if (r < RMT_N)
+                                tvo[q] = fma(sj[(S_L + r)*SH_LD], kprev[q], fma(sj[(S_G + r)*SH_LD], dP, sj[(S_R + r)*SH_LD]));
+                        }
+                        double tv[RMT_N];
+#pragma unroll
+                        for (int cc = 0; cc < RMT_N; ++cc) tv[cc] = G > 1 ? __shfl_sync(gmask, tvo[cc/G], cc % G, G) : tvo[cc/G];
+                        double dPn = 0.0;
+#pragma unroll
+                        for (int q = 0; q < NROW; ++q) {
+                            const int r = g + q*G;
+                            if (r <= RMT_N) {
+                                const double* wr = sj + (S_AUG + r*RMT_N)*SH_LD;
+                                double acc = wr[0]*tv[0];
+#pragma unroll
+                                for (int cc = 1; cc < RMT_N; ++cc) acc = fma(wr[cc*SH_LD], tv[cc], acc);
+                                if (r < RMT_N) { kprev[q] = acc; sj[(S_R + r)*SH_LD] = acc; }
+                                else dPn = fma(dP, sj[S_DPF*SH_LD], acc);
+                            }
+                        }
+                        dP = G > 1 ? __shfl_sync(gmask, dPn, RMT_N % G, G) : dPn;
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int v = 0; v < RMT_N; ++v) x[v] = SH(S_R + v);
+                    // hand-over to the next group: K of the group's last node (held row-wise), linearised pressure
+#pragma unroll
+                    for (int q = 0; q < NROW; ++q) { const int r = g + q*G; if (r < RMT_N) c[RMT_N + r] = kprev[q]; }
+                    dPg = dP;
+                }
+#else
                 // x0 = W_kk^{-1} rhs_k: all nodes of the group in parallel
                 double Wi[RMT_N][RMT_N], Lk[RMT_N], gk[RMT_N], x0[RMT_N];
 #pragma unroll
@@ -2438,6 +2590,7 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
 #pragma unroll
                 for (int v = 0; v < RMT_N; ++v) kcarry[v] = G > 1 ? __shfl_sync(gmask, x[v], G - 1, G) : x[v];
                 dPg = G > 1 ? __shfl_sync(gmask, dPn, G - 1, G) : dPn;
+#endif   // N2 (rows over lanes) / M9 (one lane per reactor)
                 if (!lastStage) {
 #pragma unroll
                     for (int v = 0; v < RMT_N; ++v) WS(W_K + s*RMT_N + v) = x[v];
@@ -2455,8 +2608,8 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
                         }
                         yn += RMT_cROS_M[s]*x[v]; ev += RMT_cROS_E[s]*x[v];
                         WY(YP + v, kg) = yn;
-                        const double sc = KAPPA*(a.atol + a.rtol*fmax(fabs(yo), fabs(yn)));
-                        ne += (ev/sc)*(ev/sc);
+                        const double en = ev*rmt_rcp(KAPPA*(a.atol + a.rtol*fmax(fabs(yo), fabs(yn))));
+                        ne += en*en;
                         bad = bad || (kg*G + g < zNo && !(fabs(yn) <= 1.7e308));
                     }
                     if (kg*G + g >= zNo) ne = 0.0;
@@ -2464,7 +2617,12 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
                     for (int j = 0; j < G; ++j) errsum += G > 1 ? __shfl_sync(gmask, ne, j, G) : ne;   // node order
                 }
 #pragma unroll
-                for (int v = 0; v < RMT_N; ++v) { c[v] = carry[v]; c[RMT_N + v] = kcarry[v]; }
+                for (int v = 0; v < RMT_N; ++v) {
+                    c[v] = carry[v];
+#if defined(RMT_MODEL_M9)
+                    c[RMT_N + v] = kcarry[v];
+#endif
+                }
                 c[2*RMT_N] = Pg; c[2*RMT_N + 1] = dPg; c[2*RMT_N + 2] = vg;
 #if defined(RMT_MODEL_M9)
                 c[2*RMT_N + 3] = dvg;
@@ -2473,23 +2631,23 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
         }
         }   // node groups
         bad = (__ballot_sync(FULL, bad) & gmask) != 0u;
-        double err = sqrt(errsum/(RMT_N*zNo));
+        double err = rmt_sqrt(errsum*inv_nz);
         if (bad || !(err == err)) err = 1e30;
 
         // ---- controller (same as N1; identical in every lane of the group) ----
         const double errc = fmax(err, 1e-10);
         double fac;
-        if (BETA > 0.0 && nacc > 0) fac = rmt_powc(errc, 1.0/(RMT_ROS_ORDER) - 0.75*BETA)*rmt_powc(erracc, -BETA)/SAFE;
-        else fac = rmt_powc(errc, 1.0/(RMT_ROS_ORDER))/SAFE;
+        if (BETA > 0.0 && nacc > 0) fac = rmt_powc(errc, 1.0/(RMT_ROS_ORDER) - 0.75*BETA)*rmt_powc(erracc, -BETA)*ISAFE;
+        else fac = rmt_powc(errc, 1.0/(RMT_ROS_ORDER))*ISAFE;
         fac = fmax(FAC2, fmin(FAC1, fac));
-        double hnew = hh/fac;
+        double hnew = hh*rmt_rcp(fac);
         int fin = -1;
         if (err <= 1.0) {
             if (nacc > 0 && BETA <= 0.0) {
-                double facgus = (hacc/hh)*rmt_powc(err*err/erracc, 1.0/(RMT_ROS_ORDER))/SAFE;
+                double facgus = (hacc*invh)*rmt_powc(err*err*rmt_rcp(erracc), 1.0/(RMT_ROS_ORDER))*ISAFE;
                 facgus = fmax(FAC2, fmin(FAC1, facgus));
                 fac = fmax(fac, facgus);
-                hnew = hh/fac;
+                hnew = hh*rmt_rcp(fac);
             }
             hacc = hh; erracc = fmax(1e-2, err);
             ++nacc; nanrej = 0;
@@ -2572,6 +2730,7 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
     }
 #undef WY
 #undef WS
+#undef SH
 }
 #endif  // RMT_DYNAMIC
 

@@ -141,34 +141,41 @@ def _fn_sig(f, depth=0):
     return (f.__code__, tuple(cells), tuple(globs), defaults, kwdefaults)
 
 
-def n2_lanes(B, zNo, sm_count=148):
-    """Threads per reactor of the N2 integrator (a power of two <= 32; the nodes of a reactor are spread over
-    them).  The kernel needs 255 registers, so 256 threads are resident per SM; about three waves of them keep
-    the queue busy without paying for lane-to-lane hand-overs that buy nothing (measured on 12 500 x 200 nodes:
-    0.29 s with 1 lane, 0.24 s with 2 or 4, 0.19 s with 8, 0.23 s with 16; 50 000 x 50 nodes: 0.24 / 0.19 / 0.18 s
-    with 1 / 2 / 4; one 50-node reactor: 67 / 15 / 5 ms with 1 / 8 / 32 lanes)."""
-    budget = 3*sm_count*256
-    lanes = 32
-    while lanes > 1 and (B*lanes > budget or lanes >= 2*zNo):
+def n2_lanes(B, zNo, sm_count=148, n=7):
+    """Threads per reactor of the N2 integrator (a power of two <= 32; the nodes of a reactor are spread over them).
+    The block forward substitution gives lane r the rows r, r + lanes, ... of the n + 1 rows of every node's update,
+    so up to n + 1 lanes are busy in it; more lanes only pay while the ensemble is too small to fill the GPU with
+    node evaluations.  Measured (12 500 x 200 nodes, n = 7): 0.195 / 0.160 / 0.202 s with 4 / 8 / 16 lanes;
+    50 000 x 50 nodes: 0.150 / 0.144 s with 4 / 8; one 50-node reactor: 9.2 / 5.3 ms with 8 / 32 lanes."""
+    cap = 1
+    while cap < min(n + 1, 32):
+        cap *= 2                                  # smallest power of two >= n + 1
+    if B*32 <= 2*sm_count*256:                    # small ensemble: as many lanes as the grid has nodes for
+        lanes = 32
+    else:
+        lanes = cap
+        while lanes > 1 and B*lanes > 16*sm_count*256:
+            lanes //= 2
+    while lanes > 1 and lanes >= 2*zNo:
         lanes //= 2
     return lanes
 
 
 def n2_block(B, sm_count=148, lanes=1):
-    """Threads per block of the N2 integrator (`lanes` threads per reactor, lockstep blocks): spread a small
-    ensemble over all SMs rather than filling a few of them."""
+    """Threads per block of the N2 integrator (`lanes` threads per reactor, lockstep blocks).  The kernel keeps a
+    78-row record per thread plus a hand-over record per reactor in shared memory ((n + 1) n + 3 n + 1 rows of
+    block + 1 doubles; 1 kB per reactor) and needs 255 registers, so 256 threads are resident per SM whatever the block
+    size; 64-thread blocks measured best (12 500 x 200 nodes, 8 lanes: 0.148 s with 64, 0.160 s with 128, 0.163 s with
+    32) — a block barrier per node group then waits for two warps, not four.  Small ensembles take 32-thread blocks
+    so that they spread over all SMs."""
     threads = B*lanes
-    # several lanes per reactor: at most 128-thread blocks (12 500 x 200 nodes, 8 lanes: 0.190 s with 128, 0.200 s with
-    # 64, 0.212 s with 256); one lane per reactor: at most 128 (0.29 / 0.31 / 0.47 s with 64 / 128 / 256)
-    for b in (128, 64):
-        if threads >= sm_count*b*3//4:
-            return b
-    return 32
+    return 64 if threads >= sm_count*64*3//4 else 32
 
 
 def compile_model_n2(modelInput, B, zNo, method=None):
     """compile_model with the launch shape (lanes per reactor, block size) for an ensemble of B reactors."""
-    lanes = n2_lanes(B, zNo) if modelInput["model"] == "N2" else 1       # M9: the velocity march is sequential
+    n_node = len(modelInput["feed"]["components"]["shell"]) + (0 if modelInput["operating-conditions"].get("process-type") == "iso-thermal" else 1)
+    lanes = n2_lanes(B, zNo, n=n_node) if modelInput["model"] == "N2" else 1       # M9: the velocity march is sequential
     return compile_model(modelInput, block=n2_block(B, lanes=lanes), method=method, lanes=lanes)
 
 

@@ -114,10 +114,11 @@ def test_m9_inputs_and_launch_shape():
 
 def test_launch_shapes_and_pipeline_cuts():
     # lanes per reactor of the dynamic integrator: about three resident waves of threads, never more lanes than nodes
-    assert [engine.n2_lanes(B, 200) for B in (1, 100, 4096, 12500, 50000, 10**6)] == [32, 32, 16, 8, 2, 1]
+    assert [engine.n2_lanes(B, 200) for B in (1, 100, 4096, 12500, 50000, 10**6)] == [32, 32, 8, 8, 8, 1]
     assert engine.n2_lanes(1, 12) == 16 and engine.n2_lanes(1, 3) == 4
-    assert engine.n2_block(12500, lanes=8) == 128 and engine.n2_block(1, lanes=32) == 32
-    assert engine.n2_block(10**6) == 128 and engine.n2_block(5000) == 32 and engine.n2_block(8000) == 64
+    assert engine.n2_lanes(12500, 200, n=3) == 4 and engine.n2_lanes(12500, 200, n=4) == 8
+    assert engine.n2_block(12500, lanes=8) == 64 and engine.n2_block(1, lanes=32) == 32
+    assert engine.n2_block(10**6) == 64 and engine.n2_block(5000) == 32 and engine.n2_block(8000) == 64
     # copy/compute pipeline: chunks cover the ensemble exactly, are non-empty and 1024-aligned inside
     for B in (3*1024, 5000, 1 << 18, (1 << 20) + 7, 10**7):
         cuts = engine.pipeline_cuts(B)

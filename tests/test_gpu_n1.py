@@ -387,7 +387,9 @@ def test_zero_feed_species_inside_a_denominator(process, reduced):
         r = eng.n1_solve_ensemble(cm, mi, None, 1, z_eval=z, **tol)
         assert r.status[0] == 0, r.status
         assert r.stats[1, 0] <= 0.25*r.stats[0, 0] + 3            # no rejection storm
-        assert (r.out[:, 3, 0] == 0.0).all()                      # the inert's mole fraction is exactly zero everywhere
+        # the inert's mole fraction: exactly zero in the extent form (y = y0 + nu^T xi, nu = 0), at the rounding floor
+        # of the linear solves in the full-state form
+        assert (r.out[:, 3, 0] == 0.0).all() if reduced else (np.abs(r.out[:, 3, 0]) < 1e-15).all()
     want = O.N1Oracle(mi).solve(method="LSODA", rtol=1e-11, atol=1e-13, t_eval=z)
     got = r.out[:, :, 0].T                                        # dataYs rows: y_i..., P, (T)
     ref = O.N1Oracle(mi).pack(want)[0]["dataYs"]
@@ -424,6 +426,6 @@ def test_irreversible_reaction_at_complete_conversion(reduced):
         assert r.status[0] == 0, r.status
         assert r.stats[1, 0] <= 0.5*r.stats[0, 0] + 3, r.stats[:, 0]
         got = r.out[:, :, 0].T
-        assert (got[:3] >= 0).all()
+        assert (got[:3] >= -1e-9).all()                           # interpolated points: zero within the tolerance
         assert np.max(np.abs(got[1:] - want[1:])/np.abs(want[1:])) < bar
         assert np.max(np.abs(got[0] - want[0])) < bar             # the vanishing reactant: absolute (mole fraction)

@@ -120,7 +120,7 @@ def test_n2_lanes_per_reactor_give_the_same_solution(n2_settings, case):
             continue
         np.testing.assert_allclose(r.out, ref.out, rtol=1e-11, atol=0)
         np.testing.assert_array_equal(r.stats[0], ref.stats[0])
-    assert engine.n2_lanes(1, 50) == 32 and engine.n2_lanes(12500, 200) == 8 and engine.n2_lanes(10**6, 50) == 1
+    assert engine.n2_lanes(1, 50) == 32 and engine.n2_lanes(12500, 200) == 8 and engine.n2_lanes(10**7, 50) == 1
     assert engine.n2_lanes(1, 4) == 4
 
 

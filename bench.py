@@ -347,10 +347,25 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------
-# executed FP64 flop per step attempt of rmt_n1_solve on this workload (methanol kinetics, Ros4, reaction-extent
-# form), from ncu's smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on.sum of one launch divided by its
-# 54.25 M attempts (profiles/r01_ncu_n1_solve_v6_final.csv); a calibration like `traffic`, not a live counter
-EXEC_FLOP_PER_ATTEMPT = 2*1400 + 693 + 272
+CALIBRATION = os.path.join(ROOT, "profiles", "r02_calibration.json")
+CPU_BASELINES = os.path.join(ROOT, "profiles", "r02_cpu_baselines.json")
+
+
+def load_json(path):
+    try:
+        with open(path) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+def calibration_for(cal, kernel, module_key):
+    """The ncu-derived numbers of one kernel (tools/make_calibration.py wrote them from profiles/*.csv together with
+    the identity of the cubin they were measured on).  Returns (entry or None, stale flag)."""
+    if not cal or kernel not in cal.get("kernels", {}):
+        return None, True
+    e = cal["kernels"][kernel]
+    return e, e.get("module_key") != module_key
 
 
 def solver_flops(info, stats, cm):
@@ -378,7 +393,7 @@ def solver_flops(info, stats, cm):
 def run_gpu_arm(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    from rmt_app_b200 import capi, engine, rmtExeBatch
+    from rmt_app_b200 import capi, engine, ensemble, rmtExe, rmtExeBatch, solverSetting
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback "
@@ -387,6 +402,27 @@ def run_gpu_arm(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(vals):
+        t = torch.tensor([float(v) for v in vals], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(v) for v in t.tolist()]
+
+    cal = load_json(CALIBRATION)
+    cpu_file = load_json(CPU_BASELINES)
 
     # CPU baseline first (rank 0, N=1 only), before the timed GPU region
     cpu_baseline = None
@@ -431,11 +467,6 @@ def run_gpu_arm(args, rank, world, local_rank):
         if ev is not None:
             ev[2].record()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     sampler = ClockSampler(local_rank)
     sampler.start()
     for _ in range(max(args.warmup, 3)):
@@ -451,24 +482,15 @@ def run_gpu_arm(args, rank, world, local_rank):
     t_end.record()
     barrier()
     clocks = sampler.stop()
-    elapsed_ms = t_start.elapsed_time(t_end)
+    elapsed_ms = max_over_ranks(t_start.elapsed_time(t_end))
     setup_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
     solve_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
-    if world > 1:
-        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
 
     status = d_status.cpu().numpy()
     stats = d_stats.cpu().numpy()
     n_ok = int((status == 0).sum())
     alg, wt, att, nfev = solver_flops(info, stats, cm)
-    if world > 1:
-        t = torch.tensor([n_ok, att, nfev], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        n_ok_all = int(t[0].item())
-    else:
-        n_ok_all = n_ok
+    n_ok_all = int(sum_over_ranks([n_ok])[0])
 
     # ---- e2e through the public API: host arrays in, host arrays out -----------------------------
     # inputs live in pinned host memory (the contract's e2e definition); results land in pinned host memory
@@ -480,16 +502,11 @@ def run_gpu_arm(args, rank, world, local_rank):
     for _ in range(args.steps):
         r = rmtExeBatch(base, psweep, workspace=ws, rtol=RTOL, atol=ATOL, return_stats=False)
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
     h2d, d2h = r["h2d_bytes"], r["d2h_bytes"]
     e2e_ok = int(r["success"].sum())
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
 
     # ---- the same through the C ABI's host-buffer entry point (rmt_n1_solve_host: no torch on the path) -----------
-    # SoA rows in pinned host memory in, pinned host arrays out; the library runs its own three-chunk pipeline
     hp_out = torch.empty((1, n, B), dtype=torch.float64).pin_memory()
     hp_status = torch.empty((B,), dtype=torch.int32).pin_memory()
     rows_np, out_np, status_np = h_rows.numpy(), hp_out.numpy(), hp_status.numpy()
@@ -499,40 +516,103 @@ def run_gpu_arm(args, rank, world, local_rank):
     t0 = time.perf_counter()
     for _ in range(args.steps):
         mod.n1_solve_host(B, rows_np, n_rows, row_map, uniform, z_eval, RTOL, ATOL, out_np, status_np, ctrl=ctrl)
-    cabi_s = time.perf_counter() - t0
+    cabi_s = max_over_ranks(time.perf_counter() - t0)
     cabi_ok = int((status_np == 0).sum())
-    if world > 1:
-        t = torch.tensor([cabi_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        cabi_s = float(t.item())
 
-    # ---- BASELINE configs[3]: parameter-estimation population, sharded, NCCL objective reduction + gather -------
+    # ---- the parity-grade tolerance (what the 1e-6 agreement with the reference is proven at) ----------------------
+    tight = None
+    if not args.no_tight:
+        cmt = engine.compile_model(base, method=engine.choose_method(base, 1e-9, 1))          # Rodas4(3)
+        modt = cmt.load(local_rank)
+        ctrl_t = engine.METHOD_CTRL.get(cmt.method)
+        Bt = B
+        for _ in range(2):
+            modt.n1_solve(Bt, d_consts, z_eval, 1e-9, 1e-12, d_out, d_status, d_stats, out_mode=1, ctrl=ctrl_t, stream=stream)
+        barrier()
+        q0 = torch.cuda.Event(enable_timing=True); q1 = torch.cuda.Event(enable_timing=True)
+        q0.record()
+        modt.n1_solve(Bt, d_consts, z_eval, 1e-9, 1e-12, d_out, d_status, d_stats, out_mode=1, ctrl=ctrl_t, stream=stream)
+        q1.record(); torch.cuda.synchronize()
+        tms = max_over_ranks(q0.elapsed_time(q1))
+        st_t = d_stats[:, :Bt].cpu().numpy()
+        ok_t, att_t = sum_over_ranks([int((d_status[:Bt] == 0).sum().item()), float(st_t[3].sum())])
+        tight = {"instances": world*Bt, "rtol": 1e-9, "atol": 1e-12, "integrator": cmt.method + " (6 stages, stiffly accurate)",
+                 "ms": tms, "solves_per_s": world*Bt/(tms*1e-3), "attempts_per_solve": att_t/(world*Bt), "converged": int(ok_t),
+                 "note": "the tolerance at which outlets agree with the converged reference to <= 1e-6 "
+                         "(tests/test_gpu_n1.py level 2); the same 2^20 config-3 reactors, inputs resident, outlet only"}
+
+    # ---- BASELINE configs[0]: one N1 reactor through rmtExe ---------------------------------------------------------
+    config1 = None
+    if rank == 0:
+        rmtExe(base)
+        best = min(_timed(lambda: rmtExe(base)) for _ in range(5))
+        config1 = {"rmtExe_single_N1_s": best, "what": "rmt_app_b200.rmtExe(modelInput): README inputs, 101-point profiles, default tolerances, "
+                                                       "warm module (trace + NVRTC + module load happen once per process)"}
+        if cpu_single:
+            config1.update(reference_rmtExe_s=cpu_single["config1_single_rmtExe_s"], reference_nfev=cpu_single["config1_nfev"],
+                           speedup=cpu_single["config1_single_rmtExe_s"]/best, reference="unmodified PyREMOT (oracle/_ref), this host, one core")
+        elif cpu_file:
+            config1.update(reference_rmtExe_s=cpu_file.get("config1_single_rmtExe_s"), reference="profiles/r02_cpu_baselines.json (measured on a GPU box host)")
+
+    # ---- BASELINE configs[3]: parameter-estimation population, sharded, ONE packed collective ----------------------
     config4 = None
     if not args.no_config4:
-        from rmt_app_b200 import ensemble
         base4 = cases.methanol_readme_input("N1")
         base4["reaction-rates"] = cases.methanol_kinetics_param(1171.2)
         B4 = 65536
         pop = cases.config4_population(B4)
+        ppop = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in pop.items()}
         cm4 = engine.compile_model(base4, method=engine.choose_method(base4, RTOL, 1))
         nominal = engine.n1_solve_ensemble(cm4, base4, None, 1, rtol=1e-9, atol=1e-12).out[0, :, 0]
         ws4 = engine.Workspace()
-        r4 = ensemble.rmtExeBatchSharded(base4, pop, B4, objective_ref=nominal, workspace=ws4)      # warm-up
-        reps = 5
+        for _ in range(2):
+            r4 = ensemble.rmtExeBatchSharded(base4, ppop, B4, objective_ref=nominal, workspace=ws4)
+        reps = 10
         barrier()
-        c0 = torch.cuda.Event(enable_timing=True); c1 = torch.cuda.Event(enable_timing=True)
-        c0.record()
+        t0 = time.perf_counter()
         for _ in range(reps):
-            r4 = ensemble.rmtExeBatchSharded(base4, pop, B4, objective_ref=nominal, workspace=ws4)
-        c1.record(); torch.cuda.synchronize()
-        t4 = torch.tensor([c0.elapsed_time(c1)/reps], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t4, op=dist.ReduceOp.MAX)
-        config4 = {"parameter_sets": B4, "ms_per_population": float(t4.item()), "parameter_sets_per_s": B4/(float(t4.item())*1e-3),
-                   "includes": "H2D of the rank's shard, setup, solve with fused objective, device reduction, "
-                               + ("NCCL all-gather of (sum, min, argmin) + all-gather of objectives and outlets" if world > 1
-                                  else "no collective (one rank)"),
-                   "objective_min": r4["objective_min"], "objective_argmin": r4["objective_argmin"], "failed": r4["failed"]}
+            r4 = ensemble.rmtExeBatchSharded(base4, ppop, B4, objective_ref=nominal, workspace=ws4)
+        torch.cuda.synchronize()
+        ms4 = max_over_ranks((time.perf_counter() - t0)/reps*1e3)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            r4b = ensemble.rmtExeBatchSharded(base4, ppop, B4, objective_ref=nominal, workspace=ws4, gather=False)
+        torch.cuda.synchronize()
+        ms4b = max_over_ranks((time.perf_counter() - t0)/reps*1e3)
+        config4 = {"parameter_sets": B4, "ms_per_population": ms4, "parameter_sets_per_s": B4/(ms4*1e-3),
+                   "ms_per_population_statistics_only": ms4b,
+                   "includes": "wall time of ensemble.rmtExeBatchSharded (max over ranks): H2D of the rank's shard from pinned memory, setup, "
+                               "solve with fused objective and fused (sum, min, argmin, failed) reduction, "
+                               + ("ONE NCCL all-gather of the packed [outlets | objectives | status | tail] buffer" if world > 1
+                                  else "no collective (one rank)") + ", one D2H of the gathered buffer; 'statistics_only' gathers the 4-number tails only",
+                   "objective_min": r4["objective_min"], "objective_argmin": r4["objective_argmin"], "failed": r4["failed"],
+                   "statistics_only_same_minimum": bool(r4b["objective_min"] == r4["objective_min"] and r4b["objective_argmin"] == r4["objective_argmin"])}
+        if cpu_file and "config4" in cpu_file:
+            c4 = cpu_file["config4"]
+            config4["reference"] = {"solves_per_s_box": c4["solves_per_s_box"], "cores": cpu_file["host"]["cores"], "sample": c4["sample"],
+                                    "ms_per_population_extrapolated": B4/c4["solves_per_s_box"]*1e3,
+                                    "source": "profiles/r02_cpu_baselines.json (unmodified reference, GPU box host)"}
+
+    # ---- strong scaling: ONE fixed ensemble over all ranks, gather to rank 0 included ------------------------------
+    strong = None
+    if not args.no_strong:
+        Bs = args.strong_instances
+        sw_s = cases.config3_sweep(Bs, SEED + 1000)                    # the same draw on every rank
+        psw_s = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in sw_s.items()}
+        wss = engine.Workspace()
+        rs = ensemble.rmtExeBatchSharded(base, psw_s, Bs, rtol=RTOL, atol=ATOL, gather="root", workspace=wss)   # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        rs = ensemble.rmtExeBatchSharded(base, psw_s, Bs, rtol=RTOL, atol=ATOL, gather="root", workspace=wss)
+        torch.cuda.synchronize()
+        ss = max_over_ranks(time.perf_counter() - t0)
+        strong = {"instances_total": Bs, "seconds": ss, "solves_per_s": Bs/ss, "failed": rs["failed"],
+                  "includes": "ensemble.rmtExeBatchSharded(gather='root'), wall time, max over ranks: every rank copies its contiguous "
+                              "1/N of the pinned inputs H2D, solves it, ONE all-gather of outlets + status, rank 0 copies the full "
+                              "result (%.0f MB) to the host" % (Bs*(8*n + 4)/1e6),
+                  "scaling": "strong (total work fixed as N grows)"}
+        del psw_s, sw_s, wss, rs
 
     # ---- the reference's own output shape: 101-point profiles of every reactor (runN1's t_eval, :2931) -----------
     profile = None
@@ -558,98 +638,117 @@ def run_gpu_arm(args, rank, world, local_rank):
 
     # ---- roofline denominators measured on this box ----------------------------------------------
     fp64_peak = mod.fp64_peak(iters=16384, repeats=5)
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
+    peaks = load_json(os.path.join(ROOT, "MEASURED_PEAKS.json")) or {}
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    hbm_src = "MEASURED_PEAKS.json (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md; of fallback)"
 
-    # stand-alone RHS kernel (HBM-bound): nconst + n rows in, n rows out per evaluation
+    # stand-alone RHS / Jacobian kernels (HBM-bound): L2 flushed before every launch
     d_y = torch.rand((n, B), dtype=torch.float64, device=dev)*0.5 + 0.25
     d_y[n - 2] = 1.0
     d_y[n - 1] = 0.1
     d_f = torch.empty((n, B), dtype=torch.float64, device=dev)
-    for _ in range(3):
-        mod.n1_rhs(B, d_consts, d_y, d_f, stream=stream)
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    reps = 10
-    e0.record()
-    for _ in range(reps):
-        mod.n1_rhs(B, d_consts, d_y, d_f, stream=stream)
-    e1.record()
-    torch.cuda.synchronize()
-    rhs_ms = e0.elapsed_time(e1)/reps
-    # algorithmic bytes per evaluation: the 14 hot constants + kinetic parameters + state in, derivative out
-    rhs_bytes = 8.0*(14 + info.nkp + 2*n)*B
     d_J = torch.empty((n*n, B), dtype=torch.float64, device=dev)
-    for _ in range(3):
-        mod.n1_jac(B, d_consts, d_y, d_f, d_J, stream=stream)
-    e0.record()
-    for _ in range(reps):
-        mod.n1_jac(B, d_consts, d_y, d_f, d_J, stream=stream)
-    e1.record()
-    torch.cuda.synchronize()
-    jac_ms = e0.elapsed_time(e1)/reps
-    jac_bytes = 8.0*(14 + info.nkp + 2*n + n*n)*B
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    # ---- the dynamic model (BASELINE configs[1] and configs[4]), informational ---------------------
-    # every rank solves its own 12 500-reactor share of config 5 (100 000 reactors x 200 nodes over 8 GPUs); the time is
-    # the max over ranks.  The single 50-node reactor (config 2) runs on rank 0.
+    def timed_flushed(fn, reps=10):
+        ts = []
+        for _ in range(reps + 3):
+            flush.zero_()                                           # 256 MB > 126 MB L2
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return float(np.mean(ts[3:]))
+    rhs_ms = timed_flushed(lambda: mod.n1_rhs(B, d_consts, d_y, d_f, stream=stream))
+    jac_ms = timed_flushed(lambda: mod.n1_jac(B, d_consts, d_y, d_f, d_J, stream=stream))
+    # algorithmic bytes per evaluation: the 14 hot constants + kinetic parameters + state in, derivative (+ Jacobian) out
+    rhs_bytes = 8.0*(14 + info.nkp + 2*n)*B
+    jac_bytes = 8.0*(14 + info.nkp + 2*n + n*n)*B
+    del flush
+
+    # ---- the dynamic model (BASELINE configs[1] and configs[4]) through the product API -----------------------------
     n2 = None
     if not args.no_n2:
-        from rmt_app_b200 import rmtExe, solverSetting
         mi2 = cases.methanol_readme_input("N2")
         single_s = None
         if rank == 0:
             solverSetting["N2"]["zNo"] = 50
             rmtExe(mi2)
-            t0 = time.perf_counter()
-            rmtExe(mi2)
-            single_s = time.perf_counter() - t0
+            single_s = min(_timed(lambda: rmtExe(mi2)) for _ in range(3))
             solverSetting["N2"]["zNo"] = 20
-        Bn, zn = 12500, 200
-        cm2 = engine.compile_model_n2(mi2, Bn, zn)
-        sw2 = cases.config3_sweep(Bn, 20240613 + rank)
-        r2 = engine.n2_solve_ensemble(cm2, mi2, sw2, Bn, zNo=zn, tNo=5, period=0.5, keep_on_device=True, workspace=ws)   # warm-up
+        Bn, zn = 12500*world, 200
+        sw2 = cases.config3_sweep(Bn, 20240613)                        # the SAME 100 000-reactor draw on every rank (N = 8)
+        psw2 = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in sw2.items()}
+        ws2 = engine.Workspace()
+        r2 = ensemble.rmtExeBatchN2Sharded(mi2, psw2, Bn, zNo=zn, tNo=5, gather=None, workspace=ws2)        # warm-up
         barrier()
         q0 = torch.cuda.Event(enable_timing=True); q1 = torch.cuda.Event(enable_timing=True)
         q0.record()
-        r2 = engine.n2_solve_ensemble(cm2, mi2, sw2, Bn, zNo=zn, tNo=5, period=0.5, keep_on_device=True, workspace=ws)
+        r2 = ensemble.rmtExeBatchN2Sharded(mi2, psw2, Bn, zNo=zn, tNo=5, gather=None, workspace=ws2)
         q1.record(); torch.cuda.synchronize()
+        ens_s = max_over_ranks(q0.elapsed_time(q1)*1e-3)
+        barrier()
+        t0 = time.perf_counter()
+        r2g = ensemble.rmtExeBatchN2Sharded(mi2, psw2, Bn, zNo=zn, tNo=5, gather="final", workspace=ws2, keep_on_device=True)
+        torch.cuda.synchronize()
+        ens_gather_s = max_over_ranks(time.perf_counter() - t0)
+        lanes2 = engine.n2_lanes(12500, zn)
+        cm2 = engine.compile_model_n2(mi2, 12500, zn)
         i2 = cm2.load(local_rank).info
-        t2 = torch.tensor([q0.elapsed_time(q1)*1e-3, float(r2.stats[3].double().sum().item()),
-                           float((r2.status == 0).sum().item()), float(r2.stats[0].double().sum().item())],
-                          dtype=torch.float64, device=dev)
-        if world > 1:
-            tmax = t2[:1].clone()
-            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-            dist.all_reduce(t2, op=dist.ReduceOp.SUM)
-            t2[0] = tmax[0]
-        ens_s, att2, ok2, acc2 = (float(v) for v in t2.tolist())
+        att2, ok2, acc2 = sum_over_ranks([float(r2["local_stats"][3].double().sum().item()),
+                                          float((r2["local_status"] == 0).sum().item()),
+                                          float(r2["local_stats"][0].double().sum().item())])
         nn = i2.n
-        # per attempt and node: 1 f + Jacobian blocks, (s-1) RHS, LU + n unit-vector solves (explicit inverse), per stage
-        # two n x n matrix-vector products and the stage combinations
-        lin = (2.0*nn**3)/3.0 + nn*2.0*nn*nn + i2.stages*(4.0*nn*nn + 4.0*nn*i2.stages)
+        # per attempt and node: f + Jacobian blocks, (s-1) RHS, LU + n unit-vector solves (explicit inverse) + the pressure row,
+        # per stage one (n+1) x n matrix-vector product and the stage combinations
+        lin = (2.0*nn**3)/3.0 + nn*2.0*nn*nn + 2.0*nn*nn + i2.stages*(2.0*(nn + 1)*nn + 4.0*nn*i2.stages)
         alg2 = att2*zn*(i2.flops_jac_alg + (i2.stages - 1)*i2.flops_rhs_alg + lin)
-        n2 = {"config2_single_50_nodes_s": single_s, "reference_bdf_same_case_s": 446.3,
-              "ensemble": {"instances": world*Bn, "instances_per_gpu": Bn, "nodes": zn, "period_s": 0.5, "seconds": ens_s,
-                           "instances_per_s": world*Bn/ens_s, "converged": int(ok2), "steps_mean": acc2/(world*Bn),
-                           "lanes_per_reactor": cm2.lanes, "block": cm2.block,
+        e2, stale2 = calibration_for(cal, "rmt_n2_solve", cm2.key())
+        n2 = {"config2_single_50_nodes_s": single_s,
+              "config2_reference_bdf_s": (cpu_file or {}).get("config2_single_n2_50_nodes_bdf_s"),
+              "config2_reference_source": "profiles/r02_cpu_baselines.json: the unmodified reference, same inputs, solverSetting zNo = 50, "
+                                          "ivp = BDF, measured on a GPU box host (one core)" if cpu_file else None,
+              "ensemble": {"instances": Bn, "instances_per_gpu": Bn//world, "nodes": zn, "period_s": 0.5, "seconds": ens_s,
+                           "instances_per_s": Bn/ens_s, "converged": int(ok2), "failed": r2["failed"], "steps_mean": acc2/Bn,
+                           "lanes_per_reactor": lanes2, "block": cm2.block,
+                           "seconds_incl_gather_of_final_profiles": ens_gather_s,
+                           "gathered_bytes_per_rank": int(8*r2g["layout"].length*world),
                            "node_rhs_evals_per_s": att2*zn*i2.stages/ens_s,
-                           "fp64_tflops_algorithmic": alg2/ens_s/1e12,
-                           # dram bytes of one launch from ncu (profiles/r01_ncu_n2_solve_lanes8_v4_final.csv: 15 + 101 GB
-                           # at 12 500 x 200 nodes x 43.0 attempts; L2 hit rate 92 %), scaled per node-attempt
-                           "hbm_traffic_gbs_ncu_calibrated": 1080.0*att2*zn/ens_s/1e9,
-                           "note": "device time (CUDA events, max over ranks) of engine.n2_solve_ensemble: H2D of the sweep, "
-                                   "setup, integrator; results stay on the device; bound: FP64 / instruction latency at "
-                                   "8 warps per SM (work rows stay in L2), see DESIGN.md 5.2"}}
+                           "fp64_tflops_algorithmic": alg2/ens_s/1e12, "fp64_frac_of_measured_peak": alg2/ens_s/1e12/fp64_peak/world,
+                           "api": "rmt_app_b200.rmtExeBatchN2Sharded(modelInput, sweep, zNo=200, tNo=5): every rank integrates its "
+                                  "contiguous block; device time (CUDA events, max over ranks) incl. H2D of the rank's inputs, setup, "
+                                  "integrator, ONE packed all-gather (status + tails; with gather='final' also the [n][200] profiles)",
+                           "reference_rhs_200_nodes_s_per_call": (cpu_file or {}).get("config5_modelEquationN2_200_nodes_s_per_call")}}
+        if e2:
+            n2["ensemble"]["ncu"] = dict(e2, calibration_stale=stale2)
+        del psw2, sw2, r2g
 
     if rank == 0:
         steps = args.steps
         total = world*B*steps
         solve_s = solve_ms*1e-3
+        e1, stale1 = calibration_for(cal, "rmt_n1_solve", cm.key())
+        er, staler = calibration_for(cal, "rmt_n1_rhs", cm.key())
+        ej, stalej = calibration_for(cal, "rmt_n1_jac", cm.key())
+        roof = {
+            "kernel": "rmt_n1_solve", "bound": "fp64", "achieved": alg/solve_s/1e12, "peak": fp64_peak,
+            "unit": "TFLOP/s", "frac": alg/solve_s/1e12/fp64_peak,
+            "traffic": None, "traffic_algorithmic": 8.0*(22 + n)*B + 20.0*B,
+            "achieved_weighted": wt/solve_s/1e12, "frac_weighted": wt/solve_s/1e12/fp64_peak,
+            "peak_source": "rmt_dfma_peak measured in this run (MEASURED_PEAKS.json has no FP64 figure; "
+                           "nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2)",
+            "kernel_ms": solve_ms, "kernel_share_of_step": solve_ms/(elapsed_ms/steps),
+            "flops_per_launch_alg": alg, "flops_per_launch_weighted": wt,
+            "attempts_per_solve": att/B, "rhs_evals_per_solve": (nfev + att)/B,
+            "note": "contract offers hbm|tensor; this kernel keeps all state on-chip (HBM traffic = 200 B in + 64 B "
+                    "out per reactor) and has no contraction, so the bounding pipe is FP64 FMA",
+        }
+        if e1:
+            # numbers read off the ncu capture named in the calibration file (per launch of 2^20 reactors / per step attempt)
+            fl = 2*e1["dfma_per_attempt"] + e1["dmul_per_attempt"] + e1["dadd_per_attempt"]
+            roof.update(traffic=e1["dram_bytes_per_reactor"]*B, achieved_executed=fl*att/solve_s/1e12,
+                        frac_executed=fl*att/solve_s/1e12/fp64_peak, fp64_pipe_busy_ncu=e1["fp64_pipe_busy"],
+                        calibration={"file": "profiles/r02_calibration.json", "source": e1.get("source"),
+                                     "module_key": e1.get("module_key")}, calibration_stale=stale1)
         line = {
             "metric": METRIC, "value": total/(elapsed_ms*1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
             "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms/steps, "higher_is_better": True, "scaling": "weak",
@@ -663,55 +762,49 @@ def run_gpu_arm(args, rank, world, local_rank):
                                         "api": "rmt_n1_solve_host (include/rmt_b200.h) with pinned host buffers, same bytes"}},
             "gpu_launches": 2*steps,
             "converged": n_ok_all, "instances": world*B,
-            "roofline": {
-                "kernel": "rmt_n1_solve", "bound": "fp64", "achieved": alg/solve_s/1e12, "peak": fp64_peak,
-                "unit": "TFLOP/s", "frac": alg/solve_s/1e12/fp64_peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the ncu --set full capture of this
-                # command at 2^20 reactors (profiles/r01_ncu_n1_solve_v6_final.csv: 179.7 MB + 63.2 MB), scaled per reactor
-                "traffic": 232.0*B, "traffic_algorithmic": 8.0*(22 + n)*B + 20.0*B,
-                # FP64 flops the hardware executed: thread-level DFMA (x2) + DMUL + DADD counts of the same ncu capture
-                # per step attempt (1400 + 693 + 272 instructions = 3765 flop), times this run's attempts
-                "achieved_executed": EXEC_FLOP_PER_ATTEMPT*att/solve_s/1e12,
-                "frac_executed": EXEC_FLOP_PER_ATTEMPT*att/solve_s/1e12/fp64_peak,
-                "fp64_pipe_busy_ncu": 0.565,
-                # model count with one FP64 instruction per operation and exp 25 / log 35 / div 10: an
-                # upper estimate of the instruction count — FMA fusion halves it in practice
-                "achieved_weighted": wt/solve_s/1e12, "frac_weighted": wt/solve_s/1e12/fp64_peak,
-                "peak_source": "rmt_dfma_peak measured in this run (MEASURED_PEAKS.json has no FP64 figure; "
-                               "nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2)",
-                "kernel_ms": solve_ms, "kernel_share_of_step": solve_ms/(elapsed_ms/steps),
-                "flops_per_launch_alg": alg, "flops_per_launch_weighted": wt,
-                "attempts_per_solve": att/B, "rhs_evals_per_solve": (nfev + att)/B,
-                "note": "contract offers hbm|tensor; this kernel keeps all state on-chip (HBM traffic = 200 B in + 64 B "
-                        "out per reactor) and has no contraction, so the bounding pipe is FP64 FMA",
-            },
+            "roofline": roof,
             "roofline_rhs_kernel": {
                 "kernel": "rmt_n1_rhs", "bound": "hbm", "achieved": rhs_bytes/(rhs_ms*1e-3)/1e9, "peak": hbm_peak,
-                "unit": "GB/s", "frac": rhs_bytes/(rhs_ms*1e-3)/1e9/hbm_peak, "traffic": None, "peak_source": hbm_src,
-                "kernel_ms": rhs_ms, "rhs_evals_per_s": B/(rhs_ms*1e-3),
+                "unit": "GB/s", "frac": rhs_bytes/(rhs_ms*1e-3)/1e9/hbm_peak,
+                "traffic": er["dram_bytes_per_launch"]*B/er["instances"] if er else None,
+                "frac_by_traffic": (er["dram_bytes_per_launch"]*B/er["instances"]/(rhs_ms*1e-3)/1e9/hbm_peak) if er else None,
+                "fp64_pipe_busy_ncu": er["fp64_pipe_busy"] if er else None, "calibration_stale": staler,
+                "peak_source": hbm_src, "kernel_ms": rhs_ms, "rhs_evals_per_s": B/(rhs_ms*1e-3),
+                "timing": "CUDA events, L2 flushed (256 MB memset) before every launch",
                 "fp64_tflops_weighted": B*info.flops_rhs_wt/(rhs_ms*1e-3)/1e12,
             },
             "roofline_jac_kernel": {
                 "kernel": "rmt_n1_jac", "bound": "hbm", "achieved": jac_bytes/(jac_ms*1e-3)/1e9, "peak": hbm_peak,
-                "unit": "GB/s", "frac": jac_bytes/(jac_ms*1e-3)/1e9/hbm_peak, "traffic": None, "peak_source": hbm_src,
-                "kernel_ms": jac_ms, "jac_evals_per_s": B/(jac_ms*1e-3),
+                "unit": "GB/s", "frac": jac_bytes/(jac_ms*1e-3)/1e9/hbm_peak,
+                "traffic": ej["dram_bytes_per_launch"]*B/ej["instances"] if ej else None,
+                "frac_by_traffic": (ej["dram_bytes_per_launch"]*B/ej["instances"]/(jac_ms*1e-3)/1e9/hbm_peak) if ej else None,
+                "fp64_pipe_busy_ncu": ej["fp64_pipe_busy"] if ej else None, "calibration_stale": stalej,
+                "peak_source": hbm_src, "kernel_ms": jac_ms, "jac_evals_per_s": B/(jac_ms*1e-3),
+                "timing": "CUDA events, L2 flushed (256 MB memset) before every launch",
                 "fp64_tflops_weighted": B*info.flops_jac_wt/(jac_ms*1e-3)/1e12,
             },
             "rhs_evals_per_sec_in_solver": world*(nfev + att)/solve_s,
             "setup_kernel_ms": setup_ms,
         }
-        if n2 is not None:
-            line["n2_dynamic_model"] = n2
-        if config4 is not None:
-            line["config4_population"] = config4
-        if profile is not None:
-            line["profile_101_points"] = profile
-        if cpu_baseline is not None:
-            line["cpu_baseline"] = cpu_baseline
+        if cpu_single:
+            line["reference_rhs_only"] = {"modelEquationN1_evals_per_s_per_core": cpu_single["modelEquationN1_evals_per_s_per_core"],
+                                          "s_per_call": cpu_single["modelEquationN1_s_per_call"],
+                                          "what": "the unmodified reference's RHS called on states of its own solution, one host core"}
+        for key, val in (("tight_tolerance", tight), ("config1_single_reactor", config1), ("n2_dynamic_model", n2),
+                         ("config4_population", config4), ("strong_scaling", strong), ("profile_101_points", profile),
+                         ("cpu_baseline", cpu_baseline)):
+            if val is not None:
+                line[key] = val
         emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def _timed(fn):
+    t0 = time.perf_counter()
+    fn()
+    return time.perf_counter() - t0
 
 
 _JSON_OUT = None
@@ -747,6 +840,9 @@ def main():
     ap.add_argument("--no-n2", action="store_true", help="skip the informational N2 (dynamic model) timings")
     ap.add_argument("--no-config4", action="store_true", help="skip the informational parameter-estimation population timing")
     ap.add_argument("--no-profile", action="store_true", help="skip the informational 101-point-profile timing")
+    ap.add_argument("--no-tight", action="store_true", help="skip the parity-grade-tolerance timing (Rodas4, rtol 1e-9)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling block (one fixed ensemble over all ranks)")
+    ap.add_argument("--strong-instances", type=int, default=1 << 23)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -135,13 +135,13 @@ int rmt_n1_solve(rmt_module_t m, int64_t B, const double* d_consts, int32_t n_ev
                  double* d_out, int32_t* d_status, int32_t* d_stats,
                  const double* obj_ref, double* d_obj, const double* ctrl, void* stream);
 
-/* Parameter-estimation populations: rmt_n1_solve for the outlet only (z = 1, out_mode 1:
- * d_out [n][B]) with the fused objective AND its reduction: the last block of the integrator kernel to finish folds
+/* Parameter-estimation populations: rmt_n1_solve for the outlet only (z_end = 1 for N1, ReLe
+ * for M7; out_mode 1: d_out [n][B]) with the fused objective AND its reduction: the last block of the integrator kernel to finish folds
  * d_obj[0..B) and d_status[0..B) — in a fixed order, deterministic — into d_red[0..3] = {sum, min, argmin +
  * index_offset (exact as a double), number of reactors with status != 0}.  No second kernel and no host round trip
  * before the cross-GPU step: d_red may point into the buffer that is handed to rmt_comm_allgather.
  * (no reference counterpart: the reference never implemented the estimation loop its README names, README.md:5) */
-int rmt_n1_solve_population(rmt_module_t m, int64_t B, const double* d_consts, double rtol, double atol,
+int rmt_n1_solve_population(rmt_module_t m, int64_t B, const double* d_consts, double z_end, double rtol, double atol,
                             int32_t max_steps, double* d_out, int32_t* d_status, int32_t* d_stats,
                             const double* obj_ref, double* d_obj, double* d_red, int64_t index_offset,
                             const double* ctrl, void* stream);

@@ -7,10 +7,10 @@ pseudo-homogeneous packed-bed reactor models N1 (steady state) and N2
 from .rmt import rmtExe, rmtCom, rmtExeBatch, rmtExeBatchN2      # noqa: F401
 from .engine import solverSetting, Workspace       # noqa: F401
 
-from .ensemble import rmtExeBatchSharded            # noqa: F401
+from .ensemble import rmtExeBatchSharded, rmtExeBatchN2Sharded            # noqa: F401
 
 from .textkin import parse_reaction_rates           # noqa: F401
 from .estimate import differential_evolution        # noqa: F401
 
-__all__ = ["rmtExe", "rmtCom", "rmtExeBatch", "rmtExeBatchN2", "rmtExeBatchSharded", "solverSetting", "Workspace",
+__all__ = ["rmtExe", "rmtCom", "rmtExeBatch", "rmtExeBatchN2", "rmtExeBatchSharded", "rmtExeBatchN2Sharded", "solverSetting", "Workspace",
            "parse_reaction_rates", "differential_evolution"]

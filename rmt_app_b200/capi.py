@@ -54,7 +54,7 @@ SIGNATURES = {
     "rmt_n1_sys": (C.c_int, [_u64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "rmt_n1_solve": (C.c_int, [_u64, _i64, _vp, _i32, _pdbl, _dbl, _dbl, _i32, _i32, _i32, _vp, _vp, _vp, _pdbl,
                                _vp, _pdbl, _vp]),
-    "rmt_n1_solve_population": (C.c_int, [_u64, _i64, _vp, _dbl, _dbl, _i32, _vp, _vp, _vp, _pdbl, _vp, _vp, _i64, _pdbl,
+    "rmt_n1_solve_population": (C.c_int, [_u64, _i64, _vp, _dbl, _dbl, _dbl, _i32, _vp, _vp, _vp, _pdbl, _vp, _vp, _i64, _pdbl,
                                           _vp]),
     "rmt_n1_solve_host": (C.c_int, [_u64, _i64, _vp, _i32, _pi32, _pdbl, _i32, _pdbl, _dbl, _dbl, _i32, _i32, _i32,
                                     _vp, _vp, _vp, _pdbl, _vp, _pdbl]),
@@ -140,17 +140,24 @@ def nvrtc_compile(model_src, block=128, arch="sm_100a", extra_opts=(), want_ptx=
     return (cubin, log, ptx) if want_ptx else (cubin, log)
 
 
-def cached_cubin(model_src, block=128, arch="sm_100a"):
-    """Disk cache keyed by the exact translation unit + options."""
+def cubin_key(model_src, block=128, arch="sm_100a", extra_opts=()):
+    """Identity of a compiled module: hash of the exact translation unit (generated header + hand-written
+    kernels) and its options.  Names the cache file; profiles/*calibration.json records it so that numbers
+    read off an ncu capture can be recognised as stale when the kernel source has changed since."""
     h = hashlib.sha256()
-    for part in (model_src, kernels_source(), arch, str(block), lib().rmt_version().decode()):
+    for part in (model_src, kernels_source(), arch, str(block), lib().rmt_version().decode()) + tuple(extra_opts):
         h.update(part.encode())
         h.update(b"\0")
-    path = os.path.join(CACHE_DIR, h.hexdigest()[:24] + ".cubin")
+    return h.hexdigest()[:24]
+
+
+def cached_cubin(model_src, block=128, arch="sm_100a", extra_opts=()):
+    """Disk cache keyed by the exact translation unit + options."""
+    path = os.path.join(CACHE_DIR, cubin_key(model_src, block, arch, extra_opts) + ".cubin")
     if os.path.exists(path):
         with open(path, "rb") as f:
             return f.read()
-    cubin, _ = nvrtc_compile(model_src, block=block, arch=arch)
+    cubin, _ = nvrtc_compile(model_src, block=block, arch=arch, extra_opts=extra_opts)
     try:
         os.makedirs(CACHE_DIR, exist_ok=True)
         tmp = path + ".%d.tmp" % os.getpid()
@@ -220,11 +227,11 @@ class Module:
                                   None if ref is None else _dptr(ref), _ptr(d_obj),
                                   None if ctl is None else _dptr(ctl), stream))
 
-    def n1_solve_population(self, B, d_consts, rtol, atol, d_out, d_status, d_stats, obj_ref, d_obj, d_red,
+    def n1_solve_population(self, B, d_consts, z_end, rtol, atol, d_out, d_status, d_stats, obj_ref, d_obj, d_red,
                             index_offset=0, max_steps=100000, ctrl=None, stream=None):
         ref = np.ascontiguousarray(obj_ref, dtype=np.float64)
         ctl = None if ctrl is None else np.ascontiguousarray(ctrl, dtype=np.float64)
-        _check(lib().rmt_n1_solve_population(self.handle, B, _ptr(d_consts), rtol, atol, max_steps, _ptr(d_out),
+        _check(lib().rmt_n1_solve_population(self.handle, B, _ptr(d_consts), z_end, rtol, atol, max_steps, _ptr(d_out),
                                              _ptr(d_status), _ptr(d_stats), _dptr(ref), _ptr(d_obj), _ptr(d_red),
                                              index_offset, None if ctl is None else _dptr(ctl), stream))
 

@@ -617,15 +617,12 @@ int rmt_n1_solve(rmt_module_t m, int64_t B, const double* d_consts, int32_t n_ev
                          obj_ref, d_obj, nullptr, 0, ctrl, stream);
 }
 
-int rmt_n1_solve_population(rmt_module_t m, int64_t B, const double* d_consts, double rtol, double atol, int32_t max_steps,
-                            double* d_out, int32_t* d_status, int32_t* d_stats, const double* obj_ref, double* d_obj,
-                            double* d_red, int64_t index_offset, const double* ctrl, void* stream)
+int rmt_n1_solve_population(rmt_module_t m, int64_t B, const double* d_consts, double z_end, double rtol, double atol,
+                            int32_t max_steps, double* d_out, int32_t* d_status, int32_t* d_stats,
+                            const double* obj_ref, double* d_obj, double* d_red, int64_t index_offset,
+                            const double* ctrl, void* stream)
 {
     if (!obj_ref || !d_obj || !d_red) return fail("rmt_n1_solve_population: obj_ref, d_obj and d_red are required");
-    Module* M = get_module(m);
-    if (!M) return fail("invalid module handle");
-    const double z_end = M->info.model == 7 ? -1.0 : 1.0;
-    if (z_end < 0.0) return fail("rmt_n1_solve_population: model M7 integrates over [0, ReLe]; use rmt_n1_solve with z_eval = {ReLe}");
     return n1_solve_impl(m, B, d_consts, 1, &z_end, rtol, atol, max_steps, 0, 1, d_out, d_status, d_stats,
                          obj_ref, d_obj, d_red, index_offset, ctrl, stream);
 }

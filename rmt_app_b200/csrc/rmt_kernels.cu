@@ -67,9 +67,27 @@ __device__ __forceinline__ double rmt_clamp_abs(const double x, const int hi_lim
 #endif
 // (Literal coefficients on purpose: fetching them from the constant bank was measured — no gain for the
 // integrator, and the one-shot RHS kernel lost 25 % to the extra constant-load latency.)
+// 1 = Estrin evaluation of the exp polynomial (13 FMA + 3 MUL, depth 5) instead of Horner (14 FMA, depth 14)
+#ifndef RMT_EXP_ESTRIN
+#define RMT_EXP_ESTRIN 0
+#endif
 __device__ __forceinline__ double rmt_exp_reduced(const double r, const int k)
 {
     // exp(r) for |r| <= ln2/2 by the degree-13 Taylor polynomial (truncation 4e-18), times 2^k
+#if RMT_EXP_ESTRIN
+    const double r2 = r*r, r4 = r2*r2, r8 = r4*r4;
+    const double a0 = fma(r, 1.0, 1.0);
+    const double a1 = fma(r, 0.16666666666666666, 0.5);
+    const double a2 = fma(r, 0.008333333333333333, 0.041666666666666664);
+    const double a3 = fma(r, 0.0001984126984126984, 0.001388888888888889);
+    const double a4 = fma(r, 2.7557319223985893e-06, 2.48015873015873e-05);
+    const double a5 = fma(r, 2.505210838544172e-08, 2.755731922398589e-07);
+    const double a6 = fma(r, 1.6059043836821613e-10, 2.08767569878681e-09);
+    const double b0 = fma(a1, r2, a0), b1 = fma(a3, r2, a2), b2 = fma(a5, r2, a4);
+    const double c0 = fma(b1, r4, b0), c1 = fma(a6, r4, b2);
+    const double pe = fma(c1, r8, c0);
+    return __hiloint2double(__double2hiint(pe) + (k << 20), __double2loint(pe));
+#endif
     double p = 1.6059043836821613e-10;                 // 1/13!
     p = fma(p, r, 2.08767569878681e-09);               // 1/12!
     p = fma(p, r, 2.505210838544172e-08);              // 1/11!
@@ -217,7 +235,9 @@ __device__ __forceinline__ double rmt_sqrt(const double x)
     g = fma(g, r, g); hh = fma(hh, r, hh);
     const double d = fma(-g, g, x);
     g = fma(d, hh, g);
-    return x == 0.0 ? 0.0 : g;
+    // 0 -> 0; +Inf -> +Inf and NaN -> NaN (x + x) instead of the NaN / garbage the iteration makes of them
+    const bool special = (__double2hiint(x) & 0x7fffffff) >= 0x7ff00000;
+    return x == 0.0 ? 0.0 : (special ? x + x : g);
 #endif
 }
 // x^a for the step-size controllers (x > 0): exp(a*log(x)) with the branch-free pair above.  libdevice's pow is a
@@ -243,6 +263,20 @@ __device__ __forceinline__ double rmt_powc(const double x, const double a)
 #endif
 
 #include "rmt_model.cuh"
+
+// err^(1/order) for the step-size controller.  For the fourth-order tableaux this is a fourth root of a number in
+// [1e-10, 1e30], and the controller needs three digits of it: two MUFU.RSQ in single precision (rsqrt(rsqrt(x)) =
+// x^(1/4), relative error ~1e-6) instead of a double-precision log + exp — about 60 FP64 instructions less per call,
+// 2.2 calls per step attempt.
+__device__ __forceinline__ double rmt_root_order(const double x, const double inv_order)
+{
+#if !RMT_EXACT_MATH && RMT_ROS_ORDER == 4
+    (void)inv_order;
+    return (double)rsqrtf(rsqrtf((float)fmax(x, 1e-37)));
+#else
+    return rmt_powc(x, inv_order);
+#endif
+}
 
 #define RMT_R_CONST 8.314472            // core/constants.py:8
 #define RMT_TREF 298.15                 // core/constants.py:17-23
@@ -1053,7 +1087,11 @@ struct GlobalJac {
 };
 
 // stand-alone batched Jacobian: y [N][B] -> f [N][B], J [N*N][B] (row-major d f_r / d y_c)
-extern "C" __global__ void __launch_bounds__(128)
+// (HBM-bound, n^2 stores per reactor: occupancy buys memory-level parallelism, RMT_JAC_MINBLOCKS blocks per SM)
+#ifndef RMT_JAC_MINBLOCKS
+#define RMT_JAC_MINBLOCKS 2
+#endif
+extern "C" __global__ void __launch_bounds__(128, RMT_JAC_MINBLOCKS)
 rmt_n1_jac(const double* __restrict__ consts, const i64 B, const double* __restrict__ y,
            double* __restrict__ f, double* __restrict__ J)
 {
@@ -1561,13 +1599,13 @@ extern "C" __global__ void RMT_SOLVE_BOUNDS rmt_n1_solve(const SolveArgs a)
         if (BETA > 0.0 && nacc > 0)            // PI controller (Gustafsson 1991): uses the previous accepted error
             fac = rmt_powc(errc, 1.0/(RMT_ROS_ORDER) - 0.75*BETA)*rmt_powc(erracc, -BETA)*ISAFE;   // note erracc^(-beta): small previous error -> grow
         else
-            fac = rmt_powc(errc, 1.0/(RMT_ROS_ORDER))*ISAFE;
+            fac = rmt_root_order(errc, 1.0/(RMT_ROS_ORDER))*ISAFE;
         fac = fmax(FAC2, fmin(FAC1, fac));
         double hnew = hh*rmt_rcp(fac);
         int fin = -1;
         if (err <= 1.0) {
             if (nacc > 0 && BETA <= 0.0) {
-                double facgus = (hacc*invh)*rmt_powc(err*err*rmt_rcp(erracc), 1.0/(RMT_ROS_ORDER))*ISAFE;
+                double facgus = (hacc*invh)*rmt_root_order(err*err*rmt_rcp(erracc), 1.0/(RMT_ROS_ORDER))*ISAFE;
                 facgus = fmax(FAC2, fmin(FAC1, facgus));
                 fac = fmax(fac, facgus);
                 hnew = hh*rmt_rcp(fac);
@@ -1737,10 +1775,15 @@ struct NodeJac {                             // derivative blocks of one node
 
 // f_k and the Ergun gradient E_k [Pa/m] at one node.  u: node state, ub: upwind node state (or the
 // inlet boundary values), P: pressure at the node.
-template <bool JAC>
+// (the diagonal block d f_k / d u_k is handed entry by entry to `asink(row, col, value)`, column by column, so that it
+// never has to exist in registers as a whole: the integrator stores W_kk = I/(h gamma) - A straight into shared memory)
+struct NodeJacSink { NodeJac& nj; __device__ __forceinline__ void operator()(int r, int c, double v) const { nj.A[r][c] = v; } };
+struct NoSink { __device__ __forceinline__ void operator()(int, int, double) const {} };
+
+template <bool JAC, class AS>
 __device__ __forceinline__ void n2_node(const double (&u)[RMT_N], const double (&ub)[RMT_N], const bool inlet,
                                         const double P, const double invdz, const Hot& h,
-                                        double (&f)[RMT_N], double& E, NodeJac& nj)
+                                        double (&f)[RMT_N], double& E, NodeJac& nj, AS&& asink)
 {
     double C[RMT_NC];
 #pragma unroll
@@ -1824,7 +1867,7 @@ __device__ __forceinline__ void n2_node(const double (&u)[RMT_N], const double (
                 for (int j = 0; j < RMT_NR; ++j) if (RMT_NU[j][i] != 0.0) dr += RMT_NU[j][i]*dR[j];
                 double v = dr*F1Gm;
                 if (!isP && i == col) v -= h.F1*invdz;
-                if (isP) nj.g[i] = v; else nj.A[i][col < RMT_N ? col : 0] = v;
+                if (isP) nj.g[i] = v; else asink(i, col < RMT_N ? col : 0, v);
             }
 #if !RMT_ISO
             double dq = 0.0;
@@ -1844,7 +1887,7 @@ __device__ __forceinline__ void n2_node(const double (&u)[RMT_N], const double (
             const double dlnD = dlnrho + dCp*invCp;
             double vT = h.invZv*(dN*invD - Nn*invD*dlnD);
             if (!isP && col == RMT_ITN) vT -= h.invZv*invdz;
-            if (isP) nj.g[RMT_ITN] = vT; else nj.A[RMT_ITN][col < RMT_N ? col : 0] = vT;
+            if (isP) nj.g[RMT_ITN] = vT; else asink(RMT_ITN, col < RMT_N ? col : 0, vT);
 #endif
         }
         // upwind coupling (diagonal)
@@ -2023,7 +2066,7 @@ rmt_n2_rhs(const double* __restrict__ consts, const i64 B, const int zNo, const 
         m9_node<false>(u, ub, k == 0, P, vs, invdz, h, fo, E, V, nj);
         vs = V*dz + vs;                                                            // pbReactor.py:2612
 #else
-        n2_node<false>(u, ub, k == 0, P, invdz, h, fo, E, nj);
+        n2_node<false>(u, ub, k == 0, P, invdz, h, fo, E, nj, NoSink());
 #endif
 #pragma unroll
         for (int v = 0; v < RMT_N; ++v) { f[((i64)v*zNo + k)*B + i] = fo[v]; ub[v] = u[v]; }
@@ -2095,6 +2138,26 @@ __device__ __forceinline__ void n2_lu_solve(const double (&A)[RMT_N][RMT_N], con
     }
 }
 
+// column c of the inverse: the same solve for the unit vector e_c — the permuted right-hand side is one compare per row
+__device__ __forceinline__ void n2_lu_solve_unit(const double (&A)[RMT_N][RMT_N], const int (&perm)[RMT_N],
+                                                 const int c, double (&x)[RMT_N])
+{
+#pragma unroll
+    for (int r = 0; r < RMT_N; ++r) {
+        double v = perm[r] == c ? 1.0 : 0.0;
+#pragma unroll
+        for (int q = 0; q < r; ++q) v -= A[r][q]*x[q];
+        x[r] = v;
+    }
+#pragma unroll
+    for (int r = RMT_N - 1; r >= 0; --r) {
+        double v = x[r];
+#pragma unroll
+        for (int q = r + 1; q < RMT_N; ++q) v -= A[r][q]*x[q];
+        x[r] = v*A[r][r];
+    }
+}
+
 __device__ __forceinline__ int n2_out_rows(const int mode) { return mode == 2 ? 2*RMT_N + RMT_NC : RMT_N; }
 
 // Lanes per reactor.  G consecutive lanes serve one reactor; node k belongs to lane k % G of node group
@@ -2143,10 +2206,10 @@ __device__ __forceinline__ double n2_pressure_chain(const double Pin, const doub
 
 // One node group of a sweep: pressures (M9: and velocities) at the nodes, then the node functions.  Pg (vg) enter as
 // the values at the group's first node and leave as those of the next group's.
-template <bool JAC>
+template <bool JAC, class AS>
 __device__ __forceinline__ void dyn_eval(const double (&u)[RMT_N], const double (&ub)[RMT_N], const bool inlet,
                                          double& Pg, double& vg, const double dz, const double invdz, const Hot& h,
-                                         const int g, const unsigned gmask, double (&f)[RMT_N], NodeJac& nj)
+                                         const int g, const unsigned gmask, double (&f)[RMT_N], NodeJac& nj, AS&& asink)
 {
     double E;
 #if defined(RMT_MODEL_M9)
@@ -2155,7 +2218,7 @@ __device__ __forceinline__ void dyn_eval(const double (&u)[RMT_N], const double 
     m9_node<JAC>(u, ub, inlet, Pg, vg, invdz, h, f, E, V, nj);
     Pg = E*dz + Pg;                                                                // pbReactor.py:2546
     vg = V*dz + vg;                                                                // pbReactor.py:2612
-    (void)g; (void)gmask;
+    (void)g; (void)gmask; (void)asink;
 #else
 #if RMT_ISO
     const double Tn = 0.0*h.Tf + h.Tf;
@@ -2164,7 +2227,7 @@ __device__ __forceinline__ void dyn_eval(const double (&u)[RMT_N], const double 
 #endif
     double Pnext;
     const double P = n2_pressure_chain(Pg, n2_mw(u, h), Tn, h, dz, g, gmask, Pnext);
-    n2_node<JAC>(u, ub, inlet, P, invdz, h, f, E, nj);
+    n2_node<JAC>(u, ub, inlet, P, invdz, h, f, E, nj, asink);
     Pg = Pnext;
     (void)vg;
 #endif
@@ -2286,7 +2349,7 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
                     ub[v] = g == 0 ? carry[v] : up;
                     carry[v] = G > 1 ? __shfl_sync(gmask, u[v], G - 1, G) : u[v];
                 }
-                dyn_eval<false>(u, ub, kg == 0 && g == 0, Pg, vg, dz, invdz, h, g, gmask, fo, nj);
+                dyn_eval<false>(u, ub, kg == 0 && g == 0, Pg, vg, dz, invdz, h, g, gmask, fo, nj, NoSink());
                 double n0 = 0.0, n1 = 0.0;
 #pragma unroll
                 for (int v = 0; v < RMT_N; ++v) {
@@ -2345,7 +2408,8 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
                     ub[v] = g == 0 ? carry[v] : up;
                     carry[v] = G > 1 ? __shfl_sync(gmask, u[v], G - 1, G) : u[v];
                 }
-                dyn_eval<true>(u, ub, kg == 0 && g == 0, Pg, vg, dz, invdz, h, g, gmask, fo, nj);
+#if defined(RMT_MODEL_M9)
+                dyn_eval<true>(u, ub, kg == 0 && g == 0, Pg, vg, dz, invdz, h, g, gmask, fo, nj, NoSink());
                 // W_kk = I/(h*gamma) - A, LU with partial pivoting in registers
                 int perm[RMT_N];
 #pragma unroll
@@ -2383,20 +2447,85 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
                 // lane-to-lane hand-over of the stage sweeps waits for.
 #pragma unroll 1
                 for (int c = 0; c < RMT_N; ++c) {
-                    double b[RMT_N], xs[RMT_N];
-#pragma unroll
-                    for (int q = 0; q < RMT_N; ++q) b[q] = q == c ? 1.0 : 0.0;
-                    n2_lu_solve(nj.A, perm, b, xs);
-#if defined(RMT_MODEL_M9)
+                    double xs[RMT_N];
+                    n2_lu_solve_unit(nj.A, perm, c, xs);
 #pragma unroll
                     for (int q = 0; q < RMT_N; ++q) WS(W_LU + q*RMT_N + c) = xs[q];
+                }
 #else
+                // N2: W_kk = I/(h*gamma) - A is written into shared memory as it is computed (the rows of the inverse
+                // block, free at this point), factorised there — partial pivoting through per-row pointers held in
+                // registers, every access [row pointer + immediate] like the steady-state integrator — and inverted
+                // column by column into the work rows W_LU (global, own column, coalesced); the inverse then replaces the
+                // factors.  The block never lives in registers (round 1: 98 registers + local-memory row swaps, 1.2e9
+                // local loads per launch).
+                struct WSink {
+                    double* shc; double dg;
+                    __device__ __forceinline__ void operator()(int r, int cc, double v) const {
+                        shc[(S_AUG + r*RMT_N + cc)*(RMT_BLOCK + 1)] = (r == cc ? dg : 0.0) - v;
+                    }
+                };
+                dyn_eval<true>(u, ub, kg == 0 && g == 0, Pg, vg, dz, invdz, h, g, gmask, fo, nj, WSink{shc, dg});
+                double* rowp[RMT_N];
+                int perm[RMT_N];
+#pragma unroll
+                for (int r = 0; r < RMT_N; ++r) { rowp[r] = shc + (S_AUG + r*RMT_N)*SH_LD; perm[r] = r; }
+#define LUW(r, q) rowp[r][(q)*SH_LD]
+#pragma unroll
+                for (int c = 0; c < RMT_N; ++c) {
+                    double best = fabs(LUW(c, c));
+                    int bi = c;
+#pragma unroll
+                    for (int r = c + 1; r < RMT_N; ++r) { const double v = fabs(LUW(r, c)); if (v > best) { best = v; bi = r; } }
+#pragma unroll
+                    for (int r = c + 1; r < RMT_N; ++r)
+                        if (r == bi) {
+                            double* tr = rowp[c]; rowp[c] = rowp[r]; rowp[r] = tr;
+                            const int tp = perm[c]; perm[c] = perm[r]; perm[r] = tp;
+                        }
+                    const double piv = rmt_rcp(LUW(c, c));
+                    LUW(c, c) = piv;                               // reciprocal pivot
+                    double urow[RMT_N];
+#pragma unroll
+                    for (int q = c + 1; q < RMT_N; ++q) urow[q] = LUW(c, q);
+#pragma unroll
+                    for (int r = c + 1; r < RMT_N; ++r) {
+                        const double l = LUW(r, c)*piv;
+                        LUW(r, c) = l;
+#pragma unroll
+                        for (int q = c + 1; q < RMT_N; ++q) LUW(r, q) -= l*urow[q];
+                    }
+                }
+                // explicit inverse (see the M9 branch for why), column by column; the pressure row dz e_k^T W_kk^{-1}
+                double wrow[RMT_N];
+#pragma unroll
+                for (int c = 0; c < RMT_N; ++c) {
+                    double xs[RMT_N];
+#pragma unroll
+                    for (int r = 0; r < RMT_N; ++r) {
+                        double v = perm[r] == c ? 1.0 : 0.0;
+#pragma unroll
+                        for (int q = 0; q < r; ++q) v -= LUW(r, q)*xs[q];
+                        xs[r] = v;
+                    }
+#pragma unroll
+                    for (int r = RMT_N - 1; r >= 0; --r) {
+                        double v = xs[r];
+#pragma unroll
+                        for (int q = r + 1; q < RMT_N; ++q) v -= LUW(r, q)*xs[q];
+                        xs[r] = v*LUW(r, r);
+                    }
                     double we = 0.0;
 #pragma unroll
-                    for (int q = 0; q < RMT_N; ++q) { SH(S_AUG + q*RMT_N + c) = xs[q]; we = fma(nj.e[q], xs[q], we); }
-                    SH(S_AUG + RMT_N*RMT_N + c) = dz*we;       // row n: d(dP_{k+1})/d(tv_k) = dz * e_k^T W_kk^{-1}
-#endif
+                    for (int q = 0; q < RMT_N; ++q) { WS(W_LU + q*RMT_N + c) = xs[q]; we = fma(nj.e[q], xs[q], we); }
+                    wrow[c] = dz*we;
                 }
+#undef LUW
+#pragma unroll
+                for (int q = 0; q < RMT_N*RMT_N; ++q) SH(S_AUG + q) = WS(W_LU + q);
+#pragma unroll
+                for (int c = 0; c < RMT_N; ++c) SH(S_AUG + RMT_N*RMT_N + c) = wrow[c];     // row n: d(dP_{k+1})/d(tv_k)
+#endif
 #pragma unroll
                 for (int r = 0; r < RMT_N; ++r) {
                     WS(W_K + r) = fo[r];                   // stage-1 right-hand side
@@ -2447,10 +2576,17 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
                     double u[RMT_N], ub[RMT_N], vc[RMT_N];
 #pragma unroll
                     for (int v = 0; v < RMT_N; ++v) { u[v] = WY(YN + v, kg); vc[v] = 0.0; }
-                    for (int j = 0; j < s; ++j) {
-                        const double aj = RMT_cROS_A[s][j], cj = RMT_cROS_C[s][j]*invh;
+                    // (compile-time trip count with predicated loads: the stage vectors of all earlier stages are
+                    // fetched back to back instead of one stage per loop iteration)
 #pragma unroll
-                        for (int v = 0; v < RMT_N; ++v) { const double kv = WS(W_K + j*RMT_N + v); u[v] += aj*kv; vc[v] += cj*kv; }
+                    for (int j = 0; j < RMT_ROS_S - 1; ++j) {
+                        const bool on = j < s;
+                        const double aj = on ? RMT_cROS_A[s][j] : 0.0, cj = on ? RMT_cROS_C[s][j]*invh : 0.0;
+#pragma unroll
+                        for (int v = 0; v < RMT_N; ++v) {
+                            const double kv = on ? WS(W_K + j*RMT_N + v) : 0.0;
+                            u[v] += aj*kv; vc[v] += cj*kv;
+                        }
                     }
 #pragma unroll
                     for (int v = 0; v < RMT_N; ++v) {
@@ -2459,7 +2595,7 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
                         carry[v] = G > 1 ? __shfl_sync(gmask, u[v], G - 1, G) : u[v];
                     }
                     NodeJac njd;
-                    dyn_eval<false>(u, ub, kg == 0 && g == 0, Pg, vg, dz, invdz, h, g, gmask, rhs, njd);
+                    dyn_eval<false>(u, ub, kg == 0 && g == 0, Pg, vg, dz, invdz, h, g, gmask, rhs, njd, NoSink());
 #pragma unroll
                     for (int v = 0; v < RMT_N; ++v) rhs[v] += vc[v];
                 }
@@ -2503,9 +2639,13 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
                             const int r = g + q*G;
                             if (r <= RMT_N) {
                                 const double* wr = sj + (S_AUG + r*RMT_N)*SH_LD;
-                                double acc = wr[0]*tv[0];
+                                // two partial sums (even / odd columns): half the dependent chain of the hand-over
+                                double acc = wr[0]*tv[0], acc1 = RMT_N > 1 ? wr[SH_LD]*tv[RMT_N > 1 ? 1 : 0] : 0.0;
 #pragma unroll
-                                for (int cc = 1; cc < RMT_N; ++cc) acc = fma(wr[cc*SH_LD], tv[cc], acc);
+                                for (int cc = 2; cc < RMT_N; cc += 2) acc = fma(wr[cc*SH_LD], tv[cc], acc);
+#pragma unroll
+                                for (int cc = 3; cc < RMT_N; cc += 2) acc1 = fma(wr[cc*SH_LD], tv[cc], acc1);
+                                acc += acc1;
                                 if (r < RMT_N) { kprev[q] = acc; sj[(S_R + r)*SH_LD] = acc; }
                                 else dPn = fma(dP, sj[S_DPF*SH_LD], acc);
                             }
@@ -2602,7 +2742,8 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
                         const double yo = WY(YN + v, kg);
                         double yn = yo;
                         double ev = 0.0;
-                        for (int j = 0; j < s; ++j) {
+#pragma unroll
+                        for (int j = 0; j < RMT_ROS_S - 1; ++j) {         // the last stage: s == RMT_ROS_S - 1
                             const double kj = WS(W_K + j*RMT_N + v);
                             yn += RMT_cROS_M[j]*kj; ev += RMT_cROS_E[j]*kj;
                         }
@@ -2638,13 +2779,13 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
         const double errc = fmax(err, 1e-10);
         double fac;
         if (BETA > 0.0 && nacc > 0) fac = rmt_powc(errc, 1.0/(RMT_ROS_ORDER) - 0.75*BETA)*rmt_powc(erracc, -BETA)*ISAFE;
-        else fac = rmt_powc(errc, 1.0/(RMT_ROS_ORDER))*ISAFE;
+        else fac = rmt_root_order(errc, 1.0/(RMT_ROS_ORDER))*ISAFE;
         fac = fmax(FAC2, fmin(FAC1, fac));
         double hnew = hh*rmt_rcp(fac);
         int fin = -1;
         if (err <= 1.0) {
             if (nacc > 0 && BETA <= 0.0) {
-                double facgus = (hacc*invh)*rmt_powc(err*err*rmt_rcp(erracc), 1.0/(RMT_ROS_ORDER))*ISAFE;
+                double facgus = (hacc*invh)*rmt_root_order(err*err*rmt_rcp(erracc), 1.0/(RMT_ROS_ORDER))*ISAFE;
                 facgus = fmax(FAC2, fmin(FAC1, facgus));
                 fac = fmax(fac, facgus);
                 hnew = hh*rmt_rcp(fac);

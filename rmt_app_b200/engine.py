@@ -37,11 +37,43 @@ def _torch():
     return torch
 
 
+class nvtx_range:
+    """NVTX range around a host-side phase (trace / compile / H2D / setup / solve / D2H) — visible in Nsight Systems
+    timelines; a no-op pair of calls (~0.2 us) when no profiler is attached or CUDA is absent."""
+    __slots__ = ("name", "on")
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        try:
+            _torch().cuda.nvtx.range_push("rmt:" + self.name)
+            self.on = True
+        except Exception:
+            self.on = False
+        return self
+
+    def __exit__(self, *a):
+        if self.on:
+            try:
+                _torch().cuda.nvtx.range_pop()
+            except Exception:
+                pass
+        return False
+
+
+EXACT_MATH_OPTS = ("-DRMT_EXACT_MATH=1", "-DRMT_EXACT_DIV=1")
+
+
 class CompiledModel:
-    def __init__(self, spec, block, method="rodas4", reduced=None, lanes=1):
+    def __init__(self, spec, block, method="rodas4", reduced=None, lanes=1, exact_math=False):
         self.spec = spec
         self.block = block
         self.method = method
+        # IEEE special-value semantics (exp(-Inf) = 0, x/Inf = 0, NaN propagation) instead of the branch-free
+        # device math: libdevice exp/log/sqrt/pow and IEEE division, at ~1.5x the integrator time
+        self.exact_math = bool(exact_math)
+        self.opts = EXACT_MATH_OPTS if self.exact_math else ()
         self.reduced = use_extents(spec) if reduced is None else bool(reduced)
         self.m = system_size(spec, self.reduced)          # unknowns of the integrator's linear systems
         self.lanes = int(lanes) if spec.model in ("N2", "M9") else 1     # dynamic models: threads per reactor
@@ -52,9 +84,15 @@ class CompiledModel:
     def load(self, device):
         if self.module is None:
             capi.init(device)
-            cubin = capi.cached_cubin(self.header, block=self.block)
-            self.module = capi.Module(cubin)
+            with nvtx_range("nvrtc_compile_or_cache"):
+                cubin = capi.cached_cubin(self.header, block=self.block, extra_opts=self.opts)
+            with nvtx_range("module_load"):
+                self.module = capi.Module(cubin)
         return self.module
+
+    def key(self):
+        """Identity of the loaded cubin (see capi.cubin_key)."""
+        return capi.cubin_key(self.header, block=self.block, extra_opts=self.opts)
 
 
 def default_block(spec, stages=6, reduced=None):
@@ -228,20 +266,25 @@ def _fast_key(modelInput, block):
 _fast = {}
 
 
-def compile_model(modelInput, block=None, method=None, reduced=None, lanes=1):
+def compile_model(modelInput, block=None, method=None, reduced=None, lanes=1, exact_math=None):
     """Trace + generate + (lazily) NVRTC-compile; cached per model structure and integrator tableau.
     `method` None resolves solver-config.method for a dense-output solve (Rodas4 unless stated);
-    `reduced` None integrates in reaction extents whenever nr < nc (codegen.use_extents)."""
+    `reduced` None integrates in reaction extents whenever nr < nc (codegen.use_extents);
+    `exact_math` None reads solver-config["exact-math"] (extension key, default False): libdevice math and IEEE
+    division with their special-value semantics instead of the branch-free device versions."""
     if method is None:
         method = choose_method(modelInput, rtol=0.0)
+    if exact_math is None:
+        exact_math = bool(modelInput.get("solver-config", {}).get("exact-math", False))
     try:
-        fk = _fast_key(modelInput, block) + (method, reduced, lanes)
+        fk = _fast_key(modelInput, block) + (method, reduced, lanes, exact_math)
         cm = _fast.get(fk)
         if cm is not None:
             return cm
     except Exception:
         fk = None
-    cm = _compile_model(modelInput, block, method, reduced, lanes)
+    with nvtx_range("trace_and_codegen"):
+        cm = _compile_model(modelInput, block, method, reduced, lanes, exact_math)
     if fk is not None:
         if len(_fast) > 256:
             _fast.clear()
@@ -249,17 +292,17 @@ def compile_model(modelInput, block=None, method=None, reduced=None, lanes=1):
     return cm
 
 
-def _compile_model(modelInput, block, method, reduced=None, lanes=1):
+def _compile_model(modelInput, block, method, reduced=None, lanes=1, exact_math=False):
     from .tableau import TABLEAUX
     spec = ModelSpec(modelInput)
     if reduced is None:
         reduced = use_extents(spec)
     blk = block or default_block(spec, TABLEAUX[method]["stages"], reduced)
-    key = spec.key("b%d%s%sg%d" % (blk, method, "x" if reduced else "", lanes))
+    key = spec.key("b%d%s%sg%d%s" % (blk, method, "x" if reduced else "", lanes, "e" if exact_math else ""))
     with _lock:
         cm = _compiled.get(key)
         if cm is None:
-            cm = CompiledModel(spec, blk, method, reduced, lanes)
+            cm = CompiledModel(spec, blk, method, reduced, lanes, exact_math)
             _compiled[key] = cm
     return cm
 
@@ -527,15 +570,18 @@ def n1_solve_ensemble(cm, modelInput, sweep=None, B=1, z_eval=None, rtol=None, a
     def device_part(sub, Bc, w):
         """H2D + setup + integrator for one (sub-)ensemble on the current stream; device tensors."""
         stream = torch.cuda.current_stream().cuda_stream
-        d_rows, n_rows, row_map, h2d = sweep_rows_to_device(spec, sub, Bc, w, dev)
+        with nvtx_range("h2d"):
+            d_rows, n_rows, row_map, h2d = sweep_rows_to_device(spec, sub, Bc, w, dev)
         d_consts = w.get("d_consts", (mod.info.nconst, Bc), torch.float64, device=dev)
         d_out = w.get("d_out", (z_eval.size, out_rows, Bc), torch.float64, device=dev)
         d_status = w.get("d_status", (Bc,), torch.int32, device=dev)
         d_stats = w.get("d_stats", (4, Bc), torch.int32, device=dev)
         d_obj = w.get("d_obj", (Bc,), torch.float64, device=dev) if objective_ref is not None else None
-        mod.setup(Bc, d_rows, n_rows, row_map, uniform, d_consts, stream=stream)
-        mod.n1_solve(Bc, d_consts, z_eval, rtol, atol, d_out, d_status, d_stats, max_steps=max_steps, dense=dense,
-                     out_mode=out_mode, obj_ref=objective_ref, d_obj=d_obj, ctrl=ctrl, stream=stream)
+        with nvtx_range("setup"):
+            mod.setup(Bc, d_rows, n_rows, row_map, uniform, d_consts, stream=stream)
+        with nvtx_range("n1_solve"):
+            mod.n1_solve(Bc, d_consts, z_eval, rtol, atol, d_out, d_status, d_stats, max_steps=max_steps, dense=dense,
+                         out_mode=out_mode, obj_ref=objective_ref, d_obj=d_obj, ctrl=ctrl, stream=stream)
         return d_consts, d_out, d_status, d_stats, d_obj, h2d
 
     with torch.cuda.device(dev):
@@ -551,13 +597,14 @@ def n1_solve_ensemble(cm, modelInput, sweep=None, B=1, z_eval=None, rtol=None, a
             + (h_obj.numel()*8 if h_obj is not None else 0)
         if not pipeline:
             res.consts, d_out, d_status, d_stats, d_obj, res.h2d_bytes = device_part(sweep, B, ws)
-            h_out.copy_(d_out, non_blocking=True)
-            h_status.copy_(d_status, non_blocking=True)
-            if want_stats:
-                h_stats.copy_(d_stats, non_blocking=True)
-            if d_obj is not None:
-                h_obj.copy_(d_obj, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            with nvtx_range("d2h"):
+                h_out.copy_(d_out, non_blocking=True)
+                h_status.copy_(d_status, non_blocking=True)
+                if want_stats:
+                    h_stats.copy_(d_stats, non_blocking=True)
+                if d_obj is not None:
+                    h_obj.copy_(d_obj, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
         else:
             # chunk c runs on stream c % 2 with that stream's own device buffers: H2D(c+1) and D2H(c-1) overlap
             # the integrator kernel of chunk c, and the blocks of the next kernel fill the tail of this one
@@ -674,16 +721,19 @@ def n2_solve_ensemble(cm, modelInput, sweep=None, B=1, zNo=None, tNo=None, perio
         d_status = ws.get("d_status", (B,), torch.int32, device=dev)
         d_stats = ws.get("d_stats", (4, B), torch.int32, device=dev)
         d_work = ws.get("d_work", (mod.n2_work_doubles(B, zNo),), torch.float64, device=dev)
-        mod.setup(B, d_rows, n_rows, row_map, uniform, d_consts, stream=stream)
-        mod.n2_solve(B, zNo, tNo, period, d_consts, rtol, atol, d_out, d_status, d_stats, d_work,
-                     max_steps=max_steps, out_mode=out_mode, ctrl=ctrl, stream=stream)
+        with nvtx_range("setup"):
+            mod.setup(B, d_rows, n_rows, row_map, uniform, d_consts, stream=stream)
+        with nvtx_range("n2_solve"):
+            mod.n2_solve(B, zNo, tNo, period, d_consts, rtol, atol, d_out, d_status, d_stats, d_work,
+                         max_steps=max_steps, out_mode=out_mode, ctrl=ctrl, stream=stream)
         if keep_on_device:
             res.out, res.status, res.stats = d_out, d_status, d_stats
             res.d2h_bytes = 0
         else:
-            res.out = d_out.cpu().numpy()
-            res.status = d_status.cpu().numpy()
-            res.stats = d_stats.cpu().numpy()
+            with nvtx_range("d2h"):
+                res.out = d_out.cpu().numpy()
+                res.status = d_status.cpu().numpy()
+                res.stats = d_stats.cpu().numpy()
             res.d2h_bytes = res.out.nbytes + res.status.nbytes + res.stats.nbytes
     return res
 

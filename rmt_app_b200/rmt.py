@@ -165,7 +165,8 @@ def _runM9(modelInput):
     out = {"XYList": XYList, "dataList": dataList, "dataPack": dataPack}
     if _display(modelInput):
         from .plotting import plotResultsDynamic
-        plotResultsDynamic({"dataPack": [dict(d, dataXs=dataXs, labelList=labelList, indexList=[nc, nc + 1, nc],
+        plotResultsDynamic({"computation-time": 0.0,
+                            "dataPack": [dict(d, dataXs=dataXs, labelList=labelList, indexList=[nc, nc + 1, nc],
                                               modelId="M9") for d in dataPack]}, tNo)
     return out
 

@@ -410,6 +410,65 @@ def part_props():
     print("props done")
 
 
+class PlotRecorder:
+    """Stand-in for matplotlib.pyplot that records what is drawn."""
+
+    def __init__(self):
+        self.calls = []
+
+    def install(self, module):
+        for name in ("plot", "title", "xlabel", "ylabel", "legend", "show", "figure", "subplots"):
+            setattr(module, name, self._make(name))
+
+    def _make(self, name):
+        def f(*a, **kw):
+            if name == "plot":
+                x, y = np.asarray(a[0], float), np.asarray(a[1], float)
+                self.calls.append(["plot", str(kw.get("label")), int(x.size), float(x[0]), float(x[-1]), float(y[0]), float(y[-1])])
+            elif name in ("title", "xlabel", "ylabel"):
+                self.calls.append([name, str(a[0])])
+            else:
+                self.calls.append([name])
+        return f
+
+
+def synthetic_packs():
+    """Result dictionaries with the reference's schema (pbHomoReactor.py:2991-3007, :3664-3696) and made-up numbers."""
+    xs = np.linspace(0, 1, 5)
+    ys = np.arange(25, dtype=float).reshape(5, 5)/7.0
+    steady = [{"modelId": "N1", "processType": "non-iso-thermal", "successStatus": True, "computation-time": 0.123,
+               "dataShape": xs.shape, "labelList": ["A", "B", "C", "Pressure", "Temperature"], "indexList": [3, 3, 4],
+               "dataTime": [], "dataXs": xs, "dataYs": ys}]
+    steady_iso = [dict(steady[0], processType="iso-thermal", labelList=["A", "B", "C", "Pressure"], dataYs=ys[:4])]
+    dyn = {"computation-time": 4.5, "dataPack": [
+        {"modelId": "N2", "processType": "non-iso-thermal", "successStatus": True, "labelList": ["A", "B", "C", "Temperature"],
+         "indexList": [3, 4, 3], "dataTime": 0.1*(i + 1), "dataXs": xs, "dataYs": ys[:4] + i} for i in range(6)]}
+    return steady, steady_iso, dyn
+
+
+def part_plots():
+    """What the reference's plot hooks draw (solResultAnalysis.py:307-459) for synthetic result dictionaries ->
+    tests/golden/plot_calls_reference.json (compared call by call with rmt_app_b200/plotting.py)."""
+    import json
+    load_reference()
+    import PyREMOT.solvers.solResultAnalysis as SRA
+    import types
+    import PyREMOT.library.plot as PL
+    rec = PlotRecorder()
+    PL.plt = types.SimpleNamespace()              # the symbol plots2D draws through (library/plot.py:7)
+    rec.install(PL.plt)
+    steady, steady_iso, dyn = synthetic_packs()
+    out = {}
+    SRA.plotResultsSteadyState(steady); out["steady"] = rec.calls; rec.calls = []
+    SRA.plotResultsSteadyState(steady_iso); out["steady_iso"] = rec.calls; rec.calls = []
+    for seed in (7, 8):
+        np.random.seed(seed)
+        SRA.plotResultsDynamic(dyn, 6); out["dynamic_seed%d" % seed] = rec.calls; rec.calls = []
+    with open(os.path.join(HERE, "plot_calls_reference.json"), "w") as f:
+        json.dump(out, f, indent=0)
+    print({k: len(v) for k, v in out.items()})
+
+
 if __name__ == "__main__":
     for part in sys.argv[1:]:
         if part == "n1":
@@ -424,6 +483,8 @@ if __name__ == "__main__":
             part_n2rhs_iso()
         elif part == "props":
             part_props()
+        elif part == "plots":
+            part_plots()
         elif part == "n2rhs":
             part_n2rhs()
         elif part.startswith("n2sol_"):

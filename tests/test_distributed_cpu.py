@@ -79,3 +79,71 @@ def test_single_process_passthrough():
     assert ensemble.reduce_objective(3.0, 1.0, 5) == (3.0, 1.0, 5)
     t = torch.arange(6.0).view(2, 3)
     assert ensemble.all_gather_rows(t, 3) is t
+
+
+def _pack_worker(rank, world, port, B, nrows, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(1)
+        rows = rng.normal(size=(nrows, B))
+        status = rng.integers(0, 3, B).astype(np.int32)
+        obj = np.abs(rows[-1])
+        first = min(2, B - 1)
+        obj[[first, B - 1]] = 0.0                          # tie on the minimum: the smallest global index wins
+        rows[-1] = obj
+        lay = ensemble.PackLayout(B, world, nrows)
+        lo, hi = ensemble.partition(B, world, rank)
+        buf = torch.full((lay.length,), 7.0, dtype=torch.float64)          # stale content must not leak
+        r, st, tail = lay.views(buf, rank)
+        assert r.shape == (nrows, hi - lo) and st.shape == (hi - lo,) and tail.shape == (4,)
+        r.copy_(torch.from_numpy(rows[:, lo:hi].copy()))
+        st.copy_(torch.from_numpy(status[lo:hi].copy()))
+        loc = obj[lo:hi]
+        if hi > lo:
+            tail.copy_(torch.tensor([loc.sum(), loc.min(), float(lo + loc.argmin()), float((status[lo:hi] != 0).sum())],
+                                    dtype=torch.float64))
+        else:
+            tail.copy_(torch.tensor([0.0, float("inf"), -1.0, 0.0], dtype=torch.float64))
+        g = ensemble.all_gather_packed(buf, world)                         # the ONE collective
+        assert tuple(g.shape) == (world, lay.length)
+        full, fst, tails = lay.unpack(g.numpy())
+        s, mn, am, bad = ensemble.fold_tails(tails)
+        ok = (np.array_equal(full, rows) and np.array_equal(fst, status) and abs(s - obj.sum()) < 1e-9
+              and mn == 0.0 and am == first and bad == int((status != 0).sum()))
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,B,nrows", [(2, 11, 9), (3, 64, 3), (3, 2, 9)])
+def test_packed_single_collective_under_gloo(world, B, nrows):
+    """The cross-GPU step of a sharded ensemble: every rank's outlets / objectives / status / reduction tail in ONE
+    buffer, ONE all-gather, unpacked on the host — uneven shards, odd shard sizes (int32 status packing) and a rank
+    without any reactor (B < world)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_pack_worker, args=(r, world, port, B, nrows, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(r for r, _ in res) == list(range(world))
+    assert all(ok for _, ok in res), res
+
+
+def test_pack_layout_single_rank_and_tail_folding():
+    lay = ensemble.PackLayout(5, 1, 2)
+    assert lay.sizes == [5] and lay.length == 2*5 + 3 + 4
+    buf = torch.zeros(lay.length, dtype=torch.float64)
+    r, st, tail = lay.views(buf, 0)
+    r.copy_(torch.arange(10.0).view(2, 5)); st.copy_(torch.tensor([0, 1, 0, 2, 0], dtype=torch.int32))
+    tail.copy_(torch.tensor([3.0, 0.5, 4.0, 2.0], dtype=torch.float64))
+    full, fst, tails = lay.unpack(ensemble.all_gather_packed(buf, 1).numpy())
+    np.testing.assert_array_equal(full, np.arange(10.0).reshape(2, 5))
+    np.testing.assert_array_equal(fst, [0, 1, 0, 2, 0])
+    assert ensemble.fold_tails(tails) == (3.0, 0.5, 4, 2)
+    assert ensemble.fold_tails([[0.0, np.inf, -1.0, 0.0], [2.0, 1.0, 9.0, 1.0], [2.5, 1.0, 7.0, 0.0]]) == (4.5, 1.0, 7, 1)

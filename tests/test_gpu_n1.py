@@ -429,3 +429,31 @@ def test_irreversible_reaction_at_complete_conversion(reduced):
         assert (got[:3] >= -1e-9).all()                           # interpolated points: zero within the tolerance
         assert np.max(np.abs(got[1:] - want[1:])/np.abs(want[1:])) < bar
         assert np.max(np.abs(got[0] - want[0])) < bar             # the vanishing reactant: absolute (mole fraction)
+
+
+def test_exact_math_option_gives_ieee_special_values():
+    """the branch-free device math trades IEEE special values for speed (exp saturates at e^708 instead of
+    overflowing to Inf, x * rcp(Inf) is NaN instead of 0).  Kinetics that rely on them — here a rate switched off by an
+    overflowing np.exp in the denominator, which NumPy evaluates to exactly 0 — fail LOUDLY in the default build (status
+    3, NaN outputs) and integrate like the reference with solver-config["exact-math"] = True (libdevice + IEEE division)."""
+    eng = _engine()
+
+    def make(exact):
+        mi = cases.ch4_input("N1", "iso-thermal")
+        mi["reaction-rates"] = {"VARS": {"k0": 0.0072*1e-1, "C_CH4": lambda x: x['SpCoi'][0], "y": lambda x: x['MoFri'][0]},
+                                "RATES": {"r1": lambda x: x['k0']*(x['C_CH4']**2)/(1 + np.exp(900.0*x['y']))**3}}
+        mi["solver-config"] = dict(mi["solver-config"], **({"exact-math": True} if exact else {}))
+        return mi
+    fast = eng.compile_model(make(False))
+    exact = eng.compile_model(make(True))
+    assert exact is not fast and exact.exact_math and exact.key() != fast.key()
+    r = eng.n1_solve_ensemble(fast, make(False), None, 1)
+    assert r.status[0] in (2, 3) and np.isnan(r.out).all()      # every step is rejected on NaN: step underflow or the NaN counter
+    r = eng.n1_solve_ensemble(exact, make(True), None, 1, **TIGHT)
+    assert r.status[0] == 0
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = O.N1Oracle(make(True)).pack(O.N1Oracle(make(True)).solve(method="LSODA", rtol=1e-11, atol=1e-13))[0]["dataYs"][:, -1]
+    np.testing.assert_allclose(r.out[0, :, 0], want, rtol=1e-9)
+    np.testing.assert_allclose(r.out[0, :3, 0], [0.9, 0.05, 0.05], rtol=1e-4)          # no reaction: the feed composition

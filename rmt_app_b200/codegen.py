@@ -318,15 +318,15 @@ def generate_model_header(spec, tableau="rodas4", reduced=None, lanes=1):
     for j in range(nr):
         A("    R[%d] = %s;" % (j, next(it)))
     for j in range(nr):
-        A("    dRdT[%d] = %s;" % (j, next(it)))
+        A("    dRdT[%d] = RMT_DERIV(%s);" % (j, next(it)))
     for j in range(nr):
-        A("    dRdP[%d] = %s;" % (j, next(it)))
+        A("    dRdP[%d] = RMT_DERIV(%s);" % (j, next(it)))
     for i in range(nc):
         for j in range(nr):
-            A("    dRdy[%d][%d] = %s;" % (j, i, next(it)))
+            A("    dRdy[%d][%d] = RMT_DERIV(%s);" % (j, i, next(it)))
     for i in range(nc):
         for j in range(nr):
-            A("    dRdC[%d][%d] = %s;" % (j, i, next(it)))
+            A("    dRdC[%d][%d] = RMT_DERIV(%s);" % (j, i, next(it)))
     A("}")
     A("")
 

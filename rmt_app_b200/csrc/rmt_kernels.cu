@@ -257,6 +257,17 @@ __device__ __forceinline__ double rmt_powc(const double x, const double a)
 #define RMT_LOG10(x) rmt_log10(x)
 #define RMT_SQRT(x) rmt_sqrt(x)
 
+// Partial derivatives of the traced rates.  With IEEE special values (RMT_EXACT_MATH) a saturated factor — exp() overflowed
+// to Inf in a denominator, so the rate is exactly 0 like in NumPy — makes the SYMBOLIC derivative Inf/Inf or 0*Inf = NaN
+// although the function is flat there; the reference's integrators difference the RHS numerically and see slope 0.  The
+// exact-math build therefore takes a NaN partial as 0 (a NaN rate itself still rejects the step and fails loudly).
+#if RMT_EXACT_MATH
+#define RMT_DERIV(x) rmt_nan_to_zero(x)
+__device__ __forceinline__ double rmt_nan_to_zero(const double v) { return v == v ? v : 0.0; }
+#else
+#define RMT_DERIV(x) (x)
+#endif
+
 // full-mantissa literals of the generated kinetics: constant-bank operands (1) or instruction immediates (0)
 #ifndef RMT_USE_CBANK
 #define RMT_USE_CBANK 1

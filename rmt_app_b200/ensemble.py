@@ -72,6 +72,38 @@ class PackLayout:
         st = buf[self.nrows*Br:self.nrows*Br + (Br + 1)//2].view(torch.int32)[:Br]
         return rows, st, buf[self.length - self.TAIL:]
 
+    def unpack_device(self, gathered, ws, transpose=True):
+        """Device-side form of `unpack` for large gathers: the per-rank blocks are scattered (and transposed to
+        instance-major [B, nrows] when `transpose`) by the GPU, and rows, status and tails travel to the host in
+        ONE copy each into pinned workspace memory — instead of a pageable D2H of the packed buffer followed by two
+        host passes over it (measured on 2^23 reactors: 0.63 s -> see bench strong_scaling).  Returns host numpy
+        views (valid until the next call with the same workspace): rows [B, nrows] (or [nrows, B]), status [B],
+        tails [world, 4]."""
+        import torch
+        dev = gathered.device
+        g = gathered.view(self.world, self.length)
+        shape = (self.B, self.nrows) if transpose else (self.nrows, self.B)
+        d_rows = ws.get("d_unpack_rows", shape, torch.float64, device=dev)
+        d_st = ws.get("d_unpack_status", (self.B,), torch.int32, device=dev)
+        for r in range(self.world):
+            Br, lo = self.sizes[r], self.starts[r]
+            if Br == 0:
+                continue
+            blk = g[r, :self.nrows*Br].view(self.nrows, Br)
+            if transpose:
+                d_rows[lo:lo + Br].copy_(blk.t())
+            else:
+                d_rows[:, lo:lo + Br].copy_(blk)
+            d_st[lo:lo + Br].copy_(g[r, self.nrows*Br:self.nrows*Br + (Br + 1)//2].view(torch.int32)[:Br])
+        h_rows = ws.get("h_unpack_rows", shape, torch.float64, pinned=True)
+        h_st = ws.get("h_unpack_status", (self.B,), torch.int32, pinned=True)
+        h_tail = ws.get("h_unpack_tails", (self.world, self.TAIL), torch.float64, pinned=True)
+        h_rows.copy_(d_rows, non_blocking=True)
+        h_st.copy_(d_st, non_blocking=True)
+        h_tail.copy_(g[:, self.length - self.TAIL:], non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return h_rows.numpy(), h_st.numpy(), h_tail.numpy().copy()
+
     def unpack(self, gathered):
         """gathered [world, length] (host numpy float64) -> rows [nrows, B], status [B] int32, tails [world, 4]."""
         g = np.ascontiguousarray(gathered).reshape(self.world, self.length)
@@ -215,12 +247,20 @@ def rmtExeBatchSharded(modelInput, sweep, B=None, *, rtol=None, atol=None, objec
             g = all_gather_packed(pack, world, group, comm, stream)                        # take part in the collective;
             tails = g[:, lay.length - lay.TAIL:].cpu().numpy()                             # only the tails go to this host
         elif gather:
-            g = all_gather_packed(pack, world, group, comm, stream).cpu().numpy()          # the one D2H
-            full, st, tails = lay.unpack(g)
-            out["dataYs"] = np.ascontiguousarray(full[:n].T)
-            out["status"] = st
-            if with_obj:
-                out["objective"] = full[n].copy()
+            g = all_gather_packed(pack, world, group, comm, stream)
+            if g.is_cuda:
+                # scatter + transpose on the device, one D2H into pinned memory (views of the workspace)
+                full, st, tails = lay.unpack_device(g, ws, transpose=True)                 # [B, n (+1)]
+                out["dataYs"] = full[:, :n]
+                out["status"] = st
+                if with_obj:
+                    out["objective"] = full[:, n]
+            else:                                                                          # CPU tensors (gloo tests)
+                full, st, tails = lay.unpack(g.numpy())
+                out["dataYs"] = np.ascontiguousarray(full[:n].T)
+                out["status"] = st
+                if with_obj:
+                    out["objective"] = full[n].copy()
         else:
             tails = all_gather_packed(tail, world, group, comm, stream).cpu().numpy()
         s, mn, am, bad = fold_tails(tails)

@@ -12,8 +12,9 @@ if os.environ.get("SORT"):      # experiment: reactors ordered by a stiffness pr
     key = {"T": sw["temperature"], "P": sw["pressure"], "TP": sw["temperature"] + 1e-5*sw["pressure"]}[os.environ["SORT"]]
     o = np.argsort(key); sw = {k: v[o] for k, v in sw.items()}
 base["solver-config"]["method"] = os.environ.get("METHOD", "rodas4")
-CTRL = [float(v) for v in os.environ["CTRL"].split(",")] if os.environ.get("CTRL") else None
 cm = engine.compile_model(base)
+# step-size controller: the tableau's tuned setting (what rmtExeBatch and bench.py use) unless CTRL overrides it
+CTRL = [float(v) for v in os.environ["CTRL"].split(",")] if os.environ.get("CTRL") else engine.METHOD_CTRL.get(cm.method)
 capi.init(0)
 ws = engine.Workspace()
 h_rows, n_rows, row_map = engine.sweep_rows_into(cm.spec, sw, B, ws)

@@ -116,6 +116,10 @@ struct Module {
     CUfunction f_n2_rhs = nullptr, f_n2_solve = nullptr, f_reduce = nullptr, f_peak = nullptr, f_probe = nullptr;
     int solve_blocks_per_sm = 0;
     size_t solve_smem = 0;
+    // stage-pipelined N2 module (info.lanes == 0), read from its rmt_n2_meta kernel: reactors per block, work doubles per
+    // block and node, work doubles per block
+    int wf_reactors = 0;
+    long long wf_work_per_node = 0, wf_work_fixed = 0;
     std::mutex mu;             // guards the scratch ring
     std::mutex host_mu;        // serialises the synchronous host-buffer entry points (they share ws / pipe_ws)
     Scratch ring[8];
@@ -482,7 +486,8 @@ int rmt_module_load(const void* cubin, size_t size, rmt_module_t* module_out)
     I.stages = mv[7]; I.block = mv[8]; I.iso = mv[9];
     I.flops_rhs_alg = mv[10]; I.flops_rhs_wt = mv[11]; I.flops_jac_alg = mv[12]; I.flops_jac_wt = mv[13];
     I.m = mv[14] > 0 ? mv[14] : mv[1];
-    I.lanes = mv[15] > 0 ? mv[15] : 1;
+    // dynamic models: threads per reactor; 0 = the stage-pipelined mapping (32 reactors x (stages + 1) role warps per block)
+    I.lanes = (mv[0] == 2 || mv[0] == 9) ? std::max(mv[15], 0) : 1;
     auto get = [&](const char* name) { CUfunction f = nullptr; drv.p_cuModuleGetFunction(&f, M->mod, name); return f; };
     M->f_setup = get("rmt_setup");
     M->f_n1_rhs = get("rmt_n1_rhs");
@@ -507,6 +512,22 @@ int rmt_module_load(const void* cubin, size_t size, rmt_module_t* module_out)
         // and, with several lanes per reactor, the sweeps' hand-over records [block/lanes][stages + 1][2 n + 4]
         M->solve_smem = I.model == 2 ? 8*((size_t)(I.n + 1)*I.n + 3*(size_t)I.n + 1)*((size_t)I.block + 1) : 0;
         if (I.lanes > 1) M->solve_smem += 8*(size_t)(I.block/I.lanes)*(I.stages + 1)*(2*(size_t)I.n + 4);
+        if (I.lanes == 0) {
+            // stage pipeline: the kernel's own layout constants (WF_SMEM_BYTES, reactors per block, work rows)
+            CUfunction fm2 = get("rmt_n2_meta");
+            if (!fm2) { drv.p_cuModuleUnload(M->mod); delete M; return fail("stage-pipelined module lacks rmt_n2_meta"); }
+            int32_t wv[8] = {0};
+            CUdeviceptr dm = 0;
+            r = drv.p_cuMemAlloc(&dm, sizeof wv);
+            if (r == CUDA_SUCCESS) {
+                void* params[] = {&dm};
+                r = drv.p_cuLaunchKernel(fm2, 1, 1, 1, 32, 1, 1, 0, nullptr, params, nullptr);
+                if (r == CUDA_SUCCESS) r = drv.p_cuMemcpyDtoH(wv, dm, sizeof wv);
+                drv.p_cuMemFree(dm);
+            }
+            if (r != CUDA_SUCCESS || wv[1] <= 0) { drv.p_cuModuleUnload(M->mod); delete M; return cu_fail(r, "rmt_n2_meta"); }
+            M->solve_smem = (size_t)wv[0]; M->wf_reactors = wv[1]; M->wf_work_per_node = wv[2]; M->wf_work_fixed = wv[3];
+        }
         if (M->solve_smem) CU(cuFuncSetAttribute(fs, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)M->solve_smem));
         CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&M->solve_blocks_per_sm, fs, I.block, M->solve_smem));
         if (M->solve_blocks_per_sm < 1) { drv.p_cuModuleUnload(M->mod); delete M; return fail("dynamic-model integrator does not fit on an SM (smem %zu B)", M->solve_smem); }
@@ -769,6 +790,11 @@ int rmt_n2_rhs(rmt_module_t m, int64_t B, int32_t zNo, const double* d_consts, c
 static int64_t n2_slots(const Module* M, int64_t B)
 {
     const int block = M->info.block;
+    if (M->info.lanes == 0) {             // stage pipeline: a block serves wf_reactors reactors at a time
+        long long wantb = (B + M->wf_reactors - 1)/M->wf_reactors;
+        long long capb = (long long)g_sm_count*std::max(M->solve_blocks_per_sm, 1);
+        return (int64_t)std::max<long long>(1, std::min(wantb, capb))*block;
+    }
     long long want = (B*M->info.lanes + block - 1)/block;
     long long cap = (long long)g_sm_count*std::max(M->solve_blocks_per_sm, 1);
     return (int64_t)std::max<long long>(1, std::min(want, cap))*block;
@@ -783,6 +809,8 @@ int64_t rmt_n2_work_doubles(rmt_module_t m, int64_t B, int32_t zNo)
     // per node and integrator thread: y_n, y_{n+1}, s stage vectors, W_kk^{-1} (n x n), upwind / pressure
     // coupling vectors (3n), d E/d P
     // (M9 adds the velocity march: two more coupling vectors, one more gradient vector, four scalars)
+    if (M->info.lanes == 0)               // stage pipeline, per block: y_n / y_{n+1} and the ring of stage vectors (rmt_n2_meta)
+        return (n2_slots(M, B)/M->info.block)*(M->wf_work_per_node*zNo + M->wf_work_fixed);
     const int64_t rows = n*(5 + s + n) + 1 + (M->info.model == 9 ? 3*n + 4 : 0);
     const int64_t groups = (zNo + M->info.lanes - 1)/M->info.lanes;      // node groups, one node per lane
     // the two state rows exist per node group; the rest is scratch of the group being processed

@@ -289,6 +289,32 @@ __device__ __forceinline__ double rmt_root_order(const double x, const double in
 #endif
 }
 
+// max(x, 1e-30) (the reference's concentration clamp, pbHomoReactor.py:3897-3904) and its indicator on the integer pipe:
+// fmax of doubles is a DSETP + NaN test + selects (~10 instructions, 12 clamps per node evaluation — 7 % of the
+// stage-pipelined N2 kernel's instructions); comparing the HIGH WORD alone is one ISETP + two selects.  Values whose high
+// word equals that of 1e-30 (|x/1e-30 - 1| < 2^-20) count as "above" and pass unchanged, negative numbers and zero give
+// 1e-30, a NaN stays a NaN (the step is then rejected by the error test).
+#define RMT_EPS_HI 0x39B4484B                       // high word of 1e-30 = 0x39B4484BFEEBC2A0
+#ifndef RMT_FP_CLAMP
+#define RMT_FP_CLAMP 0
+#endif
+__device__ __forceinline__ bool rmt_above_eps(const double x)
+{
+#if RMT_EXACT_MATH || RMT_FP_CLAMP
+    return x > 1e-30;
+#else
+    return __double2hiint(x) >= RMT_EPS_HI;
+#endif
+}
+__device__ __forceinline__ double rmt_clamp_eps(const double x)
+{
+#if RMT_EXACT_MATH || RMT_FP_CLAMP
+    return fmax(x, 1e-30);
+#else
+    return rmt_above_eps(x) ? x : 1e-30;
+#endif
+}
+
 #define RMT_R_CONST 8.314472            // core/constants.py:8
 #define RMT_TREF 298.15                 // core/constants.py:17-23
 #define RMT_PI 3.141592653589793        // core/constants.py:14
@@ -336,9 +362,15 @@ __device__ __forceinline__ double rmt_root_order(const double x, const double in
 #ifndef RMT_BLOCK
 #define RMT_BLOCK 256
 #endif
-// N2 integrator: lanes per reactor (nodes evaluated in parallel), see rmt_n2_solve
+// N2 integrator: lanes per reactor (nodes evaluated in parallel), see rmt_n2_solve; 0 = the stage-pipelined
+// mapping (one thread per reactor and Rosenbrock stage, see "stage pipeline" below)
 #ifndef RMT_N2_G
 #define RMT_N2_G 1
+#endif
+#if RMT_N2_G == 0
+#define RMT_N2_WF 1
+#else
+#define RMT_N2_WF 0
 #endif
 // warps of a block are kept in (loose) lockstep so that they share instruction-cache lines:
 // 0 = free running, 1 = one block barrier per step attempt, 2 = one per Rosenbrock stage
@@ -394,7 +426,7 @@ extern "C" __global__ void rmt_meta(int* out)
     out[14] = 0;
 #endif
 #if defined(RMT_MODEL_N2) || defined(RMT_MODEL_M9)
-    out[15] = RMT_N2_G;
+    out[15] = RMT_N2_G;                     // 0: stage-pipelined mapping (block = 32 reactors x (stages + 1) roles)
 #else
     out[15] = 1;
 #endif
@@ -1798,7 +1830,7 @@ __device__ __forceinline__ void n2_node(const double (&u)[RMT_N], const double (
 {
     double C[RMT_NC];
 #pragma unroll
-    for (int i = 0; i < RMT_NC; ++i) C[i] = fmax(u[i], RMT_EPS_CONST)*h.Cmax;      // :3897-3904
+    for (int i = 0; i < RMT_NC; ++i) C[i] = rmt_clamp_eps(u[i])*h.Cmax;      // :3897-3904
 #if RMT_ISO
     const double T = 0.0*h.Tf + h.Tf;
 #else
@@ -1812,7 +1844,7 @@ __device__ __forceinline__ void n2_node(const double (&u)[RMT_N], const double (
     // mass balances (:4082-4099): F1*(-v/vf*(Ci - Ci_b)/dz + ri/GaMaCoTe0), v/vf == 1
 #pragma unroll
     for (int i = 0; i < RMT_NC; ++i) {
-        const double cb = inlet ? h.iv[i] : fmax(ub[i], RMT_EPS_CONST);
+        const double cb = inlet ? h.iv[i] : rmt_clamp_eps(ub[i]);
         f[i] = h.F1*(-1*((u[i] - cb)*invdz) + p.r[i]*h.invGm);
     }
 #if !RMT_ISO
@@ -1848,7 +1880,7 @@ __device__ __forceinline__ void n2_node(const double (&u)[RMT_N], const double (
             double dlnrho, dR[RMT_NR];
             if (isC) {
                 const int c = col < RMT_NC ? col : 0;
-                const double sc = (u[c] > RMT_EPS_CONST) ? h.Cmax : 0.0;    // d max(u, eps)/du
+                const double sc = rmt_above_eps(u[c]) ? h.Cmax : 0.0;    // d max(u, eps)/du
                 dlnrho = sc*(1e-3*RMT_cMW[c] - p.MWm)*invS*invMW;
 #pragma unroll
                 for (int j = 0; j < RMT_NR; ++j) {
@@ -1887,7 +1919,7 @@ __device__ __forceinline__ void n2_node(const double (&u)[RMT_N], const double (
             double dCp = 0.0, dQm = 0.0;
             if (isC) {
                 const int c = col < RMT_NC ? col : 0;
-                dCp = ((u[c] > RMT_EPS_CONST) ? h.Cmax : 0.0)*(p.cpm[c] - p.Cp)*invS;
+                dCp = (rmt_above_eps(u[c]) ? h.Cmax : 0.0)*(p.cpm[c] - p.Cp)*invS;
             } else if (!isP) {
                 dCp = h.Tf*pj.dCpdT;
 #pragma unroll
@@ -1903,7 +1935,7 @@ __device__ __forceinline__ void n2_node(const double (&u)[RMT_N], const double (
         }
         // upwind coupling (diagonal)
 #pragma unroll
-        for (int i = 0; i < RMT_NC; ++i) nj.L[i] = inlet ? 0.0 : ((ub[i] > RMT_EPS_CONST) ? h.F1*invdz : 0.0);
+        for (int i = 0; i < RMT_NC; ++i) nj.L[i] = inlet ? 0.0 : (rmt_above_eps(ub[i]) ? h.F1*invdz : 0.0);
 #if !RMT_ISO
         nj.L[RMT_ITN] = inlet ? 0.0 : h.invZv*invdz;
 #endif
@@ -1925,7 +1957,7 @@ __device__ __forceinline__ void m9_node(const double (&u)[RMT_N], const double (
 {
     double C[RMT_NC];
 #pragma unroll
-    for (int i = 0; i < RMT_NC; ++i) C[i] = fmax(u[i], RMT_EPS_CONST);            // :2487-2491
+    for (int i = 0; i < RMT_NC; ++i) C[i] = rmt_clamp_eps(u[i]);            // :2487-2491
     const double T = u[RMT_ITN];
     Point p; PointJac pj;
     rmt_point<JAC>(C, T, P, h, p, pj);
@@ -1946,7 +1978,7 @@ __device__ __forceinline__ void m9_node(const double (&u)[RMT_N], const double (
     double cb[RMT_NC];
 #pragma unroll
     for (int i = 0; i < RMT_NC; ++i) {
-        cb[i] = inlet ? h.iv[i] : fmax(ub[i], RMT_EPS_CONST);
+        cb[i] = inlet ? h.iv[i] : rmt_clamp_eps(ub[i]);
         f[i] = h.F1*(-v*((u[i] - cb[i])*invdz) - u[i]*V + p.r[i]);                 // :2626-2640 (centre value un-clamped)
     }
     const double SCp = p.S*p.Cp;
@@ -1976,7 +2008,7 @@ __device__ __forceinline__ void m9_node(const double (&u)[RMT_N], const double (
 #pragma unroll
             for (int j = 0; j < RMT_NR; ++j) dR[j] = 0.0;
             if (isC) {
-                const double sc = (u[c] > RMT_EPS_CONST) ? 1.0 : 0.0;             // d max(u, eps)/du
+                const double sc = rmt_above_eps(u[c]) ? 1.0 : 0.0;             // d max(u, eps)/du
                 dS = sc;
                 dE = -1*h.ergC*(v*v)*(sc*1e-3*RMT_cMW[c]);
                 dSCp = sc*p.cpm[c];
@@ -2042,7 +2074,7 @@ __device__ __forceinline__ void m9_node(const double (&u)[RMT_N], const double (
         nj.eVb = dVb;
 #pragma unroll
         for (int i = 0; i < RMT_NC; ++i) {
-            nj.L[i] = inlet ? 0.0 : ((ub[i] > RMT_EPS_CONST) ? h.F1*(v*invdz) : 0.0);
+            nj.L[i] = inlet ? 0.0 : (rmt_above_eps(ub[i]) ? h.F1*(v*invdz) : 0.0);
             nj.Lt[i] = h.F1*(-u[i]*dVb);
         }
         nj.L[RMT_ITN] = inlet ? 0.0 : (Svc*invdz)*invD;
@@ -2176,15 +2208,16 @@ __device__ __forceinline__ int n2_out_rows(const int mode) { return mode == 2 ? 
 // one node per lane; what is sequential in the node index — the Ergun pressure march and the block forward
 // substitution — is handed from lane to lane with shuffles, in node order, so the arithmetic (and every
 // result bit) is the same for every G.
-static_assert(RMT_N2_G >= 1 && RMT_N2_G <= 32 && (RMT_N2_G & (RMT_N2_G - 1)) == 0, "RMT_N2_G: power of two <= 32");
+static_assert(RMT_N2_G >= 0 && RMT_N2_G <= 32 && (RMT_N2_G & (RMT_N2_G - 1)) == 0, "RMT_N2_G: 0 or a power of two <= 32");
 static_assert(RMT_BLOCK % 32 == 0, "block size");
+#if !RMT_N2_WF
 
 // mixture molar mass [kg/mol] of a node state — the same arithmetic as rmt_point
 __device__ __forceinline__ double n2_mw(const double (&u)[RMT_N], const Hot& h)
 {
     double C[RMT_NC], S = 0.0;
 #pragma unroll
-    for (int i = 0; i < RMT_NC; ++i) { C[i] = fmax(u[i], RMT_EPS_CONST)*h.Cmax; S += C[i]; }
+    for (int i = 0; i < RMT_NC; ++i) { C[i] = rmt_clamp_eps(u[i])*h.Cmax; S += C[i]; }
     const double invS = rmt_rcp(S);
     double mw = 0.0;
 #pragma unroll
@@ -2884,6 +2917,518 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
 #undef WS
 #undef SH
 }
+#endif  // !RMT_N2_WF
+
+#if RMT_N2_WF
+// ---------------------------------------------------------------------------------
+// N2 integrator, stage pipeline.  Same method, same arithmetic per node as above; different mapping.
+//
+// The forward substitution over the nodes is sequential (upwind block + linearised pressure), and so are the marches
+// of the stage arguments: spreading the NODES of a reactor over lanes makes every one of those chains a lane-to-lane
+// hand-over (shuffles, shared-memory transposes, explicit inverse blocks to keep the hand-over short — 2/3 of the
+// instructions of the lanes kernel, profiles/r02_n2_lanes_line_profile.txt).  Here the parallelism is over the
+// STAGES instead.  A block serves 32*WF_RW reactors, one per lane of WF_RW "reactor warps", with WF_ROLES warps
+// per reactor warp, one role each —
+//   role 0   "JA": f(y_n) and the Jacobian blocks of node k, written as W_kk = I/(h gamma) - A into a ring slot
+//   role r   (r >= 1) the WF_SPR stages (r-1)*WF_SPR + 1 ... r*WF_SPR of node k, one after the other: stage argument,
+//            f, right-hand side, LU solve.  Role 1 first factorises W_kk in the ring slot (partial pivoting; its
+//            first stage takes f(y_n) from JA); the last role forms y_{n+1} and the error norm.
+// — all walking the nodes in flow direction, skewed by one node per role: at block step tau role r works on node
+// tau - r.  Every chain (upwind stage state, K of the node before, marched and linearised pressure) is then private
+// to ONE thread and lives in its registers; a solve is a plain LU solve by the thread that needs it.  What crosses
+// roles goes through memory one block step later: the factorised block, its pivot order and the coupling vectors
+// through a shared-memory ring of WF_DEPTH node slots per reactor, the stage vectors K_j[k] through a ring of global
+// work rows (L1/L2 resident), y_n / y_{n+1} through the two state rows.  One block barrier per step; no shuffles,
+// no redundant arithmetic.  The warps of one role (WF_RW of them) run the same instructions at the same time and
+// share the fetched instruction lines.
+//
+// Control: the per-reactor integration state (t, h, counters, controller memory) lives in the registers of the LAST
+// role's thread of that reactor's lane, which is the one that knows the error norm; it publishes what the other roles
+// need for the next attempt (live / fresh / which state row is y_n / step size / new instance id / pending output)
+// in a small shared-memory record.  A fresh reactor's first attempt is the norm pass for the starting step (JA only).
+// Lanes pick up a new reactor from the global queue as soon as theirs is done.
+// ---------------------------------------------------------------------------------
+#if defined(RMT_MODEL_M9)
+#error "the stage pipeline covers N2; M9 uses the lanes kernel with RMT_N2_G = 1"
+#endif
+#ifndef WF_SPR
+#define WF_SPR 2                                   // stages per role
+#endif
+#define WF_ROLES (1 + RMT_ROS_S/WF_SPR)
+#define WF_RW (RMT_BLOCK/(32*WF_ROLES))            // reactor warps per block
+#define WF_NR (32*WF_RW)                           // reactors per block
+#define WF_DEPTH (WF_ROLES <= 4 ? 4 : 8)           // ring slots per reactor: > WF_ROLES - 1, a power of two
+static_assert(RMT_ROS_S % WF_SPR == 0, "stage pipeline: stages per role must divide the stage count");
+static_assert(RMT_BLOCK == 32*WF_ROLES*WF_RW && WF_RW >= 1, "stage pipeline: block = 32 reactors x roles x reactor warps");
+static_assert(WF_DEPTH >= WF_ROLES && (WF_DEPTH & (WF_DEPTH - 1)) == 0, "ring depth");
+static_assert(!RMT_ROS_REUSE, "stage pipeline: every stage after the first evaluates f at its own argument");
+static_assert(RMT_N <= 8, "pivot order (3 bits per row, bits 0..23) and the upwind mask (bits 24..31) share one 32-bit word");
+// rows of a ring slot (per reactor): W_kk -> LU (n x n), g_k, dz e_k, 1 + dz ep_k
+enum { E_W = 0, E_G = RMT_N*RMT_N, E_E = E_G + RMT_N, E_EPF = E_E + RMT_N, E_ROWS = E_EPF + 1 };
+// control record (doubles) per reactor lane
+enum { C_HH = 0, C_D0, C_D1, C_ROWS };
+enum { F_LIVE = 1, F_FRESH = 2, F_CUR = 4, F_OUT = 8, F_NEW = 16, F_OUTBUF = 32 };
+// ring of stage vectors K_j[k], j < S - 1: [RW][DEPTH][S-1][n][32] doubles — in shared memory when the block's record
+// still fits (WF_KSMEM), else in the block's global work rows
+#define WF_KRING_DOUBLES (WF_RW*WF_DEPTH*(RMT_ROS_S - 1)*RMT_N*32)
+#define WF_SMEM_BASE_DOUBLES (WF_RW*WF_DEPTH*E_ROWS*32 + WF_RW*2*RMT_N*32 + C_ROWS*WF_NR + WF_NR)
+#define WF_SMEM_INTS (WF_RW*WF_DEPTH*32 + 2*WF_NR)
+#ifndef WF_KSMEM
+#define WF_KSMEM ((8*(WF_SMEM_BASE_DOUBLES + WF_KRING_DOUBLES) + 4*WF_SMEM_INTS) <= 226*1024)
+#endif
+// shared memory, doubles: ring [RW][DEPTH][E_ROWS][32] | f(y_n) ring [RW][2][n][32] | ctl [C_ROWS][NR] | instance ids [NR]
+// | (K ring); then ints: pivot/mask words [RW][DEPTH][32], flags [NR], out_slab [NR]
+#define WF_SMEM_DOUBLES (WF_SMEM_BASE_DOUBLES + (WF_KSMEM ? WF_KRING_DOUBLES : 0))
+#define WF_SMEM_BYTES (8*WF_SMEM_DOUBLES + 4*WF_SMEM_INTS)
+// global work rows per block (doubles): y [RW][2][zNo][n][32] | (K ring)
+#define WF_WORK_PER_NODE (WF_RW*2*RMT_N*32)
+#define WF_WORK_FIXED (WF_KSMEM ? 0 : WF_KRING_DOUBLES)
+
+extern "C" __global__ void rmt_n2_meta(int* out)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    out[0] = WF_SMEM_BYTES; out[1] = WF_NR; out[2] = WF_WORK_PER_NODE; out[3] = WF_WORK_FIXED; out[4] = WF_ROLES; out[5] = WF_SPR;
+}
+
+// solve (P W = L U) x = b with the factors of a ring slot (row i of the factors is physical row (pw >> 3 i) & 7,
+// reciprocal pivots on the diagonal).  The permuted right-hand side goes through a thread-private column (local memory,
+// L1 resident) — the pivot order differs from lane to lane, so it cannot be a register index.
+__device__ __forceinline__ void wf_solve(const double* __restrict__ slot, const unsigned pw, const double (&b)[RMT_N], double (&x)[RMT_N])
+{
+    double scr[RMT_N];
+#pragma unroll
+    for (int v = 0; v < RMT_N; ++v) scr[v] = b[v];
+    const double* rowp[RMT_N];
+#pragma unroll
+    for (int i = 0; i < RMT_N; ++i) {
+        const int pi = (pw >> (3*i)) & 7;
+        rowp[i] = slot + (E_W + pi*RMT_N)*32;
+        x[i] = scr[pi];
+    }
+#pragma unroll
+    for (int i = 0; i < RMT_N; ++i) {
+        double v = x[i];
+#pragma unroll
+        for (int j = 0; j < i; ++j) v -= rowp[i][j*32]*x[j];
+        x[i] = v;
+    }
+#pragma unroll
+    for (int i = RMT_N - 1; i >= 0; --i) {
+        double v = x[i];
+#pragma unroll
+        for (int j = i + 1; j < RMT_N; ++j) v -= rowp[i][j*32]*x[j];
+        x[i] = v*rowp[i][i*32];
+    }
+}
+
+// y_{n+1} equals the last stage's argument plus its K, and the error estimator is that K (Rodas4, Rodas3)?
+// (measured: the shortcut saves the last role ~0.3 k instructions per node and still makes the kernel 8 % SLOWER — 0.088 vs
+// 0.081 s per full round of 9 472 reactors x 200 nodes — so the generic sums stay the default)
+#ifndef WF_SA
+#define WF_SA 0
+#endif
+__device__ constexpr bool wf_stiffly_accurate()
+{
+    constexpr int S = RMT_ROS_S;
+    if (!WF_SA) return false;
+    if (S < 2) return false;
+    for (int j = 0; j < S - 1; ++j)
+        if (RMT_ROS_M[j] != RMT_ROS_A[S - 1][j] || RMT_ROS_E[j] != 0.0) return false;
+    return RMT_ROS_M[S - 1] == 1.0 && RMT_ROS_E[S - 1] == 1.0;
+}
+
+#ifndef WF_MINBLOCKS
+#define WF_MINBLOCKS 1
+#endif
+extern "C" __global__ void __launch_bounds__(RMT_BLOCK, WF_MINBLOCKS) rmt_n2_solve(const SolveArgsN2 a)
+{
+    extern __shared__ double wf_sh[];
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int wid = threadIdx.x >> 5;
+    const int role = wid/WF_RW, rw = wid - role*WF_RW;
+    const int rl = rw*32 + lane;                                           // reactor slot of the block
+    const int zNo = a.zNo;
+    double* const ring = wf_sh + rw*(WF_DEPTH*E_ROWS*32) + lane;           // [(slot*E_ROWS + row)*32]
+    double* const fring = wf_sh + WF_RW*WF_DEPTH*E_ROWS*32 + rw*(2*RMT_N*32) + lane;      // [((k & 1)*n + v)*32]
+    double* const ctl = wf_sh + WF_RW*WF_DEPTH*E_ROWS*32 + WF_RW*2*RMT_N*32 + rl;        // [row*WF_NR]
+    i64* const c_inst = reinterpret_cast<i64*>(wf_sh + WF_RW*WF_DEPTH*E_ROWS*32 + WF_RW*2*RMT_N*32 + C_ROWS*WF_NR) + rl;
+    int* const ibase = reinterpret_cast<int*>(wf_sh + WF_SMEM_DOUBLES);
+    unsigned* const c_perm = reinterpret_cast<unsigned*>(ibase) + rw*(WF_DEPTH*32) + lane;   // [slot*32]
+    int* const c_flags = ibase + WF_RW*WF_DEPTH*32 + rl;
+    int* const c_oslab = ibase + WF_RW*WF_DEPTH*32 + WF_NR + rl;
+    double* const wy = a.work + (i64)blockIdx.x*((i64)WF_WORK_PER_NODE*zNo + WF_WORK_FIXED) + (i64)rw*((i64)2*zNo*RMT_N*32) + lane;
+    double* const wk = (WF_KSMEM ? wf_sh + WF_SMEM_BASE_DOUBLES
+                                 : a.work + (i64)blockIdx.x*((i64)WF_WORK_PER_NODE*zNo + WF_WORK_FIXED) + (i64)WF_WORK_PER_NODE*zNo)
+                       + (i64)rw*(WF_DEPTH*(RMT_ROS_S - 1)*RMT_N*32) + lane;
+#define YROW(buf, k, v) wy[(((i64)(buf)*zNo + (k))*RMT_N + (v))*32]
+#define KSLOT(k) (wk + ((k) & (WF_DEPTH - 1))*((RMT_ROS_S - 1)*RMT_N*32))     // K_j[k][v] = KSLOT(k)[(j*n + v)*32]
+#define SLOT(k) (ring + ((k) & (WF_DEPTH - 1))*(E_ROWS*32))
+    const double dz = 1.0/(zNo - 1), invdz = 1.0/dz;
+    const double ISAFE = 1.0/a.ctrl[0], FAC1 = a.ctrl[1], FAC2 = 1.0/a.ctrl[2], KAPPA = a.ctrl[3], BETA = a.ctrl[4];
+    const double inv_nz = 1.0/((double)RMT_N*zNo);
+    const bool controller = role == WF_ROLES - 1;
+
+    // every thread of a lane: the reactor it serves
+    i64 inst = -1;
+    Hot h = {};
+    // controller thread only: the integration state of the lane's reactor
+    bool live = false, exhausted = false, fresh = false, last_rejected = false, clipped = false;
+    double t = 0.0, hstep = 0.0, hacc = 0.0, erracc = 1e-2, tend = 0.0, hh = 1.0;
+    int nacc = 0, nrej = 0, nanrej = 0, slab = 0, cur = 0;
+    double errsum = 0.0;
+    bool bad = false;
+
+    while (true) {
+        // ---- [A] controller: result of the attempt just made, refill, step size of the next attempt ----
+        if (controller) {
+            int flags = 0;
+            if (live) {
+                int fin = -1;
+                if (fresh) {
+                    // starting step from ||y0|| / ||f(y0)|| (Hairer-Wanner II.4, first guess), scaled like N1
+                    const double d0 = rmt_sqrt(ctl[C_D0*WF_NR]*inv_nz), d1 = rmt_sqrt(ctl[C_D1*WF_NR]*inv_nz);
+                    const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01*d0*rmt_rcp(d1);
+                    hstep = fmin(a.ctrl[5]*100.0*h0, tend);
+                    fresh = false;
+                } else {
+                    const double invh = rmt_rcp(hh);
+                    double err = rmt_sqrt(errsum*inv_nz);
+                    if (bad || !(err == err)) err = 1e30;
+                    const double errc = fmax(err, 1e-10);
+                    double fac;
+                    if (BETA > 0.0 && nacc > 0) fac = rmt_powc(errc, 1.0/(RMT_ROS_ORDER) - 0.75*BETA)*rmt_powc(erracc, -BETA)*ISAFE;
+                    else fac = rmt_root_order(errc, 1.0/(RMT_ROS_ORDER))*ISAFE;
+                    fac = fmax(FAC2, fmin(FAC1, fac));
+                    double hnew = hh*rmt_rcp(fac);
+                    if (err <= 1.0) {
+                        if (nacc > 0 && BETA <= 0.0) {
+                            double facgus = (hacc*invh)*rmt_root_order(err*err*rmt_rcp(erracc), 1.0/(RMT_ROS_ORDER))*ISAFE;
+                            facgus = fmax(FAC2, fmin(FAC1, facgus));
+                            fac = fmax(fac, facgus);
+                            hnew = hh*rmt_rcp(fac);
+                        }
+                        hacc = hh; erracc = fmax(1e-2, err);
+                        ++nacc; nanrej = 0;
+                        cur ^= 1;
+                        t = clipped ? tend : t + hh;
+                        if (last_rejected) hnew = fmin(hnew, hh);
+                        last_rejected = false;
+                        hstep = clipped ? fmax(hnew, hstep) : hnew;
+                        if (t >= tend) {
+                            // end of a slab: every thread of the lane un-scales and stores its share in phase [C]
+                            flags |= F_OUT | (cur ? F_OUTBUF : 0);
+                            c_oslab[0] = slab;
+                            ++slab;
+                            if (slab >= a.tNo) fin = 0;
+                            else tend = (slab + 1 == a.tNo) ? a.period : a.period*(slab + 1)/a.tNo;
+                        }
+                        if (fin < 0 && nacc + nrej >= a.max_steps) fin = 1;
+                    } else {
+                        ++nrej;
+                        if (err >= 1e29) { ++nanrej; hnew = hh*0.1; }
+                        last_rejected = true;
+                        hstep = hnew;
+                        if (nacc + nrej >= a.max_steps) fin = 1;
+                        else if (hstep < 1e-14*fmax(a.period, 1e-300)) fin = 2;
+                        else if (nanrej > 30) fin = 3;
+                    }
+                }
+                if (fin >= 0) {
+                    a.status[inst] = fin;
+                    if (a.stats) {
+                        a.stats[inst] = nacc; a.stats[a.B + inst] = nrej;
+                        a.stats[2*a.B + inst] = (nacc + nrej)*(RMT_ROS_S - 1); a.stats[3*a.B + inst] = nacc + nrej;
+                    }
+                    if (fin != 0) {
+                        const int rows = n2_out_rows(a.out_mode);
+                        const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+                        for (int sl = slab; sl < a.tNo; ++sl)
+                            for (int r = 0; r < rows; ++r)
+                                for (int k = 0; k < zNo; ++k) a.out[(((i64)sl*rows + r)*zNo + k)*a.B + inst] = qnan;
+                    }
+                    live = false;
+                }
+            }
+            // lanes without a reactor pull one from the queue (one atomic per warp)
+            const bool need = !live && !exhausted;
+            const unsigned m = __ballot_sync(FULL, need);
+            if (m) {
+                unsigned long long base = 0;
+                const int leader = __ffs(m) - 1;
+                if (lane == leader) base = atomicAdd(a.queue, (unsigned long long)__popc(m));
+                base = __shfl_sync(FULL, base, leader);
+                if (need) {
+                    const i64 cand = (i64)base + __popc(m & ((1u << lane) - 1));
+                    if (cand >= a.B) exhausted = true;
+                    else {
+                        c_inst[0] = cand;                                  // (every thread of the lane, this one included, adopts it in [C])
+                        flags |= F_NEW;
+                        live = true; fresh = true;
+                        t = 0.0; nacc = nrej = nanrej = 0; slab = 0; cur = 0; last_rejected = false;
+                        hacc = 0.0; erracc = 1e-2;
+                        tend = a.period/a.tNo;
+                    }
+                }
+            }
+            if (live && !fresh) {
+                const double hlim = tend - t;
+                clipped = hstep*1.01 >= hlim;
+                hh = clipped ? hlim : hstep;
+            } else hh = 1.0;
+            ctl[C_HH*WF_NR] = hh;
+            c_flags[0] = flags | (live ? F_LIVE : 0) | (fresh ? F_FRESH : 0) | (cur ? F_CUR : 0);
+            errsum = 0.0; bad = false;
+        }
+        __syncthreads();
+        // ---- [C] every thread: slab output of the reactor it served, then the new reactor ----
+        const int flags = c_flags[0];
+        if (flags & F_OUT) {
+            // un-scale and store (sortResult5, solResultAnalysis.py:252-301; :3630-3661): nodes role, role + roles, ...
+            const int ob = (flags & F_OUTBUF) ? 1 : 0, oslab = c_oslab[0];
+            const int rows = n2_out_rows(a.out_mode);
+            const i64 rs = (i64)zNo*a.B;
+            for (int k = role; k < zNo; k += WF_ROLES) {
+                double v[RMT_N];
+#pragma unroll
+                for (int q = 0; q < RMT_N; ++q) v[q] = YROW(ob, k, q);
+                double* o = a.out + (((i64)oslab*rows)*zNo + k)*a.B + inst;
+                if (a.out_mode != 1) {
+#pragma unroll
+                    for (int q = 0; q < RMT_N; ++q) o[q*rs] = v[q];
+                    o += RMT_N*rs;
+                }
+                if (a.out_mode != 0) {
+                    double S = 0.0, C[RMT_NC];
+#pragma unroll
+                    for (int q = 0; q < RMT_NC; ++q) { C[q] = v[q]*h.Cmax; S += C[q]; }
+                    if (a.out_mode == 2) {
+#pragma unroll
+                        for (int q = 0; q < RMT_NC; ++q) o[q*rs] = C[q];
+                        o += RMT_NC*rs;
+                    }
+#pragma unroll
+                    for (int q = 0; q < RMT_NC; ++q) o[q*rs] = C[q]/S;
+#if !RMT_ISO
+                    o[RMT_ITN*rs] = v[RMT_ITN]*h.Tf + h.Tf;
+#endif
+                }
+            }
+        }
+        if (flags & F_NEW) {
+            inst = c_inst[0];
+            rmt_load_hot(a.consts, a.B, inst, h);
+            for (int k = role; k < zNo; k += WF_ROLES) {                   // IV: feed composition at every node, T-hat = 0 (:3483-3497)
+#pragma unroll
+                for (int v = 0; v < RMT_NC; ++v) YROW(0, k, v) = h.iv[v];
+#if !RMT_ISO
+                YROW(0, k, RMT_ITN) = 0.0;
+#endif
+            }
+        }
+        const bool on = (flags & F_LIVE) != 0;
+        if (__syncthreads_and(!on)) break;                                 // also: the initial state is visible to JA
+        const bool isfresh = (flags & F_FRESH) != 0;
+        const int yn = (flags & F_CUR) ? 1 : 0;
+        const double hcur = ctl[C_HH*WF_NR];
+        const double invh = rmt_rcp(hcur), dg = invh*(1.0/RMT_ROS_GAMMA);
+        const double Lc = h.F1*invdz;                                      // upwind coupling of a species row
+#if !RMT_ISO
+        const double Lt = h.invZv*invdz;                                   // ... of the temperature row
+#endif
+
+        // ---- [E] one attempt: zNo + roles - 1 block steps; role r works on node tau - r ----
+        // chain state of the role's WF_SPR stages (JA uses set 0 for its upwind state and pressure)
+        double ub[WF_SPR][RMT_N], kprev[WF_SPR][RMT_N], P[WF_SPR], dP[WF_SPR], d0 = 0.0, d1 = 0.0;
+#pragma unroll
+        for (int q = 0; q < WF_SPR; ++q) {
+            P[q] = h.Pf; dP[q] = 0.0;
+#pragma unroll
+            for (int v = 0; v < RMT_N; ++v) { ub[q][v] = 0.0; kprev[q][v] = 0.0; }
+        }
+        const int nsteps = zNo + WF_ROLES - 1;
+        for (int tau = 0; tau < nsteps; ++tau) {
+            const int k = tau - role;
+            if (on && k >= 0 && k < zNo) {
+                double* const slot = SLOT(k);
+                if (role == 0) {
+                    // JA: f(y_n) and the Jacobian blocks of node k; W_kk = I/(h gamma) - A goes straight into the slot
+                    struct WSink {
+                        double* slot; double dg;
+                        __device__ __forceinline__ void operator()(int r, int cc, double v) const {
+                            slot[(E_W + r*RMT_N + cc)*32] = (r == cc ? dg : 0.0) - v;
+                        }
+                    };
+                    double u[RMT_N], fo[RMT_N], E;
+                    NodeJac nj;
+#pragma unroll
+                    for (int v = 0; v < RMT_N; ++v) u[v] = YROW(yn, k, v);
+                    n2_node<true>(u, ub[0], k == 0, P[0], invdz, h, fo, E, nj, WSink{slot, dg});
+                    unsigned lmask = 0u;                                   // rows whose upwind coupling L_k is switched on (:3897-3904 clamp)
+#pragma unroll
+                    for (int v = 0; v < RMT_N; ++v) {
+                        slot[(E_G + v)*32] = nj.g[v]; slot[(E_E + v)*32] = dz*nj.e[v];
+                        fring[((k & 1)*RMT_N + v)*32] = fo[v];
+                        lmask |= (nj.L[v] != 0.0 ? 1u : 0u) << v;
+                    }
+                    slot[E_EPF*32] = fma(dz, nj.ep, 1.0);
+                    c_perm[(k & (WF_DEPTH - 1))*32] = lmask << 24;         // role 1 adds the pivot order below it
+                    if (isfresh) {
+                        double n0 = 0.0, n1 = 0.0;
+#pragma unroll
+                        for (int v = 0; v < RMT_N; ++v) {
+                            const double isc = rmt_rcp(KAPPA*(a.atol + a.rtol*fabs(u[v])));
+                            n0 += (u[v]*isc)*(u[v]*isc); n1 += (fo[v]*isc)*(fo[v]*isc);
+                        }
+                        d0 += n0; d1 += n1;
+                        if (k == zNo - 1) { ctl[C_D0*WF_NR] = d0; ctl[C_D1*WF_NR] = d1; }
+                    }
+                    P[0] = fma(E, dz, P[0]);                               // :3979 (dimensionless dz, kept)
+#pragma unroll
+                    for (int v = 0; v < RMT_N; ++v) ub[0][v] = u[v];
+                } else if (!isfresh) {
+                    unsigned pw = c_perm[(k & (WF_DEPTH - 1))*32];
+                    if (role == 1) {
+                        // LU of W_kk with partial pivoting in the slot (per-row pointers in registers)
+                        double* rowp[RMT_N];
+                        int perm[RMT_N];
+#pragma unroll
+                        for (int r = 0; r < RMT_N; ++r) { rowp[r] = slot + (E_W + r*RMT_N)*32; perm[r] = r; }
+#define LUW(r, q) rowp[r][(q)*32]
+#pragma unroll
+                        for (int c = 0; c < RMT_N; ++c) {
+                            double best = fabs(LUW(c, c));
+                            int bi = c;
+#pragma unroll
+                            for (int r = c + 1; r < RMT_N; ++r) { const double v = fabs(LUW(r, c)); if (v > best) { best = v; bi = r; } }
+#pragma unroll
+                            for (int r = c + 1; r < RMT_N; ++r)
+                                if (r == bi) {
+                                    double* tr = rowp[c]; rowp[c] = rowp[r]; rowp[r] = tr;
+                                    const int tp = perm[c]; perm[c] = perm[r]; perm[r] = tp;
+                                }
+                            const double piv = rmt_rcp(LUW(c, c));
+                            LUW(c, c) = piv;                               // reciprocal pivot
+                            double urow[RMT_N];
+#pragma unroll
+                            for (int q = c + 1; q < RMT_N; ++q) urow[q] = LUW(c, q);
+#pragma unroll
+                            for (int r = c + 1; r < RMT_N; ++r) {
+                                const double l = LUW(r, c)*piv;
+                                LUW(r, c) = l;
+#pragma unroll
+                                for (int q = c + 1; q < RMT_N; ++q) LUW(r, q) -= l*urow[q];
+                            }
+                        }
+#undef LUW
+#pragma unroll
+                        for (int r = 0; r < RMT_N; ++r) pw |= (unsigned)perm[r] << (3*r);
+                        c_perm[(k & (WF_DEPTH - 1))*32] = pw;
+                    }
+                    // the role's stages of node k, one after the other (one copy of the code: the chain sets rotate)
+#pragma unroll 1
+                    for (int q = 0; q < WF_SPR; ++q) {
+                        const int s = (role - 1)*WF_SPR + q;
+                        double rhs[RMT_N], x[RMT_N];
+                        if (s == 0) {
+                            // stage 1: right-hand side f(y_n)
+#pragma unroll
+                            for (int v = 0; v < RMT_N; ++v) rhs[v] = fring[((k & 1)*RMT_N + v)*32];
+                        } else {
+                            // argument y_n + sum_j a_sj K_j, f, right-hand side f + sum_j (c_sj / h) K_j
+                            double u[RMT_N], vc[RMT_N], E;
+#pragma unroll
+                            for (int v = 0; v < RMT_N; ++v) { u[v] = YROW(yn, k, v); vc[v] = 0.0; }
+                            const double* kj = KSLOT(k);
+                            const double* arow = &RMT_cROS_A[s][0];
+                            const double* crow = &RMT_cROS_C[s][0];
+#pragma unroll 1
+                            for (int j = 0; j < s; ++j) {
+                                const double aj = arow[j], cj = crow[j]*invh;
+#pragma unroll
+                                for (int v = 0; v < RMT_N; ++v) {
+                                    const double kv = kj[v*32];
+                                    u[v] += aj*kv; vc[v] += cj*kv;
+                                }
+                                kj += RMT_N*32;
+                            }
+                            NodeJac njd;
+                            n2_node<false>(u, ub[0], k == 0, P[0], invdz, h, rhs, E, njd, NoSink());
+                            P[0] = fma(E, dz, P[0]);
+#pragma unroll
+                            for (int v = 0; v < RMT_N; ++v) { ub[0][v] = u[v]; rhs[v] += vc[v]; }
+                        }
+                        double tv[RMT_N];
+#pragma unroll
+                        for (int v = 0; v < RMT_N; ++v) {
+#if !RMT_ISO
+                            const double lv = ((pw >> (24 + v)) & 1u) ? (v == RMT_ITN ? Lt : Lc) : 0.0;
+#else
+                            const double lv = ((pw >> (24 + v)) & 1u) ? Lc : 0.0;
+#endif
+                            tv[v] = fma(lv, kprev[0][v], fma(slot[(E_G + v)*32], dP[0], rhs[v]));
+                        }
+                        wf_solve(slot, pw, tv, x);
+                        // K_k of this stage: kept for the next node's upwind term, stored for the later stages
+                        double ek = 0.0;
+#pragma unroll
+                        for (int v = 0; v < RMT_N; ++v) { kprev[0][v] = x[v]; ek = fma(slot[(E_E + v)*32], x[v], ek); }
+                        dP[0] = fma(dP[0], slot[E_EPF*32], ek);            // dP_{k+1} = (1 + dz ep_k) dP_k + dz e_k . K_k
+                        if (s < RMT_ROS_S - 1) {
+                            double* ks = KSLOT(k) + s*(RMT_N*32);
+#pragma unroll
+                            for (int v = 0; v < RMT_N; ++v) ks[v*32] = x[v];
+                        } else {
+                            // y_{n+1} = y_n + sum_j m_j K_j ; err = sum_j e_j K_j.  Stiffly accurate tableaux (Rodas4: the last
+                            // stage's argument is y_n + sum_{j<S} m_j K_j and the error estimator is K_S): y_{n+1} = u_S + K_S, err = K_S
+                            double ne = 0.0;
+                            const double* kr = KSLOT(k);
+#pragma unroll
+                            for (int v = 0; v < RMT_N; ++v) {
+                                const double yold = YROW(yn, k, v);
+                                double ynew, ev;
+                                if (wf_stiffly_accurate()) { ynew = ub[0][v] + x[v]; ev = x[v]; }
+                                else {
+                                    ynew = yold; ev = 0.0;
+#pragma unroll
+                                    for (int j = 0; j < RMT_ROS_S - 1; ++j) {
+                                        const double kj = kr[(j*RMT_N + v)*32];
+                                        ynew += RMT_cROS_M[j]*kj; ev += RMT_cROS_E[j]*kj;
+                                    }
+                                    ynew += RMT_cROS_M[RMT_ROS_S - 1]*x[v]; ev += RMT_cROS_E[RMT_ROS_S - 1]*x[v];
+                                }
+                                YROW(yn ^ 1, k, v) = ynew;
+                                const double en = ev*rmt_rcp(KAPPA*(a.atol + a.rtol*fmax(fabs(yold), fabs(ynew))));
+                                ne += en*en;
+                                bad = bad || !(fabs(ynew) <= 1.7e308);
+                            }
+                            errsum += ne;                                  // node order
+                        }
+                        if (WF_SPR > 1) {
+                            // rotate the chain sets: set 0 is always the one of the stage being worked on
+#pragma unroll
+                            for (int v = 0; v < RMT_N; ++v) {
+                                const double tu = ub[0][v], tk = kprev[0][v];
+#pragma unroll
+                                for (int w = 0; w + 1 < WF_SPR; ++w) { ub[w][v] = ub[w + 1][v]; kprev[w][v] = kprev[w + 1][v]; }
+                                ub[WF_SPR - 1][v] = tu; kprev[WF_SPR - 1][v] = tk;
+                            }
+                            const double tp = P[0], td = dP[0];
+#pragma unroll
+                            for (int w = 0; w + 1 < WF_SPR; ++w) { P[w] = P[w + 1]; dP[w] = dP[w + 1]; }
+                            P[WF_SPR - 1] = tp; dP[WF_SPR - 1] = td;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+#undef YROW
+#undef KSLOT
+#undef SLOT
+}
+#endif  // RMT_N2_WF
 #endif  // RMT_DYNAMIC
 
 // ---------------------------------------------------------------------------------

@@ -199,6 +199,24 @@ def n2_lanes(B, zNo, sm_count=148, n=7):
     return lanes
 
 
+# Stage-pipelined N2 kernel (lanes = 0, rmt_kernels.cu "stage pipeline"): a block serves 64 reactors — two warps per
+# role, roles = Jacobian | stages 1-2 (+ LU) | stages 3-4 | stages 5-6 — one block per SM, so an ensemble is worked off in
+# rounds of sm_count*64 reactors.  Measured on one B200 (200 nodes): a full round of 9 472 reactors takes 0.081 s where
+# the lanes kernel needs 0.094 s; 50 000 x 50 nodes 0.103 vs 0.131 s; 12 500 x 200 (1.32 rounds) 0.147 vs 0.126 s.
+N2_PIPELINE_REACTORS_PER_BLOCK = 64
+N2_PIPELINE_MIN_B = 2048
+
+
+def n2_use_pipeline(B, zNo, sm_count=148):
+    """Stage pipeline or lanes kernel?  The pipeline costs ~0.87 of the lanes kernel per reactor when its rounds are
+    full; a partly filled last round costs a full one."""
+    if B < N2_PIPELINE_MIN_B or zNo < 8:
+        return False
+    per_round = sm_count*N2_PIPELINE_REACTORS_PER_BLOCK
+    rounds = -(-B//per_round)
+    return rounds*per_round*0.87 <= B*1.0
+
+
 def n2_block(B, sm_count=148, lanes=1):
     """Threads per block of the N2 integrator (`lanes` threads per reactor, lockstep blocks).  The kernel keeps a
     78-row record per thread plus a hand-over record per reactor in shared memory ((n + 1) n + 3 n + 1 rows of
@@ -214,6 +232,15 @@ def compile_model_n2(modelInput, B, zNo, method=None):
     """compile_model with the launch shape (lanes per reactor, block size) for an ensemble of B reactors."""
     n_node = len(modelInput["feed"]["components"]["shell"]) + (0 if modelInput["operating-conditions"].get("process-type") == "iso-thermal" else 1)
     lanes = n2_lanes(B, zNo, n=n_node) if modelInput["model"] == "N2" else 1       # M9: the velocity march is sequential
+    if modelInput["model"] == "N2" and n2_use_pipeline(B, zNo):
+        from .tableau import TABLEAUX
+        m = method or choose_method(modelInput, rtol=0.0)          # like compile_model: Rodas4 unless solver-config says otherwise
+        from .tableau import new_function_flags
+        if not all(new_function_flags(TABLEAUX[m])[1:]):            # a stage re-using f (Ros4): lanes kernel
+            return compile_model(modelInput, block=n2_block(B, lanes=lanes), method=method, lanes=lanes)
+        S = TABLEAUX[m]["stages"]
+        if S % 2 == 0:                                              # two stages per role, two warps per role
+            return compile_model(modelInput, block=32*(1 + S//2)*(N2_PIPELINE_REACTORS_PER_BLOCK//32), method=m, lanes=0)
     return compile_model(modelInput, block=n2_block(B, lanes=lanes), method=method, lanes=lanes)
 
 

@@ -124,6 +124,67 @@ def test_n2_lanes_per_reactor_give_the_same_solution(n2_settings, case):
     assert engine.n2_lanes(1, 4) == 4
 
 
+@pytest.mark.parametrize("case,zNo", [("methanol", 21), ("ch4", 12), ("methanol", 50)])
+def test_n2_stage_pipeline_kernel_equals_the_lanes_kernel(n2_settings, case, zNo):
+    """The stage-pipelined mapping (one thread per reactor and pair of Rosenbrock stages, rmt_kernels.cu "stage
+    pipeline") integrates the same method with the same per-node arithmetic as the lanes kernel; only the order of the
+    linear algebra differs (LU solves instead of products with the explicit inverse blocks): same step sequence, states
+    equal to <= 1e-9 — with more reactors than one block holds, a partly filled block, a reactor that fails (NaN feed)
+    and slots that pick up a second reactor."""
+    from rmt_app_b200 import engine
+    mi = cases.methanol_testfile_input("N2") if case == "methanol" else cases.ch4_input("N2")
+    B = 150
+    rng = np.random.default_rng(11)
+    T0 = mi["operating-conditions"]["temperature"]
+    sw = {"temperature": T0*rng.uniform(0.97, 1.03, B)}
+    sw["temperature"][17] = np.nan
+    period = float(mi["operating-conditions"]["period"])
+    lanes = engine.compile_model(mi, block=64, lanes=8)
+    pipe = engine.compile_model(mi, block=256, lanes=0)
+    assert pipe is not lanes and pipe.load(0).info.lanes == 0
+    a = engine.n2_solve_ensemble(lanes, mi, sw, B, zNo=zNo, tNo=3, period=period)
+    b = engine.n2_solve_ensemble(pipe, mi, sw, B, zNo=zNo, tNo=3, period=period)
+    ok = np.arange(B) != 17
+    assert (a.status[ok] == 0).all() and (b.status[ok] == 0).all() and a.status[17] != 0 and b.status[17] != 0
+    assert np.isnan(b.out[..., 17]).all()
+    np.testing.assert_array_equal(a.stats[:, ok], b.stats[:, ok])
+    np.testing.assert_allclose(b.out[..., ok], a.out[..., ok], rtol=1e-9, atol=0)
+    # out_mode 2 (raw | C_i | dataYs rows) through the same kernel
+    a2 = engine.n2_solve_ensemble(lanes, mi, sw, B, zNo=zNo, tNo=2, period=period, out_mode=2)
+    b2 = engine.n2_solve_ensemble(pipe, mi, sw, B, zNo=zNo, tNo=2, period=period, out_mode=2)
+    np.testing.assert_allclose(b2.out[..., ok], a2.out[..., ok], rtol=1e-9, atol=0)
+    # the launch-shape policy: full rounds of 148 x 64 reactors go to the pipeline, small or badly filling ensembles do not
+    assert engine.n2_use_pipeline(9472, 200) and engine.n2_use_pipeline(100000, 200)
+    assert not engine.n2_use_pipeline(12500, 200) and not engine.n2_use_pipeline(500, 200) and not engine.n2_use_pipeline(9472, 4)
+
+
+def test_n2_stage_pipeline_kernel_against_the_converged_oracle(n2_settings):
+    """Config 5's grid (200 nodes, period 0.5 s, 5 slabs) through the stage-pipelined kernel, the fixture instances
+    planted in an ensemble of 9 472 reactors (one full round of 148 blocks x 64): temperature profiles and outlets within
+    1e-6 of the converged oracle runs — the same bar as the lanes kernel's test below."""
+    from rmt_app_b200 import engine
+    conv = np.load(os.path.join(GOLDEN, "n2_sol_config5_z200_oracle_tight.npz"))
+    zNo, idx = int(conv["zNo"]), [int(i) for i in conv["index"]]
+    mi = cases.methanol_readme_input("N2")
+    full = cases.config3_sweep(int(conv["B"]), int(conv["seed"]))
+    B = 9472
+    assert engine.n2_use_pipeline(B, zNo)
+    pick = np.r_[idx, np.setdiff1d(np.arange(B + 3), idx)[:B - len(idx)]]       # fixture instances first, then others
+    sub = {k: np.ascontiguousarray(np.asarray(v)[pick]) for k, v in full.items()}
+    cm = engine.compile_model_n2(mi, B, zNo)
+    assert cm.lanes == 0
+    r = engine.n2_solve_ensemble(cm, mi, sub, B, zNo=zNo, tNo=5, period=0.5, rtol=1e-8, atol=1e-11, keep_on_device=True)
+    assert bool((r.status == 0).all())
+    got_all = r.out[..., :len(idx)].cpu().numpy()                       # [tNo][rows][zNo][3]
+    for j, i in enumerate(idx):
+        for s_ in range(5):
+            ref = conv["dataYs"][j][s_]
+            rel = np.abs(got_all[s_, :, :, j] - ref)/np.abs(ref)
+            assert rel[-1].max() < 1e-6, (i, s_, rel[-1].max())
+            assert rel[:, -1].max() < 1e-6, (i, s_, rel[:, -1])
+            assert rel.max() < 1e-5, (i, s_, rel.max())
+
+
 def test_n2_ensemble_matches_single_and_reports_failures(n2_settings):
     from rmt_app_b200 import engine
     mi = cases.ch4_input("N2")

@@ -231,11 +231,11 @@ def generate_model_header(spec, tableau="rodas4", reduced=None, lanes=1):
     A("#ifndef RMT_REDUCED")
     A("#define RMT_REDUCED %d" % (1 if reduced else 0))
     A("#endif")
-    if spec.model == "M9" and lanes != 1:
-        raise ValueError("M9 marches the velocity through the kinetics node by node: one lane per reactor")
+    if spec.model == "M9" and lanes not in (0, 1):
+        raise ValueError("M9 marches the velocity through the kinetics node by node: one lane per reactor, or the stage pipeline (0)")
     if spec.model in ("N2", "M9"):
-        if lanes not in (0, 1, 2, 4, 8, 16, 32) or (lanes == 0 and spec.model != "N2"):
-            raise ValueError("lanes per reactor must be a power of two <= 32 (N2: or 0 = stage-pipelined mapping)")
+        if lanes not in (0, 1, 2, 4, 8, 16, 32):
+            raise ValueError("lanes per reactor must be a power of two <= 32, or 0 = stage-pipelined mapping")
         A("// threads per reactor of the dynamic integrator (nodes evaluated in parallel); 0 = one thread per reactor and")
         A("// Rosenbrock stage role (stage pipeline, block = 32 x (stages + 1))")
         A("#ifndef RMT_N2_G")

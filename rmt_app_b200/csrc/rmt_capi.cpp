@@ -511,7 +511,8 @@ int rmt_module_load(const void* cubin, size_t size, rmt_module_t* module_out)
         // N2: the substitution's shared-memory record, ((n + 1) n + 3 n + 1) rows of (block + 1) doubles (rmt_n2_solve); M9: none
         // and, with several lanes per reactor, the sweeps' hand-over records [block/lanes][stages + 1][2 n + 4]
         M->solve_smem = I.model == 2 ? 8*((size_t)(I.n + 1)*I.n + 3*(size_t)I.n + 1)*((size_t)I.block + 1) : 0;
-        if (I.lanes > 1) M->solve_smem += 8*(size_t)(I.block/I.lanes)*(I.stages + 1)*(2*(size_t)I.n + 4);
+        if (I.lanes > 1) M->solve_smem += 8*(size_t)(I.block/I.lanes)*(I.stages + 1)*(2*(size_t)I.n + 4)
+                                          + 8*((size_t)(I.block/I.lanes)*8 + 2);      // + the substitution's hand-over vectors
         if (I.lanes == 0) {
             // stage pipeline: the kernel's own layout constants (WF_SMEM_BYTES, reactors per block, work rows)
             CUfunction fm2 = get("rmt_n2_meta");

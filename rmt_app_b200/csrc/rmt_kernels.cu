@@ -2284,6 +2284,14 @@ __device__ __forceinline__ void dyn_eval(const double (&u)[RMT_N], const double 
 #ifndef RMT_N2_MINBLOCKS
 #define RMT_N2_MINBLOCKS 1
 #endif
+// stage-vector loads of the stage sweeps: 1 = loop over the earlier stages, 0 = predicated loads of all of them
+#ifndef RMT_N2_KLOOP
+#define RMT_N2_KLOOP 0
+#endif
+// hand-over vector of the substitution: 1 = gathered through shared memory (one store, wide loads), 0 = by shuffles
+#ifndef RMT_N2_TVSMEM
+#define RMT_N2_TVSMEM 1
+#endif
 extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2_solve(const SolveArgsN2 a)
 {
     constexpr int G = RMT_N2_G;
@@ -2329,6 +2337,11 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
 #if RMT_N2_G > 1
     // behind it: what the sweeps carry from one node group to the next, one record per reactor of the block
     double* const n2_carry = n2_sh + N2_SH_ROWS*SH_LD;        // [(RMT_BLOCK/G)][RMT_ROS_S + 1][N2_CARRY]
+#if RMT_N2_TVSMEM
+    // the substitution's hand-over vector, 8 doubles per reactor, 16-byte aligned (the carry records before it hold an even
+    // number of doubles per reactor and N2_SH_ROWS*SH_LD is padded to even below)
+    double* const n2_tv = n2_sh + ((N2_SH_ROWS*SH_LD + (RMT_BLOCK/G)*((RMT_ROS_S + 1)*N2_CARRY) + 1) & ~1);
+#endif
 #endif
 #endif
     i64 inst = -1;
@@ -2620,6 +2633,25 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
                     double u[RMT_N], ub[RMT_N], vc[RMT_N];
 #pragma unroll
                     for (int v = 0; v < RMT_N; ++v) { u[v] = WY(YN + v, kg); vc[v] = 0.0; }
+#if RMT_N2_KLOOP
+                    // the earlier stages' vectors, one per iteration (s is block-uniform: no divergence); the loads of an
+                    // iteration are issued together
+                    {
+                        const double* kj = &WS(W_K);
+                        const double* arow = &RMT_cROS_A[s][0];
+                        const double* crow = &RMT_cROS_C[s][0];
+#pragma unroll 1
+                        for (int j = 0; j < s; ++j) {
+                            const double aj = arow[j], cj = crow[j]*invh;
+                            double kv[RMT_N];
+#pragma unroll
+                            for (int v = 0; v < RMT_N; ++v) kv[v] = kj[v*RMT_BLOCK];
+#pragma unroll
+                            for (int v = 0; v < RMT_N; ++v) { u[v] += aj*kv[v]; vc[v] += cj*kv[v]; }
+                            kj += RMT_N*RMT_BLOCK;
+                        }
+                    }
+#else
                     // (compile-time trip count with predicated loads: the stage vectors of all earlier stages are
                     // fetched back to back instead of one stage per loop iteration)
 #pragma unroll
@@ -2632,6 +2664,7 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
                             u[v] += aj*kv; vc[v] += cj*kv;
                         }
                     }
+#endif
 #pragma unroll
                     for (int v = 0; v < RMT_N; ++v) {
                         const double up = G > 1 ? __shfl_up_sync(gmask, u[v], 1, G) : 0.0;
@@ -2675,6 +2708,23 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
                                 tvo[q] = fma(sj[(S_L + r)*SH_LD], kprev[q], fma(sj[(S_G + r)*SH_LD], dP, sj[(S_R + r)*SH_LD]));
                         }
                         double tv[RMT_N];
+#if RMT_N2_TVSMEM && RMT_N2_G >= 8
+                        if (NROW == 1) {
+                            // every lane stores its entry into the reactor's 8-double record and reads the whole vector back
+                            // with four 128-bit loads (all lanes of a reactor read the same addresses: broadcast)
+                            double* const tvs = n2_tv + (threadIdx.x/G)*8;
+                            if (g < 8) tvs[g] = g < RMT_N ? tvo[0] : 0.0;
+                            __syncwarp();
+                            const double2* t2 = reinterpret_cast<const double2*>(tvs);
+#pragma unroll
+                            for (int cc = 0; cc < RMT_N; cc += 2) {
+                                const double2 w = t2[cc/2];
+                                tv[cc] = w.x;
+                                if (cc + 1 < RMT_N) tv[cc + 1] = w.y;
+                            }
+                            __syncwarp();
+                        } else
+#endif
 #pragma unroll
                         for (int cc = 0; cc < RMT_N; ++cc) tv[cc] = G > 1 ? __shfl_sync(gmask, tvo[cc/G], cc % G, G) : tvo[cc/G];
                         double dPn = 0.0;
@@ -2948,9 +2998,11 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, RMT_N2_MINBLOCKS) rmt_n2
 // in a small shared-memory record.  A fresh reactor's first attempt is the norm pass for the starting step (JA only).
 // Lanes pick up a new reactor from the global queue as soon as theirs is done.
 // ---------------------------------------------------------------------------------
-#if defined(RMT_MODEL_M9)
-#error "the stage pipeline covers N2; M9 uses the lanes kernel with RMT_N2_G = 1"
-#endif
+// M9 (the dimensional twin, pbReactor.py:2296-2660) runs in the same pipeline: its node function marches the superficial
+// velocity as well, so a role's chain carries (P, v) and the linearised pair (dP, dv), and the ring slot holds the velocity
+// and T_{k-1} couplings (NodeJac.gv / Lt / eV / ev / eVb / eVP / eVv) besides g, e and the upwind diagonal, which depends
+// on the node's velocity and is stored instead of being rebuilt from a mask.  Because every chain is private to a thread,
+// the velocity march needs no lane hand-over here — the reason the lanes kernel serves M9 with one lane per reactor.
 #ifndef WF_SPR
 #define WF_SPR 2                                   // stages per role
 #endif
@@ -2963,8 +3015,14 @@ static_assert(RMT_BLOCK == 32*WF_ROLES*WF_RW && WF_RW >= 1, "stage pipeline: blo
 static_assert(WF_DEPTH >= WF_ROLES && (WF_DEPTH & (WF_DEPTH - 1)) == 0, "ring depth");
 static_assert(!RMT_ROS_REUSE, "stage pipeline: every stage after the first evaluates f at its own argument");
 static_assert(RMT_N <= 8, "pivot order (3 bits per row, bits 0..23) and the upwind mask (bits 24..31) share one 32-bit word");
-// rows of a ring slot (per reactor): W_kk -> LU (n x n), g_k, dz e_k, 1 + dz ep_k
+// rows of a ring slot (per reactor): W_kk -> LU (n x n), g_k, dz e_k, 1 + dz ep_k;
+// M9: + L_k, gv_k, Lt_k, dz eV_k, dz ev_k, dz eVb_k, dz eVP_k, 1 + dz eVv_k
+#if defined(RMT_MODEL_M9)
+enum { E_W = 0, E_G = RMT_N*RMT_N, E_E = E_G + RMT_N, E_EPF = E_E + RMT_N, E_L = E_EPF + 1, E_GV = E_L + RMT_N, E_LT = E_GV + RMT_N,
+       E_EV = E_LT + RMT_N, E_S0 = E_EV + RMT_N, E_ROWS = E_S0 + 4 };
+#else
 enum { E_W = 0, E_G = RMT_N*RMT_N, E_E = E_G + RMT_N, E_EPF = E_E + RMT_N, E_ROWS = E_EPF + 1 };
+#endif
 // control record (doubles) per reactor lane
 enum { C_HH = 0, C_D0, C_D1, C_ROWS };
 enum { F_LIVE = 1, F_FRESH = 2, F_CUR = 4, F_OUT = 8, F_NEW = 16, F_OUTBUF = 32 };
@@ -3064,7 +3122,9 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, WF_MINBLOCKS) rmt_n2_sol
 #define YROW(buf, k, v) wy[(((i64)(buf)*zNo + (k))*RMT_N + (v))*32]
 #define KSLOT(k) (wk + ((k) & (WF_DEPTH - 1))*((RMT_ROS_S - 1)*RMT_N*32))     // K_j[k][v] = KSLOT(k)[(j*n + v)*32]
 #define SLOT(k) (ring + ((k) & (WF_DEPTH - 1))*(E_ROWS*32))
+#if !defined(RMT_MODEL_M9)
     const double dz = 1.0/(zNo - 1), invdz = 1.0/dz;
+#endif
     const double ISAFE = 1.0/a.ctrl[0], FAC1 = a.ctrl[1], FAC2 = 1.0/a.ctrl[2], KAPPA = a.ctrl[3], BETA = a.ctrl[4];
     const double inv_nz = 1.0/((double)RMT_N*zNo);
     const bool controller = role == WF_ROLES - 1;
@@ -3201,7 +3261,11 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, WF_MINBLOCKS) rmt_n2_sol
                 if (a.out_mode != 0) {
                     double S = 0.0, C[RMT_NC];
 #pragma unroll
+#if defined(RMT_MODEL_M9)
+                    for (int q = 0; q < RMT_NC; ++q) { C[q] = v[q]; S += C[q]; }               // pbReactor.py:2189-2196
+#else
                     for (int q = 0; q < RMT_NC; ++q) { C[q] = v[q]*h.Cmax; S += C[q]; }
+#endif
                     if (a.out_mode == 2) {
 #pragma unroll
                         for (int q = 0; q < RMT_NC; ++q) o[q*rs] = C[q];
@@ -3209,7 +3273,9 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, WF_MINBLOCKS) rmt_n2_sol
                     }
 #pragma unroll
                     for (int q = 0; q < RMT_NC; ++q) o[q*rs] = C[q]/S;
-#if !RMT_ISO
+#if defined(RMT_MODEL_M9)
+                    o[RMT_ITN*rs] = v[RMT_ITN];
+#elif !RMT_ISO
                     o[RMT_ITN*rs] = v[RMT_ITN]*h.Tf + h.Tf;
 #endif
                 }
@@ -3221,7 +3287,9 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, WF_MINBLOCKS) rmt_n2_sol
             for (int k = role; k < zNo; k += WF_ROLES) {                   // IV: feed composition at every node, T-hat = 0 (:3483-3497)
 #pragma unroll
                 for (int v = 0; v < RMT_NC; ++v) YROW(0, k, v) = h.iv[v];
-#if !RMT_ISO
+#if defined(RMT_MODEL_M9)
+                YROW(0, k, RMT_ITN) = h.Tf;                                // pbReactor.py:2099-2100
+#elif !RMT_ISO
                 YROW(0, k, RMT_ITN) = 0.0;
 #endif
             }
@@ -3232,14 +3300,23 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, WF_MINBLOCKS) rmt_n2_sol
         const int yn = (flags & F_CUR) ? 1 : 0;
         const double hcur = ctl[C_HH*WF_NR];
         const double invh = rmt_rcp(hcur), dg = invh*(1.0/RMT_ROS_GAMMA);
+#if defined(RMT_MODEL_M9)
+        const double dz = h.zf/(zNo - 1), invdz = 1.0/dz;                  // dimensional grid, pbReactor.py:2076
+#else
         const double Lc = h.F1*invdz;                                      // upwind coupling of a species row
 #if !RMT_ISO
         const double Lt = h.invZv*invdz;                                   // ... of the temperature row
+#endif
 #endif
 
         // ---- [E] one attempt: zNo + roles - 1 block steps; role r works on node tau - r ----
         // chain state of the role's WF_SPR stages (JA uses set 0 for its upwind state and pressure)
         double ub[WF_SPR][RMT_N], kprev[WF_SPR][RMT_N], P[WF_SPR], dP[WF_SPR], d0 = 0.0, d1 = 0.0;
+#if defined(RMT_MODEL_M9)
+        double vel[WF_SPR], dv[WF_SPR];                                    // marched / linearised superficial velocity
+#pragma unroll
+        for (int q = 0; q < WF_SPR; ++q) { vel[q] = h.us0; dv[q] = 0.0; }  // v_z[0] = SuGaVe0, pbReactor.py:2433
+#endif
 #pragma unroll
         for (int q = 0; q < WF_SPR; ++q) {
             P[q] = h.Pf; dP[q] = 0.0;
@@ -3263,6 +3340,26 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, WF_MINBLOCKS) rmt_n2_sol
                     NodeJac nj;
 #pragma unroll
                     for (int v = 0; v < RMT_N; ++v) u[v] = YROW(yn, k, v);
+#if defined(RMT_MODEL_M9)
+                    double V;
+                    m9_node<true>(u, ub[0], k == 0, P[0], vel[0], invdz, h, fo, E, V, nj);
+#pragma unroll
+                    for (int r = 0; r < RMT_N; ++r)
+#pragma unroll
+                        for (int cc = 0; cc < RMT_N; ++cc) slot[(E_W + r*RMT_N + cc)*32] = (r == cc ? dg : 0.0) - nj.A[r][cc];
+                    (void)sizeof(WSink);
+#pragma unroll
+                    for (int v = 0; v < RMT_N; ++v) {
+                        slot[(E_G + v)*32] = nj.g[v]; slot[(E_E + v)*32] = dz*nj.e[v]; slot[(E_L + v)*32] = nj.L[v];
+                        slot[(E_GV + v)*32] = nj.gv[v]; slot[(E_LT + v)*32] = nj.Lt[v]; slot[(E_EV + v)*32] = dz*nj.eV[v];
+                        fring[((k & 1)*RMT_N + v)*32] = fo[v];
+                    }
+                    slot[E_EPF*32] = fma(dz, nj.ep, 1.0);
+                    slot[(E_S0 + 0)*32] = dz*nj.ev; slot[(E_S0 + 1)*32] = dz*nj.eVb;
+                    slot[(E_S0 + 2)*32] = dz*nj.eVP; slot[(E_S0 + 3)*32] = fma(dz, nj.eVv, 1.0);
+                    c_perm[(k & (WF_DEPTH - 1))*32] = 0u;
+                    vel[0] = V*dz + vel[0];                                // pbReactor.py:2612
+#else
                     n2_node<true>(u, ub[0], k == 0, P[0], invdz, h, fo, E, nj, WSink{slot, dg});
                     unsigned lmask = 0u;                                   // rows whose upwind coupling L_k is switched on (:3897-3904 clamp)
 #pragma unroll
@@ -3273,6 +3370,7 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, WF_MINBLOCKS) rmt_n2_sol
                     }
                     slot[E_EPF*32] = fma(dz, nj.ep, 1.0);
                     c_perm[(k & (WF_DEPTH - 1))*32] = lmask << 24;         // role 1 adds the pivot order below it
+#endif
                     if (isfresh) {
                         double n0 = 0.0, n1 = 0.0;
 #pragma unroll
@@ -3353,12 +3451,38 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, WF_MINBLOCKS) rmt_n2_sol
                                 kj += RMT_N*32;
                             }
                             NodeJac njd;
+#if defined(RMT_MODEL_M9)
+                            double V;
+                            m9_node<false>(u, ub[0], k == 0, P[0], vel[0], invdz, h, rhs, E, V, njd);
+                            vel[0] = V*dz + vel[0];
+#else
                             n2_node<false>(u, ub[0], k == 0, P[0], invdz, h, rhs, E, njd, NoSink());
+#endif
                             P[0] = fma(E, dz, P[0]);
 #pragma unroll
                             for (int v = 0; v < RMT_N; ++v) { ub[0][v] = u[v]; rhs[v] += vc[v]; }
                         }
                         double tv[RMT_N];
+#if defined(RMT_MODEL_M9)
+                        // besides the upwind block and the pressure column: the velocity column and the T_{k-1} column
+                        const double ktb = kprev[0][RMT_ITN];
+#pragma unroll
+                        for (int v = 0; v < RMT_N; ++v)
+                            tv[v] = rhs[v] + (fma(slot[(E_L + v)*32], kprev[0][v], slot[(E_G + v)*32]*dP[0])
+                                              + (slot[(E_GV + v)*32]*dv[0] + slot[(E_LT + v)*32]*ktb));
+                        wf_solve(slot, pw, tv, x);
+                        double ek = 0.0, evk = 0.0;
+#pragma unroll
+                        for (int v = 0; v < RMT_N; ++v) {
+                            kprev[0][v] = x[v];
+                            ek = fma(slot[(E_E + v)*32], x[v], ek); evk = fma(slot[(E_EV + v)*32], x[v], evk);
+                        }
+                        // dP_{k+1} = dP_k + dz (e_k . K_k + (dE/dv) dv_k);  dv_{k+1} = dv_k + dz (eV_k . K_k + (dV/dT_{k-1}) K_{k-1,T}
+                        //            + (dV/dP) dP_k + (dV/dv) dv_k)
+                        const double dPn = fma(dP[0], slot[E_EPF*32], ek + slot[(E_S0 + 0)*32]*dv[0]);
+                        dv[0] = fma(dv[0], slot[(E_S0 + 3)*32], evk + slot[(E_S0 + 1)*32]*ktb + slot[(E_S0 + 2)*32]*dP[0]);
+                        dP[0] = dPn;
+#else
 #pragma unroll
                         for (int v = 0; v < RMT_N; ++v) {
 #if !RMT_ISO
@@ -3374,6 +3498,7 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, WF_MINBLOCKS) rmt_n2_sol
 #pragma unroll
                         for (int v = 0; v < RMT_N; ++v) { kprev[0][v] = x[v]; ek = fma(slot[(E_E + v)*32], x[v], ek); }
                         dP[0] = fma(dP[0], slot[E_EPF*32], ek);            // dP_{k+1} = (1 + dz ep_k) dP_k + dz e_k . K_k
+#endif
                         if (s < RMT_ROS_S - 1) {
                             double* ks = KSLOT(k) + s*(RMT_N*32);
 #pragma unroll
@@ -3417,6 +3542,12 @@ extern "C" __global__ void __launch_bounds__(RMT_BLOCK, WF_MINBLOCKS) rmt_n2_sol
 #pragma unroll
                             for (int w = 0; w + 1 < WF_SPR; ++w) { P[w] = P[w + 1]; dP[w] = dP[w + 1]; }
                             P[WF_SPR - 1] = tp; dP[WF_SPR - 1] = td;
+#if defined(RMT_MODEL_M9)
+                            const double tvl = vel[0], tdv = dv[0];
+#pragma unroll
+                            for (int w = 0; w + 1 < WF_SPR; ++w) { vel[w] = vel[w + 1]; dv[w] = dv[w + 1]; }
+                            vel[WF_SPR - 1] = tvl; dv[WF_SPR - 1] = tdv;
+#endif
                         }
                     }
                 }

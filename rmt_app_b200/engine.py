@@ -232,7 +232,8 @@ def compile_model_n2(modelInput, B, zNo, method=None):
     """compile_model with the launch shape (lanes per reactor, block size) for an ensemble of B reactors."""
     n_node = len(modelInput["feed"]["components"]["shell"]) + (0 if modelInput["operating-conditions"].get("process-type") == "iso-thermal" else 1)
     lanes = n2_lanes(B, zNo, n=n_node) if modelInput["model"] == "N2" else 1       # M9: the velocity march is sequential
-    if modelInput["model"] == "N2" and n2_use_pipeline(B, zNo):
+    # M9: the lanes kernel has one lane per reactor, the pipeline four threads — taken from a few hundred reactors on
+    if (modelInput["model"] == "N2" and n2_use_pipeline(B, zNo)) or (modelInput["model"] == "M9" and B >= 256 and zNo >= 8):
         from .tableau import TABLEAUX
         m = method or choose_method(modelInput, rtol=0.0)          # like compile_model: Rodas4 unless solver-config says otherwise
         from .tableau import new_function_flags

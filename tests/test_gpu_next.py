@@ -147,6 +147,35 @@ def test_m9_dimensional_dynamic_twin_parity():
         O.solverSetting["S2"].update(tNo=10, zNo=100)
 
 
+def test_m9_stage_pipeline_equals_one_lane_per_reactor():
+    """M9 through the stage-pipelined kernel (four threads per reactor: the velocity march and its linearisation are
+    chains private to a thread, rmt_kernels.cu "stage pipeline") against the lanes kernel with one lane per reactor: same
+    step sequence, states equal to <= 1e-9, for node counts below and above the ring depth; the single reactor of the
+    fixture stays within 1e-6 of the converged oracle run; ensembles of a few hundred reactors take the pipeline."""
+    import os
+    from conftest import GOLDEN
+    from rmt_app_b200 import engine
+    mi = cases.methanol_m9_input()
+    B = 100
+    rng = np.random.default_rng(4)
+    sw = {"temperature": 523.0 + rng.uniform(-8.0, 8.0, B), "pressure": mi["operating-conditions"]["pressure"]*rng.uniform(0.9, 1.1, B)}
+    period = float(mi["operating-conditions"]["period"])
+    one = engine.compile_model(mi, block=64, lanes=1)
+    pipe = engine.compile_model(mi, block=256, lanes=0)
+    assert pipe.load(0).info.lanes == 0 and pipe.load(0).info.model == 9
+    for zNo in (12, 37):
+        a = engine.n2_solve_ensemble(one, mi, sw, B, zNo=zNo, tNo=3, period=period, rtol=1e-6, atol=1e-9)
+        b = engine.n2_solve_ensemble(pipe, mi, sw, B, zNo=zNo, tNo=3, period=period, rtol=1e-6, atol=1e-9)
+        assert (a.status == 0).all() and (b.status == 0).all()
+        np.testing.assert_array_equal(a.stats, b.stats)
+        np.testing.assert_allclose(b.out, a.out, rtol=1e-9, atol=0)
+    t = np.load(os.path.join(GOLDEN, "m9_sol_oracle_tight.npz"))
+    r = engine.n2_solve_ensemble(pipe, mi, None, 1, zNo=12, tNo=3, period=period, rtol=1e-9, atol=1e-12)
+    assert r.status[0] == 0
+    assert np.max(np.abs(r.out[..., 0] - t["dataYs"])/np.abs(t["dataYs"])) < 1e-6
+    assert engine.compile_model_n2(mi, 1000, 50).lanes == 0 and engine.compile_model_n2(mi, 6, 12).lanes == 1
+
+
 def test_full_state_integrator_when_reactions_do_not_outnumber_species():
     """nr >= nc: no reaction-extent form (codegen.use_extents), the integrator works on the full state; the solution
     must match the oracle on the same synthetic three-reaction methane case, for the outlet-only (Ros4) and the

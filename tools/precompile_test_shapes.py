@@ -31,9 +31,14 @@ def main(verbose=True):
     mi = cases.methanol_readme_input("N2")
     for B, z in ((1, 20), (1, 50), (12500, 200), (1, 200)):
         put(engine.compile_model_n2(mi, B, z))
+    for B, z in ((9472, 200), (100000, 200), (50000, 50)):                # stage-pipelined launch shapes
+        put(engine.compile_model_n2(mi, B, z))
+    for mk in (cases.methanol_testfile_input, cases.ch4_input):
+        put(engine.compile_model(mk("N2"), block=256, lanes=0))
     mi = cases.methanol_m9_input()
     for blk in (64, 32):
         put(engine.compile_model(mi, block=blk))
+    put(engine.compile_model(mi, block=256, lanes=0))
     base4 = cases.methanol_readme_input("N1"); base4["reaction-rates"] = cases.methanol_kinetics_param(1171.2)
     for m in ("ros4", "rodas4"):
         put(engine.compile_model(base4, method=m))

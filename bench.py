@@ -721,6 +721,35 @@ def run_gpu_arm(args, rank, world, local_rank):
         if e2:
             n2["ensemble"]["ncu"] = dict(e2, calibration_stale=stale2)
         del psw2, sw2, r2g
+        # the stage-pipelined kernel on ensembles that fill its rounds (148 blocks x 64 reactors per GPU): 200 nodes, one
+        # round; 50 nodes, six rounds — what engine.compile_model_n2 picks for these sizes
+        pipe = {}
+        for tag, Bp_, zp_ in (("one_round_200_nodes", 9472, 200), ("50000_x_50_nodes", 50000, 50)):
+            cmp2 = engine.compile_model_n2(mi2, Bp_, zp_)
+            swp = cases.config3_sweep(Bp_, 20240613 + rank)
+            dswp = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in swp.items()}
+            wsp2 = engine.Workspace()
+            engine.n2_solve_ensemble(cmp2, mi2, dswp, Bp_, zNo=zp_, tNo=5, period=0.5, keep_on_device=True, workspace=wsp2)
+            barrier()
+            p0 = torch.cuda.Event(enable_timing=True); p1 = torch.cuda.Event(enable_timing=True)
+            p0.record()
+            rp2 = engine.n2_solve_ensemble(cmp2, mi2, dswp, Bp_, zNo=zp_, tNo=5, period=0.5, keep_on_device=True, workspace=wsp2)
+            p1.record(); torch.cuda.synchronize()
+            sp = max_over_ranks(p0.elapsed_time(p1)*1e-3)
+            attp, okp = sum_over_ranks([float(rp2.stats[3].double().sum().item()), float((rp2.status == 0).sum().item())])
+            ip = cmp2.load(local_rank).info
+            # per attempt and node: f + Jacobian blocks, (s-1) RHS, one LU, s LU solves and the stage combinations
+            linp = (2.0*nn**3)/3.0 + ip.stages*(2.0*nn*nn + 4.0*nn*ip.stages)
+            algp = attp*zp_*(ip.flops_jac_alg + (ip.stages - 1)*ip.flops_rhs_alg + linp)
+            ep, stalep = calibration_for(cal, "rmt_n2_solve_pipeline", cmp2.key())
+            pipe[tag] = {"instances_per_gpu": Bp_, "nodes": zp_, "seconds": sp, "instances_per_s": world*Bp_/sp, "converged": int(okp),
+                         "kernel": "stage pipeline" if cmp2.lanes == 0 else "lanes (%d per reactor)" % cmp2.lanes, "block": cmp2.block,
+                         "node_rhs_evals_per_s": attp*zp_*ip.stages/sp, "fp64_tflops_algorithmic": algp/sp/1e12,
+                         "fp64_frac_of_measured_peak": algp/sp/1e12/fp64_peak/world}
+            if ep and zp_ == 200:
+                pipe[tag]["ncu"] = dict(ep, calibration_stale=stalep)
+            del dswp, wsp2, rp2
+        n2["stage_pipeline"] = pipe
 
     if rank == 0:
         steps = args.steps

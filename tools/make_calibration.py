@@ -40,6 +40,7 @@ KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio"]
+KEEP += ["smsp__sass_thread_inst_executed_op_%s_pred_on.sum.per_cycle_elapsed" % op for op in ("dfma", "dmul", "dadd")] + ["smsp__cycles_elapsed.avg", "smsp__inst_executed.sum"]
 UNIT_SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12,
               "nsecond": 1e-9, "usecond": 1e-6, "msecond": 1e-3, "second": 1.0}
 
@@ -63,6 +64,15 @@ def raw_rows(rep):
     return recs
 
 
+def thread_inst(r, op):
+    """Executed thread instructions of one FP64 opcode: the .sum counter, or (what `--set full` stores) its per-cycle
+    rate times the elapsed SM-sub-partition cycles."""
+    k = "smsp__sass_thread_inst_executed_op_%s_pred_on.sum" % op
+    if k in r:
+        return r[k]
+    return r[k + ".per_cycle_elapsed"]*r["smsp__cycles_elapsed.avg"]
+
+
 def write_summary(recs, path, title):
     with open(path, "w") as f:
         f.write("# %s\n# values in SI units (bytes, seconds); one column per profiled launch\n" % title)
@@ -79,6 +89,7 @@ def main():
     ap.add_argument("--n2"); ap.add_argument("--n2-attempts-per-reactor", type=float)
     ap.add_argument("--instances", type=int, default=1 << 20)
     ap.add_argument("--n2-instances", type=int, default=12500); ap.add_argument("--n2-nodes", type=int, default=200)
+    ap.add_argument("--n2wf"); ap.add_argument("--n2wf-attempts-per-reactor", type=float); ap.add_argument("--n2wf-instances", type=int, default=9472)
     ap.add_argument("--tag", default="r02")
     a = ap.parse_args()
     path = os.path.join(ROOT, "profiles", "%s_calibration.json" % a.tag)
@@ -95,10 +106,10 @@ def main():
         att = a.n1_attempts_per_solve*a.instances
         cal["kernels"]["rmt_n1_solve"] = {
             "module_key": cm1.key(), "source": out, "instances": a.instances, "attempts_per_solve": a.n1_attempts_per_solve,
-            "dfma_per_attempt": r["smsp__sass_thread_inst_executed_op_dfma_pred_on.sum"]/att,
-            "dmul_per_attempt": r["smsp__sass_thread_inst_executed_op_dmul_pred_on.sum"]/att,
-            "dadd_per_attempt": r["smsp__sass_thread_inst_executed_op_dadd_pred_on.sum"]/att,
-            "warp_instructions_per_attempt": r["sm__inst_executed.sum"]*r.get("smsp__thread_inst_executed_per_inst_executed.ratio", 32.0)/att,
+            "dfma_per_attempt": thread_inst(r, "dfma")/att,
+            "dmul_per_attempt": thread_inst(r, "dmul")/att,
+            "dadd_per_attempt": thread_inst(r, "dadd")/att,
+            "warp_instructions_per_attempt": r.get("sm__inst_executed.sum", r.get("smsp__inst_executed.sum"))*r.get("smsp__thread_inst_executed_per_inst_executed.ratio", 32.0)/att,
             "dram_bytes_per_reactor": (r["dram__bytes_read.sum"] + r["dram__bytes_write.sum"])/a.instances,
             "fp64_pipe_busy": r["sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"]/100.0,
             "registers": r["launch__registers_per_thread"], "ncu_duration_s": r["gpu__time_duration.sum"]}
@@ -125,12 +136,34 @@ def main():
         mi2 = cases.methanol_readme_input("N2")
         cm2 = engine.compile_model_n2(mi2, a.n2_instances, a.n2_nodes)
         natt = a.n2_attempts_per_reactor*a.n2_instances*a.n2_nodes
-        fl = 2*r["smsp__sass_thread_inst_executed_op_dfma_pred_on.sum"] + r["smsp__sass_thread_inst_executed_op_dmul_pred_on.sum"] \
-            + r["smsp__sass_thread_inst_executed_op_dadd_pred_on.sum"]
+        fl = 2*thread_inst(r, "dfma") + thread_inst(r, "dmul") \
+            + thread_inst(r, "dadd")
         cal["kernels"]["rmt_n2_solve"] = {
             "module_key": cm2.key(), "source": out, "instances": a.n2_instances, "nodes": a.n2_nodes,
             "attempts_per_reactor": a.n2_attempts_per_reactor,
             "executed_fp64_flop_per_node_attempt": fl/natt,
+            "warp_instructions_per_node_attempt": r.get("sm__inst_executed.sum", r.get("smsp__inst_executed.sum"))*32.0/natt,
+            "dram_bytes_per_launch": r["dram__bytes_read.sum"] + r["dram__bytes_write.sum"],
+            "dram_bytes_per_node_attempt": (r["dram__bytes_read.sum"] + r["dram__bytes_write.sum"])/natt,
+            "fp64_pipe_busy": r["sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"]/100.0,
+            "local_loads": r.get("sass__inst_executed_local_loads"), "local_stores": r.get("sass__inst_executed_local_stores"),
+            "registers": r["launch__registers_per_thread"], "ncu_duration_s": r["gpu__time_duration.sum"]}
+    if a.n2wf:
+        recs = [r for r in raw_rows(a.n2wf) if r["Kernel Name"] == "rmt_n2_solve"]
+        out = os.path.join("profiles", "%s_ncu_n2_solve_pipeline.csv" % a.tag)
+        write_summary(recs, os.path.join(ROOT, out), "rmt_n2_solve (stage pipeline), %d reactors x %d nodes = one full round" % (a.n2wf_instances, a.n2_nodes))
+        r = recs[-1]
+        mi2 = cases.methanol_readme_input("N2")
+        cm2 = engine.compile_model_n2(mi2, a.n2wf_instances, a.n2_nodes)
+        assert cm2.lanes == 0
+        natt = a.n2wf_attempts_per_reactor*a.n2wf_instances*a.n2_nodes
+        fl = 2*thread_inst(r, "dfma") + thread_inst(r, "dmul") \
+            + thread_inst(r, "dadd")
+        cal["kernels"]["rmt_n2_solve_pipeline"] = {
+            "module_key": cm2.key(), "source": out, "instances": a.n2wf_instances, "nodes": a.n2_nodes,
+            "attempts_per_reactor": a.n2wf_attempts_per_reactor,
+            "executed_fp64_flop_per_node_attempt": fl/natt,
+            "warp_instructions_per_node_attempt": r.get("sm__inst_executed.sum", r.get("smsp__inst_executed.sum"))*32.0/natt,
             "dram_bytes_per_launch": r["dram__bytes_read.sum"] + r["dram__bytes_write.sum"],
             "dram_bytes_per_node_attempt": (r["dram__bytes_read.sum"] + r["dram__bytes_write.sum"])/natt,
             "fp64_pipe_busy": r["sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"]/100.0,

@@ -39,5 +39,5 @@ for v in sys.argv[1:]:
     same = np.array_equal(out, ref)
     dev = float(np.nanmax(np.abs(out - ref)/np.abs(ref)))
     print(",".join(defs), end=" ")
-    print("lanes %2d block %3d B=%d zNo=%d: %.4fs ok %d steps %.1f rej %.1f identical %s maxdev %.1e" % (
+    print("lanes %2d block %3d B=%d zNo=%d: %.4fs ok %d steps %.3f rej %.3f identical %s maxdev %.1e" % (
         lanes, blk, B, Z, dt, ok, st[0].mean(), st[1].mean(), same, dev), flush=True)

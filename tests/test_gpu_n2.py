@@ -124,7 +124,7 @@ def test_n2_lanes_per_reactor_give_the_same_solution(n2_settings, case):
     assert engine.n2_lanes(1, 4) == 4
 
 
-@pytest.mark.parametrize("case,zNo", [("methanol", 21), ("ch4", 12), ("methanol", 50)])
+@pytest.mark.parametrize("case,zNo", [("methanol", 21), ("ch4", 12), ("methanol", 50), ("ch4iso", 16)])
 def test_n2_stage_pipeline_kernel_equals_the_lanes_kernel(n2_settings, case, zNo):
     """The stage-pipelined mapping (one thread per reactor and pair of Rosenbrock stages, rmt_kernels.cu "stage
     pipeline") integrates the same method with the same per-node arithmetic as the lanes kernel; only the order of the
@@ -132,7 +132,8 @@ def test_n2_stage_pipeline_kernel_equals_the_lanes_kernel(n2_settings, case, zNo
     equal to <= 1e-9 — with more reactors than one block holds, a partly filled block, a reactor that fails (NaN feed)
     and slots that pick up a second reactor."""
     from rmt_app_b200 import engine
-    mi = cases.methanol_testfile_input("N2") if case == "methanol" else cases.ch4_input("N2")
+    mi = {"methanol": lambda: cases.methanol_testfile_input("N2"), "ch4": lambda: cases.ch4_input("N2"),
+          "ch4iso": lambda: cases.ch4_input("N2", "iso-thermal")}[case]()
     B = 150
     rng = np.random.default_rng(11)
     T0 = mi["operating-conditions"]["temperature"]

@@ -33,7 +33,7 @@ def main(verbose=True):
         put(engine.compile_model_n2(mi, B, z))
     for B, z in ((9472, 200), (100000, 200), (50000, 50)):                # stage-pipelined launch shapes
         put(engine.compile_model_n2(mi, B, z))
-    for mk in (cases.methanol_testfile_input, cases.ch4_input):
+    for mk in (cases.methanol_testfile_input, cases.ch4_input, lambda m: cases.ch4_input(m, "iso-thermal")):
         put(engine.compile_model(mk("N2"), block=256, lanes=0))
     mi = cases.methanol_m9_input()
     for blk in (64, 32):

@@ -62,7 +62,9 @@ typedef struct rmt_module_info {
     int32_t flops_jac_alg, flops_jac_wt;     /* per RHS+Jacobian evaluation    */
     int32_t m;            /* unknowns of the integrator's linear systems: n, or */
                           /* nr + (n - nc) when it works in reaction extents    */
-    int32_t lanes;        /* N2: threads per reactor (nodes handled in parallel)*/
+    int32_t lanes;        /* N2/M9: threads per reactor (nodes handled in        */
+                          /* parallel); 0 = stage-pipelined mapping (one thread */
+                          /* per reactor and pair of Rosenbrock stages)         */
 } rmt_module_info;
 
 const char* rmt_last_error(void);

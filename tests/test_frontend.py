@@ -103,8 +103,10 @@ def test_m9_inputs_and_launch_shape():
     names = spec.input_names()
     assert u[names.index("CaDe")] == 1982 and u[names.index("CaSpHeCa")] == pytest.approx(0.96)
     assert u[names.index("concentration[0]")] == pytest.approx(0.5749, rel=1e-3)        # kmol/m^3, as test_rmt_DME5.py
-    cm = engine.compile_model_n2(mi, 5000, 100)
+    cm = engine.compile_model_n2(mi, 100, 100)          # a few reactors: the lanes kernel, one lane per reactor
     assert cm.lanes == 1 and "#define RMT_MODEL_M9 1" in cm.header and "#define RMT_N2_G 1" in cm.header
+    cp = engine.compile_model_n2(mi, 5000, 100)         # ensembles: the stage pipeline (64 reactors x 4 roles per block)
+    assert cp.lanes == 0 and cp.block == 256 and "#define RMT_N2_G 0" in cp.header
     with pytest.raises(ValueError, match="one lane per reactor"):
         engine.compile_model(mi, lanes=4)
     assert engine.solverSetting["S2"] == {"tNo": 10, "zNo": 100, "rNo": 7, "timesNo": 5}
@@ -119,6 +121,15 @@ def test_launch_shapes_and_pipeline_cuts():
     assert engine.n2_lanes(12500, 200, n=3) == 4 and engine.n2_lanes(12500, 200, n=4) == 8
     assert engine.n2_block(12500, lanes=8) == 64 and engine.n2_block(1, lanes=32) == 32
     assert engine.n2_block(10**6) == 64 and engine.n2_block(5000) == 32 and engine.n2_block(8000) == 64
+    # N2: the stage pipeline takes ensembles that fill its rounds of 148 x 64 reactors, the lanes kernel the rest
+    assert [engine.n2_use_pipeline(B, 200) for B in (500, 2048, 9472, 12500, 18944, 50000, 100000)] == \
+        [False, False, True, False, True, True, True]
+    assert not engine.n2_use_pipeline(9472, 4)
+    mi2 = cases.methanol_readme_input("N2")
+    assert engine.compile_model_n2(mi2, 12500, 200).lanes == 8 and engine.compile_model_n2(mi2, 9472, 200).lanes == 0
+    assert engine.compile_model_n2(mi2, 9472, 200).block == 256
+    with pytest.raises(ValueError):
+        engine.compile_model(mi2, block=64, lanes=3)
     # copy/compute pipeline: chunks cover the ensemble exactly, are non-empty and 1024-aligned inside
     for B in (3*1024, 5000, 1 << 18, (1 << 20) + 7, 10**7):
         cuts = engine.pipeline_cuts(B)

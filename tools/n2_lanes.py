@@ -7,8 +7,11 @@ import cases, torch
 from rmt_app_b200 import engine
 
 B = int(os.environ.get("B", 12500)); Z = int(os.environ.get("Z", 200))
-mi = cases.methanol_readme_input("N2")
+mi = cases.methanol_m9_input() if os.environ.get("MODEL") == "M9" else cases.methanol_readme_input("N2")
+PERIOD = float(os.environ.get("PERIOD", mi["operating-conditions"]["period"] if os.environ.get("MODEL") == "M9" else 0.5))
 sw = cases.config3_sweep(B, 20240613) if B > 1 else None
+if os.environ.get("MODEL") == "M9" and B > 1:       # M9's units differ (kmol/m^3): sweep the feed temperature only
+    sw = {"temperature": 523.0 + np.random.default_rng(7).uniform(-10.0, 10.0, B)}
 ref = None
 for v in sys.argv[1:]:
     parts = v.split(",")
@@ -27,7 +30,7 @@ for v in sys.argv[1:]:
         for rep in range(int(os.environ.get("REPS", 4))):
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
             torch.cuda.synchronize(); e0.record()
-            res = engine.n2_solve_ensemble(cm, mi, dsw, B, zNo=Z, tNo=5, period=0.5, keep_on_device=True, workspace=ws)
+            res = engine.n2_solve_ensemble(cm, mi, dsw, B, zNo=Z, tNo=5, period=PERIOD, keep_on_device=True, workspace=ws)
             e1.record(); torch.cuda.synchronize(); dts.append(e0.elapsed_time(e1)*1e-3)
         dt = min(dts[1:]) if len(dts) > 1 else dts[0]
     except Exception as e:

@@ -201,20 +201,44 @@ def n2_lanes(B, zNo, sm_count=148, n=7):
 
 # Stage-pipelined N2 kernel (lanes = 0, rmt_kernels.cu "stage pipeline"): a block serves 64 reactors — two warps per
 # role, roles = Jacobian | stages 1-2 (+ LU) | stages 3-4 | stages 5-6 — one block per SM, so an ensemble is worked off in
-# rounds of sm_count*64 reactors.  Measured on one B200 (200 nodes): a full round of 9 472 reactors takes 0.081 s where
-# the lanes kernel needs 0.094 s; 50 000 x 50 nodes 0.103 vs 0.131 s; 12 500 x 200 (1.32 rounds) 0.147 vs 0.126 s.
+# rounds of sm_count*64 = 9 472 reactors; the lanes kernel (8 lanes per reactor, 592 resident blocks of 8 reactors) has
+# rounds of 4 736.  Which one is faster depends on how the ensemble fills those rounds, so the choice is made from the
+# measured times of both (one B200, methanol model, 200 nodes, period 0.5 s; tools/n2_lanes.py, gpurun_out s15 sweep):
 N2_PIPELINE_REACTORS_PER_BLOCK = 64
 N2_PIPELINE_MIN_B = 2048
+_N2_T_LANES = ((1024, .0335), (2048, .0368), (3072, .0435), (4096, .0466), (6144, .0789), (8192, .0831), (9472, .0940),
+               (11000, .1147), (12500, .1215), (14000, .1278), (16000, .1524), (18944, .1674), (22000, .1979), (28416, .2452))
+_N2_T_PIPE = ((1024, .0684), (2048, .0724), (4096, .0743), (6144, .0748), (8192, .0785), (9472, .0806), (11000, .1331),
+              (14000, .1425), (16000, .1463), (18944, .1543), (22000, .2031), (28416, .2230))
+
+
+def _interp(table, x):
+    xs, ys = zip(*table)
+    return float(np.interp(x, xs, ys))
+
+
+def n2_kernel_costs(B, zNo, sm_count=148):
+    """(lanes kernel, stage pipeline): estimated seconds for B reactors x zNo nodes, interpolated from the measured
+    table above and continued beyond it (lanes: 8.63 us per reactor; pipeline: 74.5 ms per full round of 9 472 plus
+    50 + 28*fill ms for a partly filled one), scaled with the node count.  Short grids favour the pipeline a little
+    more than the scaling says (50 000 x 50 nodes: 0.100 vs 0.131 s measured)."""
+    per_round = sm_count*N2_PIPELINE_REACTORS_PER_BLOCK
+    if B <= _N2_T_LANES[-1][0]:
+        tl, tp = _interp(_N2_T_LANES, B), _interp(_N2_T_PIPE, B)
+    else:
+        full, frac = divmod(B/per_round, 1.0)
+        tl = B*8.63e-6
+        tp = 0.0745*full + ((0.050 + 0.028*frac) if frac > 0 else 0.0)
+    scale = zNo/200.0
+    return tl*scale, tp*scale*(0.85 if zNo <= 100 else 1.0)
 
 
 def n2_use_pipeline(B, zNo, sm_count=148):
-    """Stage pipeline or lanes kernel?  The pipeline costs ~0.87 of the lanes kernel per reactor when its rounds are
-    full; a partly filled last round costs a full one."""
+    """Stage pipeline or lanes kernel for an N2 ensemble?  (M9: see compile_model_n2.)"""
     if B < N2_PIPELINE_MIN_B or zNo < 8:
         return False
-    per_round = sm_count*N2_PIPELINE_REACTORS_PER_BLOCK
-    rounds = -(-B//per_round)
-    return rounds*per_round*0.87 <= B*1.0
+    tl, tp = n2_kernel_costs(B, zNo, sm_count)
+    return tp < tl
 
 
 def n2_block(B, sm_count=148, lanes=1):

@@ -30,10 +30,16 @@ for lanes, block in ((1, 64), (4, 32), (8, 64), (32, 32)):
     c2 = engine.compile_model(cases.methanol_testfile_input("N2"), block=block, lanes=lanes)
     q = engine.n2_solve_ensemble(c2, cases.methanol_testfile_input("N2"), None, 1, zNo=21, tNo=2, period=0.05)
     assert q.status[0] == 0
+c3 = engine.compile_model(cases.methanol_testfile_input("N2"), block=256, lanes=0)      # stage pipeline: 64 reactors x 4 roles per block
+q = engine.n2_solve_ensemble(c3, cases.methanol_testfile_input("N2"), {"temperature": np.linspace(500, 540, 70)}, 70, zNo=21, tNo=2, period=0.05)
+assert (q.status == 0).all()
 print("N2 ok")
 old = dict(solverSetting["S2"]); solverSetting["S2"].update(zNo=12, tNo=2)
 m9 = cases.methanol_m9_input(period=0.2)
 rmtExe(m9)
 rmtExeBatchN2(m9, {"temperature": np.array([523.0, 527.0, 531.0])})
 solverSetting["S2"].update(old)
+c9 = engine.compile_model(m9, block=256, lanes=0)
+q = engine.n2_solve_ensemble(c9, m9, {"temperature": np.linspace(520.0, 530.0, 40)}, 40, zNo=12, tNo=2, period=0.2)
+assert (q.status == 0).all()
 print("M9 ok")

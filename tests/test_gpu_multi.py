@@ -1,4 +1,5 @@
-"""Multi-GPU path (needs >= 2 GPUs; skipped otherwise): sharded population + NCCL reduction/gather."""
+"""Multi-GPU path (needs >= 2 GPUs; skipped otherwise): sharded population + NCCL reduction/gather through torch.distributed
+and through rmt_comm_*, sharded dynamic ensemble."""
 import json
 import os
 import subprocess
@@ -23,7 +24,10 @@ def test_sharded_population_matches_unsharded():
     p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     line = [ln for ln in p.stdout.splitlines() if ln.startswith("{")][-1]
-    assert json.loads(line)["ok"] is True
+    res = json.loads(line)
+    # population through torch.distributed, the same through the C ABI's own NCCL transport (rmt_comm_*), and a sharded
+    # dynamic ensemble with the packed gather of the final profiles
+    assert res["ok"] is True and res["ok_population"] and res["ok_rmt_comm_transport"] and res["ok_n2_sharded"], res
 
 
 def test_single_process_sharded_api_equals_batch_api():

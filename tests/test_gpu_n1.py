@@ -357,6 +357,23 @@ def test_branch_free_device_math_accuracy():
         assert relerr(o[3], np.power(10.0, xs), m10) < 4*ulp
         nz = (np.abs(xs) > 1e-290) & (np.abs(xs) < 1e290)
         assert relerr(o[4], 1.0/xs, nz) < 2*ulp
+    # special values: what the branch-free versions do with them is part of the contract (DESIGN.md section 6;
+    # solver-config["exact-math"] restores IEEE semantics).  exp / 10^x saturate at e^+-708 / 10^+-307 and swallow NaN; log
+    # is NaN outside the positive normal range (NaN, +-Inf, +-0, subnormals); sqrt keeps +-0 and +-Inf, gives NaN for NaN,
+    # negative and subnormal arguments; the refined reciprocal of 0, Inf, NaN or a subnormal is NaN.  A non-finite value
+    # makes the error test reject the step and ends in status 3 — never in a silent wrong answer; what the saturating exp
+    # can hide is an overflow the reference would have turned into 0 or Inf (test_exact_math_option_gives_ieee_special_values).
+    sp = np.array([np.nan, np.inf, -np.inf, 0.0, -0.0, 5e-324, 1e-310, 800.0, -800.0])
+    d_s = torch.from_numpy(sp).cuda()
+    d_q = torch.empty((5, sp.size), dtype=torch.float64, device="cuda")
+    mod.math_probe(sp.size, d_s, d_q, stream=torch.cuda.current_stream().cuda_stream)
+    ex, lg_, sq, e10, rc = d_q.cpu().numpy()
+    assert np.isfinite(ex).all() and ex[0] > 1e307 and ex[1] > 1e307 and ex[7] > 1e307 and 0 < ex[2] < 1e-307 and 0 < ex[8] < 1e-307
+    assert (ex[3:7] == 1.0).all() and np.isfinite(e10).all() and e10[7] == 1e307 and e10[8] == 1e-307
+    assert np.isnan(lg_[:7]).all() and np.isnan(lg_[8]) and abs(lg_[7] - np.log(800.0)) < 1e-14
+    assert np.isnan(sq[0]) and sq[1] == np.inf and sq[2] == -np.inf and sq[3] == 0.0 and sq[4] == 0.0
+    assert np.isnan(sq[5]) and np.isnan(sq[6]) and np.isnan(sq[8]) and abs(sq[7] - np.sqrt(800.0)) < 1e-14
+    assert np.isnan(rc[:7]).all() and rc[7] == 1.0/800.0 and rc[8] == -1.0/800.0
 
 
 def _with_inert(mi, sym="CO"):

@@ -147,3 +147,34 @@ def test_pack_layout_single_rank_and_tail_folding():
     np.testing.assert_array_equal(fst, [0, 1, 0, 2, 0])
     assert ensemble.fold_tails(tails) == (3.0, 0.5, 4, 2)
     assert ensemble.fold_tails([[0.0, np.inf, -1.0, 0.0], [2.0, 1.0, 9.0, 1.0], [2.5, 1.0, 7.0, 0.0]]) == (4.5, 1.0, 7, 1)
+
+
+def test_device_unpack_equals_host_unpack(monkeypatch):
+    """PackLayout.unpack_device (scatter + transpose by tensor copies, one D2H into pinned workspace memory) against the
+    host-side unpack on the same gathered buffer — equal shards (one strided copy) and uneven ones (per-rank copies),
+    instance-major and row-major.  CPU tensors stand in for the device here; the stream synchronisation is stubbed."""
+    import torch
+    from rmt_app_b200.ensemble import PackLayout
+
+    class _Ws:
+        def get(self, name, shape, dtype, device=None, pinned=False):
+            return torch.empty(shape, dtype=dtype)
+
+    class _Stream:
+        def synchronize(self):
+            pass
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda dev=None: _Stream())
+    rng = np.random.default_rng(0)
+    for B, world, nrows in ((64, 4, 3), (66, 4, 3), (35, 5, 2), (40, 8, 9), (3, 4, 2)):
+        lay = PackLayout(B, world, nrows)
+        g = torch.zeros((world, lay.length), dtype=torch.float64)
+        for r in range(world):
+            rows, st, tail = lay.views(g[r], r)
+            rows.copy_(torch.from_numpy(rng.normal(size=tuple(rows.shape))))
+            st.copy_(torch.from_numpy(rng.integers(0, 4, st.shape[0]).astype(np.int32)))
+            tail.copy_(torch.tensor([1.0 + r, 2.0, 3.0, float(r)]))
+        full, status, tails = lay.unpack(g.numpy())
+        a, b, c = lay.unpack_device(g, _Ws(), transpose=True)
+        assert np.array_equal(a, full.T) and np.array_equal(b, status) and np.array_equal(c, tails)
+        a, b, c = lay.unpack_device(g, _Ws(), transpose=False)
+        assert np.array_equal(a, full) and np.array_equal(b, status)

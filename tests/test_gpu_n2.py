@@ -129,8 +129,8 @@ def test_n2_stage_pipeline_kernel_equals_the_lanes_kernel(n2_settings, case, zNo
     """The stage-pipelined mapping (one thread per reactor and pair of Rosenbrock stages, rmt_kernels.cu "stage
     pipeline") integrates the same method with the same per-node arithmetic as the lanes kernel; only the order of the
     linear algebra differs (LU solves instead of products with the explicit inverse blocks): same step sequence, states
-    equal to <= 1e-9 — with more reactors than one block holds, a partly filled block, a reactor that fails (NaN feed)
-    and slots that pick up a second reactor."""
+    equal to <= 1e-9 — with more reactors than one block holds, a partly filled block and a reactor that fails (NaN
+    feed)."""
     from rmt_app_b200 import engine
     mi = {"methanol": lambda: cases.methanol_testfile_input("N2"), "ch4": lambda: cases.ch4_input("N2"),
           "ch4iso": lambda: cases.ch4_input("N2", "iso-thermal")}[case]()
@@ -157,6 +157,26 @@ def test_n2_stage_pipeline_kernel_equals_the_lanes_kernel(n2_settings, case, zNo
     # the launch-shape policy: full rounds of 148 x 64 reactors go to the pipeline, small or badly filling ensembles do not
     assert engine.n2_use_pipeline(9472, 200) and engine.n2_use_pipeline(100000, 200)
     assert not engine.n2_use_pipeline(12500, 200) and not engine.n2_use_pipeline(500, 200) and not engine.n2_use_pipeline(9472, 4)
+
+
+def test_n2_stage_pipeline_lanes_pick_up_further_reactors(n2_settings):
+    """More reactors than the resident blocks have lanes (148 x 64 = 9 472): lanes that finish draw the next reactor from
+    the queue while their neighbours are still integrating — new instance, pending slab output of the old one and the norm
+    pass of the new one in the same block step.  Every reactor must come out as from the lanes kernel."""
+    from rmt_app_b200 import engine
+    mi = cases.ch4_input("N2")
+    B, zNo = 9472 + 777, 12
+    rng = np.random.default_rng(5)
+    sw = {"temperature": rng.uniform(900.0, 1000.0, B), "k0": 7.2e-4*rng.uniform(0.5, 2.0, B)}
+    lanes = engine.compile_model(mi, block=64, lanes=8)
+    pipe = engine.compile_model(mi, block=256, lanes=0)
+    a = engine.n2_solve_ensemble(lanes, mi, sw, B, zNo=zNo, tNo=3, period=5.0, keep_on_device=True)
+    oa, sa, ta = a.out.clone(), a.status.clone(), a.stats.clone()
+    b = engine.n2_solve_ensemble(pipe, mi, sw, B, zNo=zNo, tNo=3, period=5.0, keep_on_device=True)
+    assert bool((sa == 0).all()) and bool((b.status == 0).all())
+    assert bool((ta == b.stats).all())
+    rel = ((b.out - oa).abs()/oa.abs()).max().item()
+    assert rel < 1e-9, rel
 
 
 def test_n2_stage_pipeline_kernel_against_the_converged_oracle(n2_settings):

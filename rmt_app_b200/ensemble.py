@@ -85,28 +85,18 @@ class PackLayout:
         shape = (self.B, self.nrows) if transpose else (self.nrows, self.B)
         d_rows = ws.get("d_unpack_rows", shape, torch.float64, device=dev)
         d_st = ws.get("d_unpack_status", (self.B,), torch.int32, device=dev)
-        Br0 = self.sizes[0] if self.sizes else 0
-        if Br0 > 0 and all(b == Br0 for b in self.sizes):
-            # equal shards (the usual case): one strided copy for the rows, one for the status words
-            blk = g[:, :self.nrows*Br0].view(self.world, self.nrows, Br0)
+        # (one 2-D transposing copy per rank: a single batched permute-copy over all ranks was measured 5x slower — torch's
+        # strided-copy kernel writes 9-double rows uncoalesced — 11 ms instead of 2.2 ms per 65 536-set population)
+        for r in range(self.world):
+            Br, lo = self.sizes[r], self.starts[r]
+            if Br == 0:
+                continue
+            blk = g[r, :self.nrows*Br].view(self.nrows, Br)
             if transpose:
-                d_rows.view(self.world, Br0, self.nrows).copy_(blk.permute(0, 2, 1))
+                d_rows[lo:lo + Br].copy_(blk.t())
             else:
-                d_rows.view(self.nrows, self.world, Br0).copy_(blk.permute(1, 0, 2))
-            nst = (Br0 + 1)//2
-            st = g[:, self.nrows*Br0:self.nrows*Br0 + nst].contiguous().view(torch.int32).view(self.world, 2*nst)[:, :Br0]
-            d_st.view(self.world, Br0).copy_(st)
-        else:
-            for r in range(self.world):
-                Br, lo = self.sizes[r], self.starts[r]
-                if Br == 0:
-                    continue
-                blk = g[r, :self.nrows*Br].view(self.nrows, Br)
-                if transpose:
-                    d_rows[lo:lo + Br].copy_(blk.t())
-                else:
-                    d_rows[:, lo:lo + Br].copy_(blk)
-                d_st[lo:lo + Br].copy_(g[r, self.nrows*Br:self.nrows*Br + (Br + 1)//2].view(torch.int32)[:Br])
+                d_rows[:, lo:lo + Br].copy_(blk)
+            d_st[lo:lo + Br].copy_(g[r, self.nrows*Br:self.nrows*Br + (Br + 1)//2].view(torch.int32)[:Br])
         h_rows = ws.get("h_unpack_rows", shape, torch.float64, pinned=True)
         h_st = ws.get("h_unpack_status", (self.B,), torch.int32, pinned=True)
         h_tail = ws.get("h_unpack_tails", (self.world, self.TAIL), torch.float64, pinned=True)

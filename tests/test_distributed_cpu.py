@@ -151,7 +151,7 @@ def test_pack_layout_single_rank_and_tail_folding():
 
 def test_device_unpack_equals_host_unpack(monkeypatch):
     """PackLayout.unpack_device (scatter + transpose by tensor copies, one D2H into pinned workspace memory) against the
-    host-side unpack on the same gathered buffer — equal shards (one strided copy) and uneven ones (per-rank copies),
+    host-side unpack on the same gathered buffer — equal and uneven shards, a rank without reactors,
     instance-major and row-major.  CPU tensors stand in for the device here; the stream synchronisation is stubbed."""
     import torch
     from rmt_app_b200.ensemble import PackLayout
